@@ -1,0 +1,186 @@
+/*
+ * oramacore_b200.h — C ABI of the B200-native OramaCore search hot path.
+ *
+ * The reference (oramasearch/oramacore @ 666ab48) has no plugin / FFI boundary for this
+ * path: the seam is Rust-to-Rust.  Each entry point below names the
+ * reference interface it replaces (file:line relative to the reference root).  Plain
+ * pointers and sizes only; all `out_*` buffers are caller-allocated HOST memory; the
+ * library owns every device allocation behind the opaque handles.  The shared library
+ * (liboramacore_b200.so) is CUDA-only: there is no CPU fallback, every call fails with
+ * OC_ERR_CUDA when no sm_100-class device is usable.
+ *
+ * Status: 0 = OC_OK, <0 = error; text via oc_last_error() (thread-local, valid until the
+ * next call on that thread).  Handles are Send+Sync: calls on one ctx are serialised
+ * internally (one stream per ctx); different ctxs run concurrently.
+ */
+#ifndef ORAMACORE_B200_H
+#define ORAMACORE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OC_OK 0
+#define OC_ERR_INVALID (-1)     /* bad argument / shape                                   */
+#define OC_ERR_CUDA (-2)        /* CUDA runtime failure (incl. "no device")               */
+#define OC_ERR_OOM (-3)         /* device or host allocation failed                       */
+#define OC_ERR_UNSUPPORTED (-4) /* e.g. limit+offset > OC_MAX_TOPK                        */
+#define OC_ERR_COMM (-5)        /* NCCL failure / libnccl not loadable                    */
+
+#define OC_MAX_TOPK 1024u       /* max limit+offset handled on device                     */
+#define OC_MAX_TOKENS 32u       /* u32 token bitmask, token_score.rs:293                  */
+
+#define OC_MODE_FULLTEXT 0      /* ScoreMode::FullText | Default, token_score.rs:472-484  */
+#define OC_MODE_VECTOR 1        /* ScoreMode::Vector,             token_score.rs:485-494  */
+#define OC_MODE_HYBRID 2        /* ScoreMode::Hybrid,             token_score.rs:495-503  */
+
+#define OC_DTYPE_F32 0
+#define OC_DTYPE_BF16 1         /* storage extension (reference stores f32, embedding_field.rs:232) */
+
+typedef struct oc_ctx oc_ctx;   /* one device + stream + workspace (one per process/GPU)  */
+typedef struct oc_emb oc_emb;   /* == one EmbeddingFieldStorage (embedding_field.rs:29-34) */
+typedef struct oc_str oc_str;   /* == the StringFieldStorage set of one Index (string_field.rs:32-36) */
+
+const char *oc_last_error(void);
+int oc_version(void);
+/* sizeof of {oc_search_params, oc_timing, oc_emb_info_t, oc_str_info_t} as compiled: lets a
+ * binding (Rust repr(C), ctypes) verify its mirror of the structs at load time. */
+void oc_abi_sizes(size_t out[4]);
+
+/* ---- context ------------------------------------------------------------------------ */
+/* Replaces nothing in the reference (it has no device); one ctx per GPU, one process per GPU. */
+int oc_init(int device_id, oc_ctx **out);
+void oc_shutdown(oc_ctx *ctx);
+/* Number of SMs / device name, for bench reporting. */
+int oc_device_info(oc_ctx *ctx, int *sm_count, size_t *hbm_bytes, char *name, size_t name_cap);
+
+/* Document-sharded multi-GPU (no reference analogue — the reference is
+ * single-node).  Rank 0 creates the id, the host runtime broadcasts it, every rank joins.
+ * After oc_comm_init, oc_search with params.sharded=1 all-gathers per-shard top-k over
+ * NCCL/NVLink and merges on device; every rank receives the global answer. */
+#define OC_COMM_ID_BYTES 128
+int oc_comm_unique_id(uint8_t out_id[OC_COMM_ID_BYTES]);
+int oc_comm_init(oc_ctx *ctx, int world_size, int rank, const uint8_t id[OC_COMM_ID_BYTES]);
+
+/* ---- embedding store ------------------------------------------------------------------
+ * EmbeddingFieldStorage::new (embedding_field.rs:64-78): metric fixed = cosine;
+ * rescale_e5 = Model::rescale_score for the E5 family (python/embeddings.rs:71-92). */
+int oc_emb_create(oc_ctx *ctx, uint32_t dim, int dtype, int rescale_e5, oc_emb **out);
+void oc_emb_destroy(oc_emb *emb);
+int oc_emb_reserve(oc_emb *emb, uint64_t n_rows);
+/* EmbeddingFieldStorage::insert(DocumentId, Vec<Vec<f32>>) (embedding_field.rs:232-237),
+ * batched: n vectors, doc_ids[i] may repeat (several chunks per document). rows = n x dim
+ * row-major in the store's dtype, host memory. */
+int oc_emb_insert(oc_emb *emb, const uint64_t *doc_ids, const void *rows, uint64_t n);
+/* EmbeddingFieldStorage::delete (embedding_field.rs:240-242). */
+int oc_emb_delete(oc_emb *emb, const uint64_t *doc_ids, uint64_t n);
+
+typedef struct {
+    uint64_t num_embeddings;  /* live vectors,   info().num_embeddings (embedding_field.rs:303-310) */
+    uint64_t num_rows;        /* incl. tombstones */
+    uint32_t dimensions;
+    int dtype;
+    uint64_t device_bytes;
+} oc_emb_info_t;
+int oc_emb_info(oc_emb *emb, oc_emb_info_t *out);
+
+/* EmbeddingFieldStorage::search (embedding_field.rs:250-278) for B targets at once:
+ * exact top-`limit` by cosine distance (== storage.search(target, limit, None) :255-266),
+ * then similarity = 1 - distance, rescale, keep score >= similarity (:268-276).
+ * filter_bits: NULL or a bitmap over DocumentId (FilterResult::contains, :54-61).
+ * out_doc_ids/out_scores: B x limit, best first; out_counts[b] = hits kept (<= limit). */
+int oc_emb_search(oc_emb *emb, const float *queries, uint32_t B, uint32_t limit, float similarity,
+                  const uint64_t *filter_bits, uint64_t filter_nbits, uint64_t *out_doc_ids,
+                  float *out_scores, uint32_t *out_counts);
+
+/* ---- string (BM25F) store --------------------------------------------------------------
+ * One oc_str holds all string fields of an Index over a shared row space
+ * (row -> DocumentId).  Committed postings are handed over in CSR per field — what
+ * StringFieldStorage::insert(DocumentId, IndexedValue{field_length:u16, terms}) accumulates
+ * and compact() lays out (string_field.rs:155-177, 186-191). */
+int oc_str_create(oc_ctx *ctx, uint32_t n_fields, oc_str **out);
+void oc_str_destroy(oc_str *s);
+/* row_doc_ids: NULL => DocumentId == row; must be ascending. document_count = N for idf
+ * (Index::document_count, token_score.rs:221) — GLOBAL when sharded. */
+int oc_str_set_rows(oc_str *s, uint64_t n_rows, const uint64_t *row_doc_ids, uint64_t document_count);
+/* Postings of one field: term t owns [term_offsets[t], term_offsets[t+1]); rows ascending,
+ * unique per term. avg_field_len = info().avg_field_length (string_field.rs:228-235),
+ * global when sharded. global_df: NULL, or per-term corpus df across all shards. */
+int oc_str_load_field(oc_str *s, uint32_t field, float avg_field_len, uint32_t n_terms,
+                      const uint64_t *term_offsets, const uint32_t *post_row, const uint16_t *post_tf,
+                      const uint16_t *post_len, const uint32_t *global_df);
+/* StringFieldStorage::delete (string_field.rs:180-182): tombstones rows until the next load. */
+int oc_str_delete(oc_str *s, const uint64_t *doc_ids, uint64_t n);
+
+typedef struct {
+    uint64_t total_documents;  /* rows                              */
+    uint64_t total_postings;
+    uint64_t unique_terms_count;
+    uint32_t n_fields;
+    uint64_t device_bytes;
+} oc_str_info_t;
+int oc_str_info(oc_str *s, oc_str_info_t *out);
+
+/* ---- search() ---------------------------------------------------------------------------
+ * TokenScoreContext::execute (token_score.rs:460-509) + apply_omc_multipliers
+ * (search.rs:39-48) + count (search.rs:482) + sort_token_scores/top_n (sort.rs:17-46,
+ * 260-279) + skip(offset).take(limit) (search.rs:494-498), for a batch of B queries.
+ *
+ * Query text is resolved to index terms on the host (tokenise+stem token_score.rs:196-209;
+ * prefix/Levenshtein expansion inside StringStorage); the ABI takes, per query, its tokens,
+ * and per token the expanded (field, term id, weight) list, weight = field boost x
+ * exact-match factor (the "ntf already includes boost" contract, token_score.rs:180-185). */
+typedef struct {
+    int mode;                          /* OC_MODE_*                                         */
+    uint32_t n_queries;                /* B                                                  */
+    uint32_t limit, offset;            /* Limit / SearchOffset (types.rs:747-756)            */
+    float similarity;                  /* Similarity (types.rs:878-901); vector & hybrid     */
+    float threshold;                   /* Threshold (types.rs:859-876); < 0 => None          */
+    float bm25_k, bm25_b;              /* 1.2 / 0.75 (token_score.rs:283; bm25.rs:56-63)     */
+    const float *q_vecs;               /* B x dim fp32 (vector, hybrid) or NULL              */
+    const uint32_t *q_token_offsets;   /* B+1 (fulltext, hybrid) or NULL                     */
+    const uint32_t *token_term_offsets;/* n_tokens+1                                         */
+    const uint32_t *term_field;        /* per expanded term                                  */
+    const uint32_t *term_id;
+    const float *term_weight;
+    const uint64_t *filter_bits;       /* NULL or bitmap over DocumentId                     */
+    uint64_t filter_nbits;
+    const uint64_t *omc_doc_ids;       /* OMC multipliers sorted by doc id (index/mod.rs:1720-1739) */
+    const float *omc_mult;
+    uint64_t n_omc;
+    int sharded;                       /* 1 => all-gather + merge across oc_comm ranks       */
+} oc_search_params;
+
+/* out_doc_ids/out_scores: B x limit (best first, after offset); out_n[b] hits written;
+ * out_count[b] = all matching documents. emb may be NULL for fulltext, str NULL for vector. */
+int oc_search(oc_ctx *ctx, oc_emb *emb, oc_str *str, const oc_search_params *p,
+              uint64_t *out_doc_ids, float *out_scores, uint32_t *out_n, uint64_t *out_count);
+
+/* ---- measurement ------------------------------------------------------------------------
+ * CUDA-event timings (ms, on the ctx stream) of the last oc_search / oc_emb_search on this
+ * ctx, and launch counts. */
+typedef struct {
+    float h2d_ms;        /* query / term / filter upload                                   */
+    float device_ms;     /* all kernels of the call (inputs resident)                      */
+    float d2h_ms;        /* result download                                                */
+    float scan_ms;       /* embedding scan kernel(s) only                                  */
+    float bm25_ms;       /* posting-list scorer kernel(s) only                             */
+    float fuse_ms;       /* merge / fusion / top-k kernel(s)                               */
+    float comm_ms;       /* all-gather + cross-shard merge                                 */
+    uint32_t kernel_launches;
+    uint32_t scan_launches;
+    uint64_t scan_bytes;     /* algorithmic bytes swept by the scan kernels (rows x stride x elem) */
+    uint64_t bm25_postings;  /* postings walked by the scorer (x8 B = algorithmic bytes)    */
+    uint64_t h2d_bytes, d2h_bytes;
+} oc_timing;
+int oc_last_timing(oc_ctx *ctx, oc_timing *out);
+/* Total kernels this library has launched on ctx since oc_init. */
+uint64_t oc_launch_count(oc_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,13 @@
+"""oramacore_b200 — B200-native (sm_100a) implementation of OramaCore's search hot path:
+embedding scan + BM25F posting scorer + hybrid fusion/top-k behind the reference's
+search() surface (mode = fulltext | vector | hybrid).  CUDA only; no CPU fallback."""
+from .types import (FieldPostings, StringIndexData, TextQuery, SearchHits, MODE_FULLTEXT, MODE_VECTOR,
+                    MODE_HYBRID, BM25_B, BM25_K)
+from ._lib import OcError, build, lib, SO_PATH
+from .engine import (Context, EmbeddingFieldStorage, StringFieldStorage, TokenScoreContext, TokenScoreParams,
+                     VectorSearchParams, search)
+
+__all__ = ["FieldPostings", "StringIndexData", "TextQuery", "SearchHits", "MODE_FULLTEXT", "MODE_VECTOR",
+           "MODE_HYBRID", "BM25_B", "BM25_K", "OcError", "build", "lib", "SO_PATH", "Context",
+           "EmbeddingFieldStorage", "StringFieldStorage", "TokenScoreContext", "TokenScoreParams",
+           "VectorSearchParams", "search"]

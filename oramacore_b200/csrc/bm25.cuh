@@ -1,0 +1,384 @@
+// bm25.cuh — K3: BM25F posting-list scorer over device-resident postings.
+//
+// Replaces, for a batch of queries, the hot loops of search_full_text
+// (read/index/token_score.rs:186-303): the external
+// StringStorage::collect_contributions posting walk (string_field.rs:208-225), the
+// per-token corpus_df / add_precomputed_field accumulation (token_score.rs:257-276) and
+// BM25Scorer::finalize_term / get_scores (bm25.rs:369-428, 484-524).
+//
+// Design (HBM-bound, postings read exactly once per (query, term)):
+//   * the document-row space is cut into tiles of TILE rows; one CTA scores one
+//     (query, tile) pair entirely in shared memory: score[TILE] (+ S[TILE] when a token
+//     expands to several index terms, + mask[TILE] in threshold mode), so there is no
+//     accumulator traffic to HBM and no atomics (rows are unique inside a posting list and
+//     terms are processed one after another between barriers);
+//   * a plan kernel binary-searches, once per batch, the posting sub-range of every
+//     (expanded term, tile) pair;
+//   * after accumulation the tile is scanned once: matched-doc count, pre-OMC min/max,
+//     and threshold-gated insertion (against a per-query global threshold tau that earlier
+//     tiles raise with atomicMax) into a small top-n buffer that is compressed by a
+//     bitonic sort only when it overflows;
+//   * arithmetic uses explicit round-to-nearest intrinsics in the reference's operation
+//     order (no FMA contraction), idf is computed on the host with the same libm as the
+//     oracle, so BM25 scores are bit-identical to the CPU restatement.
+//
+// Algorithmic bytes: 8 B per posting walked (u32 row, u16 tf, u16 field_len).
+#pragma once
+#include "oc_common.cuh"
+
+namespace oc {
+
+constexpr uint32_t BM25_TILE = 16384;          // rows per tile
+constexpr uint32_t BM25_THREADS = 256;
+constexpr uint32_t BM25_CHUNK = BM25_THREADS * 4;
+
+struct Posting {       // 8 bytes
+    uint32_t row;
+    uint16_t tf, len;
+};
+
+struct TermDesc {      // one expanded index term of one token of one query
+    const Posting *ptr;    // first posting of the term (device)
+    uint32_t len;          // postings in the list (rows unique, ascending)
+    float weight;          // field boost x exact-match factor
+    float avg_len;         // the field's avg_field_length
+    uint32_t pad;
+};
+
+struct TokenDesc {
+    uint32_t term_begin, term_end;  // into TermDesc[]
+    float idf;                      // host-computed (libm log1pf), bm25.rs:78-82
+    uint32_t bit;                   // 1 << (token_index & 31), token_score.rs:293
+};
+
+struct QueryDesc {
+    uint32_t token_begin, token_end;  // into TokenDesc[]
+    uint32_t required;                // floor(n_tokens * threshold), token_score.rs:211-218
+    uint32_t flags;                   // bit0: threshold mode; bit1: some token has != 1 terms
+};
+constexpr uint32_t QF_THRESHOLD = 1u, QF_MULTI = 2u;
+
+// ---- plan: seg[e][t] = first posting of term e with row >= t*TILE (relative to begin) ----
+__global__ void bm25_plan_kernel(const TermDesc *terms, uint32_t n_terms, uint32_t n_tiles, uint32_t *seg) {
+    const uint64_t gid = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const uint64_t per = uint64_t(n_tiles) + 1;
+    if (gid >= uint64_t(n_terms) * per) return;
+    const uint32_t e = uint32_t(gid / per), t = uint32_t(gid % per);
+    const TermDesc td = terms[e];
+    const uint64_t len = td.len;
+    if (t == n_tiles) { seg[gid] = uint32_t(len); return; }
+    const uint64_t target = uint64_t(t) * BM25_TILE;
+    uint64_t lo = 0, hi = len;
+    const Posting *pp = td.ptr;
+    while (lo < hi) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if (uint64_t(pp[mid].row) < target) lo = mid + 1; else hi = mid;
+    }
+    seg[gid] = uint32_t(lo);
+}
+
+// bm25.rs:99-110 with the boost baked in (token_score.rs:180-185):
+//   ntf = w * (tf / (1 - b + b * (len / avglen)))   — every op rounded separately.
+__device__ __forceinline__ float bm25_ntf(uint32_t tf, uint32_t len, float avg, float b, float one_minus_b,
+                                          float w) {
+    const float r = __fdiv_rn(float(len), avg);
+    const float den = __fadd_rn(one_minus_b, __fmul_rn(b, r));
+    return __fmul_rn(w, __fdiv_rn(float(tf), den));
+}
+// bm25.rs:124-126: idf * (k + 1) * S / (k + S)
+__device__ __forceinline__ float bm25_sat(float S, float k, float kp1, float idf) {
+    return __fdiv_rn(__fmul_rn(__fmul_rn(idf, kp1), S), __fadd_rn(k, S));
+}
+__device__ __forceinline__ bool f32_is_normal(float x) {
+    const uint32_t e = (__float_as_uint(x) >> 23) & 0xffu;
+    return e != 0u && e != 0xffu;
+}
+
+struct Bm25Params {
+    const TermDesc *terms;
+    const TokenDesc *tokens;
+    const QueryDesc *queries;
+    const uint32_t *seg;          // [n_term_desc][n_tiles+1]
+    uint32_t n_queries, n_tiles;
+    uint64_t n_rows;
+    float k, b;
+    const uint32_t *row_ok_bits;  // NULL or bitmap over rows (alive AND filter)
+    // OMC (search.rs:39-48), sorted by row
+    const uint32_t *omc_row;
+    const float *omc_mult;
+    uint32_t n_omc;
+    // hybrid: vector hits mapped to string rows, [n_queries][v_stride]; 0xffffffff = none
+    const uint32_t *v_row;
+    uint32_t v_stride;
+    float *v_ft;                  // out: fulltext score of each vector hit (0 if absent)
+    uint8_t *v_present;           // out: 1 if the hit's doc is in the fulltext map
+    const float *min_hint;        // [n_queries] assumed global min for the rank proxy (0)
+    // outputs per (query, tile)
+    uint32_t n_keep;              // limit + offset
+    uint32_t cap;                 // top buffer capacity, pow2 >= n_keep + BM25_CHUNK
+    unsigned long long *tau;      // [n_queries] running global threshold keys
+    uint64_t *cand_key;           // [n_queries][n_tiles][n_keep]
+    float *cand_ft;               // raw fulltext score of each candidate
+    uint32_t *cand_cnt;           // [n_queries][n_tiles]
+    uint32_t *tile_count;         // matched docs
+    float *tile_max, *tile_min;   // pre-OMC extrema (fold start 0.0, token_score.rs:398-401)
+    uint32_t tile_first;          // first tile handled by this launch (sharding of launches)
+};
+
+__host__ __device__ inline size_t bm25_smem_bytes(bool multi, bool threshold, bool omc, uint32_t cap) {
+    size_t b = size_t(BM25_TILE) * 4;                 // score
+    if (multi || omc) b += size_t(BM25_TILE) * 4;     // S / omc multipliers
+    if (threshold) b += size_t(BM25_TILE) * 4;        // token masks
+    b += size_t(BM25_TILE) / 8;                       // row_ok bits
+    b += size_t(cap) * 12;                            // top buffer keys + ft
+    return b + 64;
+}
+
+// ---- df pre-pass (only when a filter / tombstones / multi-term tokens make df != list length):
+// corpus_df = |union over the token's terms of docs passing the filter| (token_score.rs:262-275).
+struct DfParams {
+    const TermDesc *terms;
+    const TokenDesc *tokens;
+    uint32_t n_tokens, n_tiles;
+    const uint32_t *seg;
+    const uint32_t *row_ok_bits;
+    unsigned int *df;  // [n_tokens]
+};
+__global__ void __launch_bounds__(BM25_THREADS) bm25_df_kernel(const DfParams p) {
+    __shared__ uint8_t flag[BM25_TILE];
+    __shared__ uint32_t okb[BM25_TILE / 32];
+    __shared__ uint32_t s_sum;
+    const uint32_t tile = blockIdx.x % p.n_tiles, tok = blockIdx.x / p.n_tiles;
+    const uint32_t row0 = tile * BM25_TILE;
+    const TokenDesc tk = p.tokens[tok];
+    for (uint32_t i = threadIdx.x; i < BM25_TILE / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(flag)[i] = 0;
+    for (uint32_t i = threadIdx.x; i < BM25_TILE / 32; i += blockDim.x)
+        okb[i] = p.row_ok_bits ? p.row_ok_bits[row0 / 32 + i] : 0xffffffffu;
+    if (threadIdx.x == 0) s_sum = 0;
+    __syncthreads();
+    for (uint32_t e = tk.term_begin; e < tk.term_end; e++) {
+        const TermDesc td = p.terms[e];
+        const uint32_t *sg = p.seg + size_t(e) * (p.n_tiles + 1);
+        const uint32_t lo = sg[tile], hi = sg[tile + 1];
+        for (uint32_t pi = lo + threadIdx.x; pi < hi; pi += blockDim.x) {
+            const uint32_t l = td.ptr[pi].row - row0;
+            if ((okb[l >> 5] >> (l & 31)) & 1u) flag[l] = 1;
+        }
+    }
+    __syncthreads();
+    uint32_t c = 0;
+    for (uint32_t i = threadIdx.x; i < BM25_TILE / 4; i += blockDim.x)
+        c += __popc(reinterpret_cast<uint32_t *>(flag)[i] & 0x01010101u);
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_sum, c);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_sum) atomicAdd(&p.df[tok], s_sum);
+}
+
+// ---- the scorer: one CTA per (query, tile) ----
+template <bool MULTI, bool THRESH, bool OMC>
+__global__ void __launch_bounds__(BM25_THREADS) bm25_tile_kernel(const Bm25Params p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    float *score = reinterpret_cast<float *>(smem);
+    float *aux = score + BM25_TILE;                                    // S, then OMC multipliers
+    uint32_t *mask = reinterpret_cast<uint32_t *>(score + BM25_TILE * ((MULTI || OMC) ? 2 : 1));
+    uint32_t *okb = mask + (THRESH ? BM25_TILE : 0);
+    uint64_t *tbuf = reinterpret_cast<uint64_t *>(okb + BM25_TILE / 32);
+    float *tft = reinterpret_cast<float *>(tbuf + p.cap);
+    __shared__ uint32_t s_cnt, s_matched;
+    __shared__ unsigned int s_maxo, s_mino;   // extrema in order-preserving uint space
+    __shared__ unsigned long long s_tau;
+
+    const uint32_t q = blockIdx.x % p.n_queries;
+    const uint32_t tile = p.tile_first + blockIdx.x / p.n_queries;
+    const uint32_t row0 = tile * BM25_TILE;
+    const uint32_t tid = threadIdx.x;
+    const QueryDesc qd = p.queries[q];
+    const float one_minus_b = __fsub_rn(1.0f, p.b);
+    const float kp1 = __fadd_rn(p.k, 1.0f);
+    const bool use_ok = p.row_ok_bits != nullptr;
+
+    for (uint32_t i = tid; i < BM25_TILE; i += BM25_THREADS) {
+        score[i] = 0.f;
+        if (MULTI) aux[i] = 0.f;
+        if (THRESH) mask[i] = 0u;
+    }
+    if (use_ok)
+        for (uint32_t i = tid; i < BM25_TILE / 32; i += BM25_THREADS) okb[i] = p.row_ok_bits[row0 / 32 + i];
+    if (tid == 0) { s_cnt = 0; s_matched = 0; s_maxo = f32_ordered(0.f); s_mino = f32_ordered(0.f); s_tau = p.tau[q]; }
+    __syncthreads();
+
+    // ------------------------------------------------ accumulate, token by token
+    for (uint32_t t = qd.token_begin; t < qd.token_end; t++) {
+        const TokenDesc tk = p.tokens[t];
+        const bool single = !MULTI || (tk.term_end - tk.term_begin == 1);
+        for (uint32_t e = tk.term_begin; e < tk.term_end; e++) {
+            const TermDesc td = p.terms[e];
+            const uint32_t *sg = p.seg + size_t(e) * (p.n_tiles + 1);
+            const uint32_t lo = sg[tile], hi = sg[tile + 1];
+            const uint2 *pp = reinterpret_cast<const uint2 *>(td.ptr);
+            for (uint32_t base = lo; base < hi; base += BM25_THREADS * 4) {
+                uint2 rec[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t pi = base + tid + u * BM25_THREADS;
+                    rec[u] = pi < hi ? __ldg(pp + pi) : make_uint2(0xffffffffu, 0u);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (rec[u].x == 0xffffffffu) continue;
+                    const uint32_t l = rec[u].x - row0;
+                    if (use_ok && !((okb[l >> 5] >> (l & 31)) & 1u)) continue;
+                    const float ntf = bm25_ntf(rec[u].y & 0xffffu, rec[u].y >> 16, td.avg_len, p.b, one_minus_b,
+                                               td.weight);
+                    if (single) {
+                        // S = 0.0 + 1.0*ntf; skip unless is_normal (bm25.rs:387,501)
+                        if (f32_is_normal(ntf)) {
+                            const float c = bm25_sat(ntf, p.k, kp1, tk.idf);
+                            if (c == c) {
+                                score[l] = __fadd_rn(score[l], c);
+                                if (THRESH) mask[l] |= tk.bit;
+                            }
+                        }
+                    } else {
+                        aux[l] = __fadd_rn(aux[l], ntf);  // S += weight(1.0) * ntf, push order
+                    }
+                }
+            }
+            __syncthreads();  // next term / token may touch the same rows
+        }
+        if (MULTI && !single) {
+            // finalize_term: drain S over the rows this token touched (second walk, L2-hot)
+            for (uint32_t e = tk.term_begin; e < tk.term_end; e++) {
+                const TermDesc td = p.terms[e];
+                const uint32_t *sg = p.seg + size_t(e) * (p.n_tiles + 1);
+                const uint32_t lo = sg[tile], hi = sg[tile + 1];
+                for (uint32_t pi = lo + tid; pi < hi; pi += BM25_THREADS) {
+                    const uint32_t l = td.ptr[pi].row - row0;
+                    const float S = __uint_as_float(atomicExch(reinterpret_cast<unsigned int *>(&aux[l]), 0u));
+                    if (f32_is_normal(S)) {
+                        const float c = bm25_sat(S, p.k, kp1, tk.idf);
+                        if (c == c) {
+                            score[l] = __fadd_rn(score[l], c);
+                            if (THRESH) mask[l] |= tk.bit;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+    }
+
+    // ------------------------------------------------ OMC multipliers for this tile
+    uint32_t omc_lo = 0, omc_hi = 0;
+    if (OMC) {
+        for (uint32_t i = tid; i < BM25_TILE; i += BM25_THREADS) aux[i] = 1.0f;
+        // binary search [row0, row0+TILE) in omc_row (uniform across the block)
+        uint32_t lo = 0, hi = p.n_omc;
+        while (lo < hi) { uint32_t m = (lo + hi) >> 1; if (p.omc_row[m] < row0) lo = m + 1; else hi = m; }
+        omc_lo = lo; hi = p.n_omc;
+        const uint64_t rend = uint64_t(row0) + BM25_TILE;
+        while (lo < hi) { uint32_t m = (lo + hi) >> 1; if (uint64_t(p.omc_row[m]) < rend) lo = m + 1; else hi = m; }
+        omc_hi = lo;
+        __syncthreads();
+        for (uint32_t i = omc_lo + tid; i < omc_hi; i += BM25_THREADS) aux[p.omc_row[i] - row0] = p.omc_mult[i];
+        __syncthreads();
+    }
+
+    // ------------------------------------------------ hybrid: report ft of the vector hits
+    if (p.v_row) {
+        for (uint32_t j = tid; j < p.v_stride; j += BM25_THREADS) {
+            const uint32_t vr = p.v_row[size_t(q) * p.v_stride + j];
+            if (vr != 0xffffffffu && vr >= row0 && uint64_t(vr) < uint64_t(row0) + BM25_TILE) {
+                const uint32_t l = vr - row0;
+                bool present;
+                if (THRESH) present = mask[l] != 0u && uint32_t(__popc(mask[l])) >= qd.required;
+                else present = score[l] != 0.f;
+                p.v_ft[size_t(q) * p.v_stride + j] = present ? score[l] : 0.f;
+                p.v_present[size_t(q) * p.v_stride + j] = present ? 1 : 0;
+            }
+        }
+    }
+
+    // ------------------------------------------------ scan: count, extrema, gated top-n
+    const float mh = p.min_hint ? p.min_hint[q] : 0.f;
+    unsigned long long tau = s_tau;
+    uint32_t matched = 0;
+    float lmax = 0.f, lmin = 0.f;
+    const uint64_t rows_here = min(uint64_t(BM25_TILE), p.n_rows - row0);
+    for (uint32_t base = 0; base < rows_here; base += BM25_CHUNK) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint32_t l = base + tid + u * BM25_THREADS;
+            if (l >= rows_here) continue;
+            const float s = score[l];
+            bool present;
+            if (THRESH) present = mask[l] != 0u && uint32_t(__popc(mask[l])) >= qd.required;  // bm25.rs:416-428
+            else present = s != 0.f;
+            if (!present) continue;
+            matched++;
+            lmax = fmaxf(lmax, s);
+            lmin = fminf(lmin, s);
+            float proxy = __fsub_rn(s, mh);
+            if (OMC) proxy = __fmul_rn(proxy, aux[l]);
+            if (proxy == proxy) {
+                const unsigned long long key = make_key(proxy, row0 + l);
+                if (key > tau) {
+                    const uint32_t slot = atomicAdd(&s_cnt, 1u);
+                    tbuf[slot] = key;   // slot < cap guaranteed by the compress rule below
+                    tft[slot] = s;
+                }
+            }
+        }
+        __syncthreads();
+        const uint32_t c = s_cnt;   // snapshot, then barrier, so the branch is block-uniform
+        __syncthreads();
+        if (c + BM25_CHUNK > p.cap && base + BM25_CHUNK < rows_here) {
+            // compress: keep the best n_keep
+            for (uint32_t i = c + tid; i < p.cap; i += BM25_THREADS) tbuf[i] = KEY_NONE;
+            // sort keys; ft travels by re-lookup (score[] still holds it): key -> row -> score
+            group_bitonic_desc(tbuf, p.cap, tid, BM25_THREADS, 0);
+            const uint32_t kept = min(c, p.n_keep);
+            if (tid == 0) s_cnt = kept;
+            if (kept == p.n_keep) tau = max(tau, (unsigned long long)tbuf[p.n_keep - 1]);
+            for (uint32_t i = tid; i < kept; i += BM25_THREADS) tft[i] = score[key_idx(tbuf[i]) - row0];
+            __syncthreads();
+        }
+    }
+    // ---- block reductions of count / extrema
+    matched = __reduce_add_sync(0xffffffffu, matched);
+    for (int o = 16; o > 0; o >>= 1) {
+        lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+        lmin = fminf(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+    }
+    if ((tid & 31) == 0) {
+        if (matched) atomicAdd(&s_matched, matched);
+        atomicMax(&s_maxo, f32_ordered(lmax));
+        atomicMin(&s_mino, f32_ordered(lmin));
+    }
+    __syncthreads();
+
+    // ---- final emit: best <= n_keep of the buffer
+    const size_t slot_base = (size_t(q) * p.n_tiles + tile);
+    uint32_t c = s_cnt;
+    if (c >= p.n_keep && c > 0) {
+        for (uint32_t i = c + tid; i < p.cap; i += BM25_THREADS) tbuf[i] = KEY_NONE;
+        group_bitonic_desc(tbuf, p.cap, tid, BM25_THREADS, 0);
+        c = p.n_keep;
+        for (uint32_t i = tid; i < c; i += BM25_THREADS) tft[i] = score[key_idx(tbuf[i]) - row0];
+        __syncthreads();
+        if (tid == 0) atomicMax(p.tau + q, (unsigned long long)tbuf[p.n_keep - 1]);
+    }
+    for (uint32_t i = tid; i < c; i += BM25_THREADS) {
+        p.cand_key[slot_base * p.n_keep + i] = tbuf[i];
+        p.cand_ft[slot_base * p.n_keep + i] = tft[i];
+    }
+    if (tid == 0) {
+        p.cand_cnt[slot_base] = c;
+        p.tile_count[slot_base] = s_matched;
+        p.tile_max[slot_base] = f32_unordered(s_maxo);
+        p.tile_min[slot_base] = f32_unordered(s_mino);
+    }
+}
+
+}  // namespace oc

@@ -1,0 +1,927 @@
+// capi.cu — host side of liboramacore_b200.so: the C ABI declared in
+// include/oramacore_b200.h over the sm_100a kernels (emb_scan.cuh, bm25.cuh, fuse.cuh).
+// No torch, no CPU fallback: every entry point needs a live CUDA device.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "bm25.cuh"
+#include "comm.h"
+#include "emb_scan.cuh"
+#include "fuse.cuh"
+#include "oramacore_b200.h"
+
+using namespace oc;
+
+// ------------------------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+static int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CU(x)                                                                                   \
+    do {                                                                                        \
+        cudaError_t _e = (x);                                                                   \
+        if (_e != cudaSuccess)                                                                  \
+            return fail(_e == cudaErrorMemoryAllocation ? OC_ERR_OOM : OC_ERR_CUDA, "%s: %s (%s:%d)", #x, \
+                        cudaGetErrorString(_e), __FILE__, __LINE__);                            \
+    } while (0)
+#define OCTRY(x)                \
+    do {                        \
+        int _r = (x);           \
+        if (_r != OC_OK) return _r; \
+    } while (0)
+
+extern "C" const char *oc_last_error(void) { return g_err; }
+extern "C" int oc_version(void) { return 100; }
+extern "C" void oc_abi_sizes(size_t out[4]) {
+    out[0] = sizeof(oc_search_params); out[1] = sizeof(oc_timing); out[2] = sizeof(oc_emb_info_t); out[3] = sizeof(oc_str_info_t);
+}
+
+// ------------------------------------------------------------------------------------ buffers
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return OC_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { e = cudaMalloc(&p, bytes); want = bytes; }
+        if (e != cudaSuccess) return fail(OC_ERR_OOM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+        cap = want;
+        return OC_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T *as() { return reinterpret_cast<T *>(p); }
+};
+struct HostBuf {  // pinned staging
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return OC_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e != cudaSuccess) return fail(OC_ERR_OOM, "cudaMallocHost(%zu): %s", want, cudaGetErrorString(e));
+        cap = want;
+        return OC_OK;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <typename T> T *as() { return reinterpret_cast<T *>(p); }
+};
+
+// packs several host arrays into one pinned blob -> one H2D copy
+struct Packer {
+    std::vector<uint8_t> blob;
+    size_t add(const void *src, size_t bytes) {
+        size_t off = (blob.size() + 255) & ~size_t(255);
+        blob.resize(off + bytes);
+        if (bytes && src) memcpy(blob.data() + off, src, bytes);
+        return off;
+    }
+    size_t reserve(size_t bytes) { return add(nullptr, bytes); }
+};
+
+enum { EV_START, EV_H2D, EV_DEV, EV_D2H, EV_SCAN0, EV_SCAN1, EV_BM0, EV_BM1, EV_FUSE0, EV_FUSE1, EV_COMM0, EV_COMM1, EV_N };
+
+struct oc_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaDeviceProp prop{};
+    std::mutex mu;
+    cudaEvent_t ev[EV_N]{};
+    oc_timing timing{};
+    uint64_t launches = 0;
+    uint32_t call_launches = 0, call_scan_launches = 0;
+    // workspaces
+    DevBuf in_blob, q_pad, q_inv, eff_norm, filter_dev, scan_cand, v_doc, v_score, v_row, v_cnt, v_srow, v_ft, v_present;
+    DevBuf seg, df_dev, row_ok, tau, cand_key, cand_ft, cand_cnt, tile_cnt, tile_max, tile_min, min_hint;
+    DevBuf out_blob, shard_send, shard_recv;
+    HostBuf h_in, h_out;
+    OcComm comm;
+};
+
+static inline void launched(oc_ctx *c, bool scan = false) {
+    c->launches++; c->call_launches++;
+    if (scan) c->call_scan_launches++;
+}
+
+extern "C" int oc_init(int device_id, oc_ctx **out) {
+    if (!out) return fail(OC_ERR_INVALID, "oc_init: out is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(OC_ERR_CUDA, "no CUDA device: %s (this library has no CPU fallback)", cudaGetErrorString(e));
+    if (device_id < 0 || device_id >= n) return fail(OC_ERR_INVALID, "device %d out of range (%d devices)", device_id, n);
+    CU(cudaSetDevice(device_id));
+    oc_ctx *c = new oc_ctx();
+    c->device = device_id;
+    CU(cudaGetDeviceProperties(&c->prop, device_id));
+    if (c->prop.major < 10) {
+        int mj = c->prop.major, mn = c->prop.minor;
+        delete c;
+        return fail(OC_ERR_CUDA, "device sm_%d%d is not sm_100-class; kernels are built for sm_100a only", mj, mn);
+    }
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < EV_N; i++) CU(cudaEventCreate(&c->ev[i]));
+    *out = c;
+    return OC_OK;
+}
+
+extern "C" void oc_shutdown(oc_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->comm.destroy();
+    DevBuf *bufs[] = {&c->in_blob, &c->q_pad, &c->q_inv, &c->eff_norm, &c->filter_dev, &c->scan_cand, &c->v_doc,
+                      &c->v_score, &c->v_row, &c->v_cnt, &c->v_srow, &c->v_ft, &c->v_present, &c->seg, &c->df_dev,
+                      &c->row_ok, &c->tau, &c->cand_key, &c->cand_ft, &c->cand_cnt, &c->tile_cnt, &c->tile_max,
+                      &c->tile_min, &c->min_hint, &c->out_blob, &c->shard_send, &c->shard_recv};
+    for (DevBuf *b : bufs) b->release();
+    c->h_in.release(); c->h_out.release();
+    for (int i = 0; i < EV_N; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" int oc_device_info(oc_ctx *c, int *sm_count, size_t *hbm_bytes, char *name, size_t name_cap) {
+    if (!c) return fail(OC_ERR_INVALID, "ctx is NULL");
+    if (sm_count) *sm_count = c->prop.multiProcessorCount;
+    if (hbm_bytes) *hbm_bytes = c->prop.totalGlobalMem;
+    if (name && name_cap) { strncpy(name, c->prop.name, name_cap - 1); name[name_cap - 1] = 0; }
+    return OC_OK;
+}
+
+extern "C" int oc_last_timing(oc_ctx *c, oc_timing *out) {
+    if (!c || !out) return fail(OC_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> g(c->mu);
+    *out = c->timing;
+    return OC_OK;
+}
+extern "C" uint64_t oc_launch_count(oc_ctx *c) { return c ? c->launches : 0; }
+
+extern "C" int oc_comm_unique_id(uint8_t out_id[OC_COMM_ID_BYTES]) {
+    std::string err;
+    if (!OcComm::unique_id(out_id, &err)) return fail(OC_ERR_COMM, "%s", err.c_str());
+    return OC_OK;
+}
+extern "C" int oc_comm_init(oc_ctx *c, int world, int rank, const uint8_t id[OC_COMM_ID_BYTES]) {
+    if (!c || world < 1 || rank < 0 || rank >= world) return fail(OC_ERR_INVALID, "bad comm arguments");
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    std::string err;
+    if (!c->comm.init(world, rank, id, &err)) return fail(OC_ERR_COMM, "%s", err.c_str());
+    return OC_OK;
+}
+
+// ------------------------------------------------------------------------------------ embedding store
+struct oc_emb {
+    oc_ctx *ctx;
+    uint32_t dim, stride;
+    int dtype, e5;
+    float *rows = nullptr;       // [cap][stride]
+    float *inv_norm = nullptr;   // [cap] (NaN = tombstone)
+    uint64_t *row_doc = nullptr; // [cap]
+    uint64_t n_rows = 0, cap = 0, n_live = 0;
+    std::unordered_multimap<uint64_t, uint64_t> doc_rows;  // doc -> rows (for delete)
+};
+
+extern "C" int oc_emb_create(oc_ctx *c, uint32_t dim, int dtype, int rescale_e5, oc_emb **out) {
+    if (!c || !out) return fail(OC_ERR_INVALID, "NULL argument");
+    if (dim == 0 || dim > 1024) return fail(OC_ERR_UNSUPPORTED, "dim %u unsupported (1..1024)", dim);
+    if (dtype != OC_DTYPE_F32) return fail(OC_ERR_UNSUPPORTED, "dtype %d not built yet (f32 only)", dtype);
+    oc_emb *e = new oc_emb();
+    e->ctx = c; e->dim = dim; e->dtype = dtype; e->e5 = rescale_e5 ? 1 : 0;
+    e->stride = ((dim + 127) / 128) * 128;
+    if (e->stride / 128 == 5 || e->stride / 128 == 7) e->stride += 128;  // instantiated widths: 1,2,3,4,6,8
+    *out = e;
+    return OC_OK;
+}
+
+extern "C" void oc_emb_destroy(oc_emb *e) {
+    if (!e) return;
+    cudaSetDevice(e->ctx->device);
+    cudaStreamSynchronize(e->ctx->stream);
+    cudaFree(e->rows); cudaFree(e->inv_norm); cudaFree(e->row_doc);
+    delete e;
+}
+
+static int emb_grow(oc_emb *e, uint64_t want_rows) {
+    if (want_rows <= e->cap) return OC_OK;
+    oc_ctx *c = e->ctx;
+    uint64_t ncap = std::max<uint64_t>(want_rows, e->cap + e->cap / 2);
+    ncap = (ncap + 63) / 64 * 64;
+    float *nr = nullptr, *nn = nullptr; uint64_t *nd = nullptr;
+    CU(cudaMalloc(&nr, ncap * e->stride * sizeof(float)));
+    CU(cudaMalloc(&nn, (ncap + 64) * sizeof(float)));
+    CU(cudaMalloc(&nd, ncap * sizeof(uint64_t)));
+    if (e->n_rows) {
+        CU(cudaMemcpyAsync(nr, e->rows, e->n_rows * e->stride * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+        CU(cudaMemcpyAsync(nn, e->inv_norm, e->n_rows * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+        CU(cudaMemcpyAsync(nd, e->row_doc, e->n_rows * sizeof(uint64_t), cudaMemcpyDeviceToDevice, c->stream));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    cudaFree(e->rows); cudaFree(e->inv_norm); cudaFree(e->row_doc);
+    e->rows = nr; e->inv_norm = nn; e->row_doc = nd; e->cap = ncap;
+    return OC_OK;
+}
+
+extern "C" int oc_emb_reserve(oc_emb *e, uint64_t n_rows) {
+    if (!e) return fail(OC_ERR_INVALID, "emb is NULL");
+    std::lock_guard<std::mutex> g(e->ctx->mu);
+    CU(cudaSetDevice(e->ctx->device));
+    return emb_grow(e, n_rows);
+}
+
+extern "C" int oc_emb_insert(oc_emb *e, const uint64_t *doc_ids, const void *rows, uint64_t n) {
+    if (!e || (!doc_ids && n) || (!rows && n)) return fail(OC_ERR_INVALID, "NULL argument");
+    if (n == 0) return OC_OK;
+    oc_ctx *c = e->ctx;
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    if (e->n_rows + n > 0xfffffff0ull) return fail(OC_ERR_UNSUPPORTED, "more than 2^32 rows per store");
+    OCTRY(emb_grow(e, e->n_rows + n));
+    float *dst = e->rows + e->n_rows * e->stride;
+    if (e->stride != e->dim) CU(cudaMemsetAsync(dst, 0, n * e->stride * sizeof(float), c->stream));
+    CU(cudaMemcpy2DAsync(dst, e->stride * sizeof(float), rows, e->dim * sizeof(float), e->dim * sizeof(float), n,
+                         cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(e->row_doc + e->n_rows, doc_ids, n * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+    const uint64_t warps_per_block = 8;
+    const uint64_t blocks = (n + warps_per_block - 1) / warps_per_block;
+    emb_inv_norm_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(e->rows, e->stride, e->n_rows, e->n_rows + n, e->inv_norm);
+    launched(c);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+    for (uint64_t i = 0; i < n; i++) e->doc_rows.emplace(doc_ids[i], e->n_rows + i);
+    e->n_rows += n; e->n_live += n;
+    return OC_OK;
+}
+
+__global__ void tombstone_rows_kernel(float *inv_norm, const uint64_t *rows, uint64_t n) {
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) inv_norm[rows[i]] = __int_as_float(0x7fc00000);
+}
+
+extern "C" int oc_emb_delete(oc_emb *e, const uint64_t *doc_ids, uint64_t n) {
+    if (!e || (!doc_ids && n)) return fail(OC_ERR_INVALID, "NULL argument");
+    oc_ctx *c = e->ctx;
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    std::vector<uint64_t> rows;
+    for (uint64_t i = 0; i < n; i++) {
+        auto range = e->doc_rows.equal_range(doc_ids[i]);
+        for (auto it = range.first; it != range.second; ++it) rows.push_back(it->second);
+        e->doc_rows.erase(range.first, range.second);
+    }
+    if (rows.empty()) return OC_OK;
+    OCTRY(c->in_blob.ensure(rows.size() * 8));
+    CU(cudaMemcpyAsync(c->in_blob.p, rows.data(), rows.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    tombstone_rows_kernel<<<(unsigned)((rows.size() + 255) / 256), 256, 0, c->stream>>>(e->inv_norm, c->in_blob.as<uint64_t>(), rows.size());
+    launched(c);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+    e->n_live -= rows.size();
+    return OC_OK;
+}
+
+extern "C" int oc_emb_info(oc_emb *e, oc_emb_info_t *out) {
+    if (!e || !out) return fail(OC_ERR_INVALID, "NULL argument");
+    out->num_embeddings = e->n_live; out->num_rows = e->n_rows; out->dimensions = e->dim; out->dtype = e->dtype;
+    out->device_bytes = e->cap * (uint64_t(e->stride) * 4 + 4 + 8);
+    return OC_OK;
+}
+
+// ---- scan launch plumbing
+template <int NCH, int QB>
+static int launch_scan_t(oc_ctx *c, const ScanParams &sp, uint32_t grid, size_t smem) {
+    static bool configured = false;  // per instantiation
+    if (!configured) {
+        CU(cudaFuncSetAttribute(emb_scan_kernel<NCH, QB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured = true;
+    }
+    emb_scan_kernel<NCH, QB><<<grid, SCAN_THREADS, smem, c->stream>>>(sp);
+    launched(c, true);
+    CU(cudaGetLastError());
+    return OC_OK;
+}
+template <int QB>
+static int launch_scan_q(oc_ctx *c, const ScanParams &sp, uint32_t grid, size_t smem) {
+    switch (sp.stride / 128) {
+        case 1: return launch_scan_t<1, QB>(c, sp, grid, smem);
+        case 2: return launch_scan_t<2, QB>(c, sp, grid, smem);
+        case 3: return launch_scan_t<3, QB>(c, sp, grid, smem);
+        case 4: return launch_scan_t<4, QB>(c, sp, grid, smem);
+        case 6: return launch_scan_t<6, QB>(c, sp, grid, smem);
+        case 8: return launch_scan_t<8, QB>(c, sp, grid, smem);
+    }
+    return fail(OC_ERR_UNSUPPORTED, "stride %u not instantiated", sp.stride);
+}
+
+struct ScanPlan {
+    uint32_t rows_per_stage, n_stages, wcap, grid;
+};
+static ScanPlan plan_scan(const oc_ctx *c, const oc_emb *e, uint32_t n_keep, uint32_t qb) {
+    ScanPlan pl;
+    const uint32_t row_bytes = e->stride * 4;
+    uint32_t R = (32768 / row_bytes) / 8 * 8;
+    if (R < 8) R = 8;
+    pl.rows_per_stage = R;
+    pl.wcap = std::max<uint32_t>(32, next_pow2(2 * n_keep));
+    const size_t budget = 227 * 1024 - 1024;
+    const size_t fixed = size_t(SCAN_CONSUMER_WARPS) * qb * pl.wcap * 8 + 256;
+    const size_t per_stage = size_t(R) * row_bytes + R * 4 + 16;
+    uint32_t S = (uint32_t)std::min<size_t>(8, fixed < budget ? (budget - fixed) / per_stage : 0);
+    pl.n_stages = S;
+    const uint64_t tiles = (e->n_rows + R - 1) / R;
+    pl.grid = (uint32_t)std::min<uint64_t>(c->prop.multiProcessorCount, std::max<uint64_t>(tiles, 1));
+    return pl;
+}
+
+// Runs prep + scan sweeps + merge for B queries already in device memory (q_dev: B x dim).
+// Leaves hits in c->v_doc / v_score / v_row / v_cnt ([B][limit]).
+static int run_vector_stage(oc_ctx *c, oc_emb *e, const float *q_dev, uint32_t B, uint32_t limit, float similarity,
+                            const uint64_t *filter_dev, uint64_t filter_nbits) {
+    OCTRY(c->v_doc.ensure(size_t(B) * limit * 8));
+    OCTRY(c->v_score.ensure(size_t(B) * limit * 4));
+    OCTRY(c->v_row.ensure(size_t(B) * limit * 4));
+    OCTRY(c->v_cnt.ensure(size_t(B) * 4));
+    if (e->n_rows == 0) {
+        CU(cudaMemsetAsync(c->v_cnt.p, 0, size_t(B) * 4, c->stream));
+        CU(cudaMemsetAsync(c->v_doc.p, 0, size_t(B) * limit * 8, c->stream));
+        CU(cudaMemsetAsync(c->v_score.p, 0, size_t(B) * limit * 4, c->stream));
+        CU(cudaMemsetAsync(c->v_row.p, 0xff, size_t(B) * limit * 4, c->stream));
+        return OC_OK;
+    }
+    OCTRY(c->q_pad.ensure(size_t(B) * e->stride * 4));
+    OCTRY(c->q_inv.ensure(size_t(B) * 4));
+    emb_prep_queries_kernel<<<(B + 7) / 8, 256, 0, c->stream>>>(q_dev, e->dim, e->stride, B, c->q_pad.as<float>(), c->q_inv.as<float>());
+    launched(c);
+    const float *inv_norm = e->inv_norm;
+    if (filter_dev) {
+        OCTRY(c->eff_norm.ensure((e->n_rows + 64) * 4));
+        emb_apply_filter_kernel<<<(unsigned)((e->n_rows + 255) / 256), 256, 0, c->stream>>>(
+            e->inv_norm, e->row_doc, e->n_rows, filter_dev, filter_nbits, c->eff_norm.as<float>());
+        launched(c);
+        inv_norm = c->eff_norm.as<float>();
+    }
+    ScanPlan pl = plan_scan(c, e, limit, 4);
+    if (pl.n_stages < 2) return fail(OC_ERR_UNSUPPORTED, "limit %u leaves no shared memory for the scan ring", limit);
+    OCTRY(c->scan_cand.ensure(size_t(B) * pl.grid * limit * 8));
+    CU(cudaEventRecord(c->ev[EV_SCAN0], c->stream));
+    uint32_t q0 = 0;
+    while (q0 < B) {
+        const uint32_t rem = B - q0;
+        const uint32_t qb = rem >= 4 ? 4 : (rem >= 2 ? 2 : 1);
+        ScanParams sp{};
+        sp.rows = e->rows; sp.inv_norm = inv_norm; sp.n_rows = e->n_rows; sp.stride = e->stride;
+        sp.queries = c->q_pad.as<float>() + size_t(q0) * e->stride;
+        sp.inv_qnorm = c->q_inv.as<float>() + q0;
+        sp.n_keep = limit; sp.wcap = pl.wcap; sp.rows_per_stage = pl.rows_per_stage; sp.n_stages = pl.n_stages;
+        sp.n_ctas_total = pl.grid;
+        sp.cand = c->scan_cand.as<uint64_t>() + size_t(q0) * pl.grid * limit;
+        const size_t smem = scan_smem_bytes(e->stride, pl.rows_per_stage, pl.n_stages, pl.wcap, qb);
+        if (qb == 4) OCTRY((launch_scan_q<4>(c, sp, pl.grid, smem)));
+        else if (qb == 2) OCTRY((launch_scan_q<2>(c, sp, pl.grid, smem)));
+        else OCTRY((launch_scan_q<1>(c, sp, pl.grid, smem)));
+        c->timing.scan_bytes += e->n_rows * (uint64_t(e->stride) * 4 + 4);
+        q0 += qb;
+    }
+    CU(cudaEventRecord(c->ev[EV_SCAN1], c->stream));
+    ScanMergeParams mp{};
+    mp.cand = c->scan_cand.as<uint64_t>(); mp.n_lists = pl.grid; mp.n_keep = limit; mp.limit = limit;
+    mp.capb = std::max<uint32_t>(2048, next_pow2(2 * limit));
+    mp.row_doc_ids = e->row_doc; mp.rescale_e5 = e->e5; mp.similarity = similarity;
+    mp.out_doc = c->v_doc.as<uint64_t>(); mp.out_score = c->v_score.as<float>(); mp.out_row = c->v_row.as<uint32_t>();
+    mp.out_count = c->v_cnt.as<uint32_t>();
+    emb_scan_merge_kernel<<<B, 256, mp.capb * 8, c->stream>>>(mp);
+    launched(c);
+    CU(cudaGetLastError());
+    return OC_OK;
+}
+
+static void begin_call(oc_ctx *c) {
+    c->call_launches = 0; c->call_scan_launches = 0;
+    memset(&c->timing, 0, sizeof(c->timing));
+}
+static int finish_timing(oc_ctx *c, bool scan, bool bm, bool fuse, bool comm) {
+    auto el = [&](int a, int b) { float ms = 0; cudaEventElapsedTime(&ms, c->ev[a], c->ev[b]); return ms; };
+    c->timing.h2d_ms = el(EV_START, EV_H2D);
+    c->timing.device_ms = el(EV_H2D, EV_DEV);
+    c->timing.d2h_ms = el(EV_DEV, EV_D2H);
+    c->timing.scan_ms = scan ? el(EV_SCAN0, EV_SCAN1) : 0;
+    c->timing.bm25_ms = bm ? el(EV_BM0, EV_BM1) : 0;
+    c->timing.fuse_ms = fuse ? el(EV_FUSE0, EV_FUSE1) : 0;
+    c->timing.comm_ms = comm ? el(EV_COMM0, EV_COMM1) : 0;
+    c->timing.kernel_launches = c->call_launches;
+    c->timing.scan_launches = c->call_scan_launches;
+    return OC_OK;
+}
+
+extern "C" int oc_emb_search(oc_emb *e, const float *queries, uint32_t B, uint32_t limit, float similarity,
+                             const uint64_t *filter_bits, uint64_t filter_nbits, uint64_t *out_doc_ids,
+                             float *out_scores, uint32_t *out_counts) {
+    if (!e || !queries || !out_doc_ids || !out_scores || !out_counts) return fail(OC_ERR_INVALID, "NULL argument");
+    if (B == 0) return OC_OK;
+    if (limit == 0 || limit > OC_MAX_TOPK) return fail(OC_ERR_UNSUPPORTED, "limit %u outside 1..%u", limit, OC_MAX_TOPK);
+    oc_ctx *c = e->ctx;
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    begin_call(c);
+    const size_t qbytes = size_t(B) * e->dim * 4;
+    const size_t fwords = filter_bits ? (filter_nbits + 63) / 64 : 0;
+    OCTRY(c->in_blob.ensure(qbytes));
+    CU(cudaEventRecord(c->ev[EV_START], c->stream));
+    CU(cudaMemcpyAsync(c->in_blob.p, queries, qbytes, cudaMemcpyHostToDevice, c->stream));
+    if (fwords) {
+        OCTRY(c->filter_dev.ensure(fwords * 8));
+        CU(cudaMemcpyAsync(c->filter_dev.p, filter_bits, fwords * 8, cudaMemcpyHostToDevice, c->stream));
+    }
+    c->timing.h2d_bytes = qbytes + fwords * 8;
+    CU(cudaEventRecord(c->ev[EV_H2D], c->stream));
+    OCTRY(run_vector_stage(c, e, c->in_blob.as<float>(), B, limit, similarity,
+                           fwords ? c->filter_dev.as<uint64_t>() : nullptr, filter_nbits));
+    CU(cudaEventRecord(c->ev[EV_DEV], c->stream));
+    const size_t ob = size_t(B) * limit * 12 + size_t(B) * 4;
+    OCTRY(c->h_out.ensure(ob));
+    uint8_t *h = c->h_out.as<uint8_t>();
+    CU(cudaMemcpyAsync(h, c->v_doc.p, size_t(B) * limit * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(h + size_t(B) * limit * 8, c->v_score.p, size_t(B) * limit * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(h + size_t(B) * limit * 12, c->v_cnt.p, size_t(B) * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaEventRecord(c->ev[EV_D2H], c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->timing.d2h_bytes = ob;
+    memcpy(out_doc_ids, h, size_t(B) * limit * 8);
+    memcpy(out_scores, h + size_t(B) * limit * 8, size_t(B) * limit * 4);
+    memcpy(out_counts, h + size_t(B) * limit * 12, size_t(B) * 4);
+    return finish_timing(c, e->n_rows > 0, false, false, false);
+}
+
+// ------------------------------------------------------------------------------------ string store
+struct StrField {
+    float avg_len = 0;
+    uint32_t n_terms = 0;
+    std::vector<uint64_t> term_offsets;  // host copy (n_terms+1)
+    std::vector<uint32_t> global_df;     // optional
+    Posting *post = nullptr;             // device
+    uint64_t n_post = 0;
+};
+struct oc_str {
+    oc_ctx *ctx;
+    std::vector<StrField> fields;
+    uint64_t n_rows = 0, document_count = 0;
+    std::vector<uint64_t> row_doc_host;  // empty => identity
+    uint64_t *row_doc = nullptr;         // device or NULL
+    uint32_t *alive = nullptr;           // device bitmap (allocated on first delete)
+    std::vector<uint32_t> alive_host;
+    uint64_t n_deleted = 0;
+};
+
+extern "C" int oc_str_create(oc_ctx *c, uint32_t n_fields, oc_str **out) {
+    if (!c || !out || n_fields == 0) return fail(OC_ERR_INVALID, "bad arguments");
+    oc_str *s = new oc_str();
+    s->ctx = c;
+    s->fields.resize(n_fields);
+    *out = s;
+    return OC_OK;
+}
+extern "C" void oc_str_destroy(oc_str *s) {
+    if (!s) return;
+    cudaSetDevice(s->ctx->device);
+    cudaStreamSynchronize(s->ctx->stream);
+    for (auto &f : s->fields) cudaFree(f.post);
+    cudaFree(s->row_doc); cudaFree(s->alive);
+    delete s;
+}
+
+extern "C" int oc_str_set_rows(oc_str *s, uint64_t n_rows, const uint64_t *row_doc_ids, uint64_t document_count) {
+    if (!s) return fail(OC_ERR_INVALID, "str is NULL");
+    if (n_rows > 0xfffffff0ull) return fail(OC_ERR_UNSUPPORTED, "more than 2^32 rows per store");
+    oc_ctx *c = s->ctx;
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    cudaFree(s->row_doc); s->row_doc = nullptr; s->row_doc_host.clear();
+    cudaFree(s->alive); s->alive = nullptr; s->alive_host.clear(); s->n_deleted = 0;
+    s->n_rows = n_rows; s->document_count = document_count;
+    if (row_doc_ids && n_rows) {
+        for (uint64_t i = 1; i < n_rows; i++)
+            if (row_doc_ids[i] <= row_doc_ids[i - 1]) return fail(OC_ERR_INVALID, "row_doc_ids must be strictly ascending");
+        s->row_doc_host.assign(row_doc_ids, row_doc_ids + n_rows);
+        CU(cudaMalloc(&s->row_doc, n_rows * 8));
+        CU(cudaMemcpy(s->row_doc, row_doc_ids, n_rows * 8, cudaMemcpyHostToDevice));
+    }
+    return OC_OK;
+}
+
+extern "C" int oc_str_load_field(oc_str *s, uint32_t field, float avg_field_len, uint32_t n_terms,
+                                 const uint64_t *term_offsets, const uint32_t *post_row, const uint16_t *post_tf,
+                                 const uint16_t *post_len, const uint32_t *global_df) {
+    if (!s || field >= s->fields.size() || !term_offsets) return fail(OC_ERR_INVALID, "bad arguments");
+    oc_ctx *c = s->ctx;
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    StrField &f = s->fields[field];
+    cudaFree(f.post); f.post = nullptr;
+    const uint64_t np = term_offsets[n_terms];
+    if (np && (!post_row || !post_tf || !post_len)) return fail(OC_ERR_INVALID, "posting arrays are NULL");
+    for (uint32_t t = 0; t < n_terms; t++) {
+        if (term_offsets[t + 1] < term_offsets[t]) return fail(OC_ERR_INVALID, "term_offsets not monotone");
+        if (term_offsets[t + 1] - term_offsets[t] > 0xffffffffull) return fail(OC_ERR_UNSUPPORTED, "posting list too long");
+    }
+    f.avg_len = avg_field_len; f.n_terms = n_terms; f.n_post = np;
+    f.term_offsets.assign(term_offsets, term_offsets + n_terms + 1);
+    f.global_df.clear();
+    if (global_df) f.global_df.assign(global_df, global_df + n_terms);
+    if (np) {
+        CU(cudaMalloc(&f.post, (np + 4) * sizeof(Posting)));
+        // interleave (row, tf, len) into 8-byte records through a bounded pinned staging buffer
+        const uint64_t CH = 8u << 20;
+        OCTRY(c->h_in.ensure(std::min<uint64_t>(np, CH) * sizeof(Posting)));
+        for (uint64_t off = 0; off < np; off += CH) {
+            const uint64_t m = std::min<uint64_t>(CH, np - off);
+            Posting *h = c->h_in.as<Posting>();
+            for (uint64_t i = 0; i < m; i++) {
+                if (post_row[off + i] >= s->n_rows && s->n_rows) return fail(OC_ERR_INVALID, "posting row %u >= n_rows", post_row[off + i]);
+                h[i].row = post_row[off + i]; h[i].tf = post_tf[off + i]; h[i].len = post_len[off + i];
+            }
+            CU(cudaMemcpyAsync(f.post + off, h, m * sizeof(Posting), cudaMemcpyHostToDevice, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+        }
+    }
+    return OC_OK;
+}
+
+extern "C" int oc_str_delete(oc_str *s, const uint64_t *doc_ids, uint64_t n) {
+    if (!s || (!doc_ids && n)) return fail(OC_ERR_INVALID, "NULL argument");
+    oc_ctx *c = s->ctx;
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    const uint64_t words = (s->n_rows + BM25_TILE - 1) / BM25_TILE * (BM25_TILE / 32);
+    if (s->alive_host.empty()) {
+        s->alive_host.assign(words, 0xffffffffu);
+        CU(cudaMalloc(&s->alive, words * 4));
+    }
+    for (uint64_t i = 0; i < n; i++) {
+        uint64_t r;
+        if (s->row_doc_host.empty()) { r = doc_ids[i]; if (r >= s->n_rows) continue; }
+        else {
+            auto it = std::lower_bound(s->row_doc_host.begin(), s->row_doc_host.end(), doc_ids[i]);
+            if (it == s->row_doc_host.end() || *it != doc_ids[i]) continue;
+            r = uint64_t(it - s->row_doc_host.begin());
+        }
+        if (s->alive_host[r >> 5] & (1u << (r & 31))) { s->alive_host[r >> 5] &= ~(1u << (r & 31)); s->n_deleted++; }
+    }
+    CU(cudaMemcpy(s->alive, s->alive_host.data(), words * 4, cudaMemcpyHostToDevice));
+    return OC_OK;
+}
+
+extern "C" int oc_str_info(oc_str *s, oc_str_info_t *out) {
+    if (!s || !out) return fail(OC_ERR_INVALID, "NULL argument");
+    out->total_documents = s->n_rows - s->n_deleted; out->n_fields = (uint32_t)s->fields.size();
+    out->total_postings = 0; out->unique_terms_count = 0;
+    for (auto &f : s->fields) { out->total_postings += f.n_post; out->unique_terms_count += f.n_terms; }
+    out->device_bytes = out->total_postings * 8 + (s->row_doc ? s->n_rows * 8 : 0);
+    return OC_OK;
+}
+
+// ------------------------------------------------------------------------------------ search()
+// bm25.rs:78-82, evaluated on the host with libm (the same log1pf the oracle uses)
+static inline float host_idf(float total_documents, uint64_t corpus_df) {
+    const float df = (float)corpus_df;
+    const float ratio = (total_documents - df + 0.5f) / (df + 0.5f);
+    return log1pf(ratio);
+}
+
+template <bool MULTI, bool THRESH, bool OMC>
+static int launch_tile_t(oc_ctx *c, const Bm25Params &bp, uint32_t grid, size_t smem) {
+    static bool configured = false;
+    if (!configured) {
+        CU(cudaFuncSetAttribute(bm25_tile_kernel<MULTI, THRESH, OMC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured = true;
+    }
+    bm25_tile_kernel<MULTI, THRESH, OMC><<<grid, BM25_THREADS, smem, c->stream>>>(bp);
+    launched(c);
+    CU(cudaGetLastError());
+    return OC_OK;
+}
+static int launch_tile(oc_ctx *c, const Bm25Params &bp, uint32_t grid, bool multi, bool thr, bool omc) {
+    const size_t smem = bm25_smem_bytes(multi, thr, omc, bp.cap);
+    const int sel = (multi ? 4 : 0) | (thr ? 2 : 0) | (omc ? 1 : 0);
+    switch (sel) {
+        case 0: return launch_tile_t<false, false, false>(c, bp, grid, smem);
+        case 1: return launch_tile_t<false, false, true>(c, bp, grid, smem);
+        case 2: return launch_tile_t<false, true, false>(c, bp, grid, smem);
+        case 3: return launch_tile_t<false, true, true>(c, bp, grid, smem);
+        case 4: return launch_tile_t<true, false, false>(c, bp, grid, smem);
+        case 5: return launch_tile_t<true, false, true>(c, bp, grid, smem);
+        case 6: return launch_tile_t<true, true, false>(c, bp, grid, smem);
+        default: return launch_tile_t<true, true, true>(c, bp, grid, smem);
+    }
+}
+
+#include "shard.cuh"
+
+extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_params *p, uint64_t *out_doc_ids,
+                         float *out_scores, uint32_t *out_n, uint64_t *out_count) {
+    if (!c || !p || !out_doc_ids || !out_scores || !out_n || !out_count) return fail(OC_ERR_INVALID, "NULL argument");
+    const uint32_t B = p->n_queries;
+    if (B == 0) return OC_OK;
+    const bool has_v = p->mode == OC_MODE_VECTOR || p->mode == OC_MODE_HYBRID;
+    const bool has_ft = p->mode == OC_MODE_FULLTEXT || p->mode == OC_MODE_HYBRID;
+    if (!has_v && !has_ft) return fail(OC_ERR_INVALID, "unknown mode %d", p->mode);
+    if (has_v && (!emb || !p->q_vecs)) return fail(OC_ERR_INVALID, "vector/hybrid mode needs emb and q_vecs");
+    if (has_ft && (!str || !p->q_token_offsets)) return fail(OC_ERR_INVALID, "fulltext/hybrid mode needs str and tokens");
+    if (emb && emb->ctx != c) return fail(OC_ERR_INVALID, "emb belongs to another ctx");
+    if (str && str->ctx != c) return fail(OC_ERR_INVALID, "str belongs to another ctx");
+    if (p->limit == 0) return fail(OC_ERR_INVALID, "limit must be >= 1");
+    const uint64_t n_keep64 = uint64_t(p->limit) + p->offset;
+    if (n_keep64 > OC_MAX_TOPK) return fail(OC_ERR_UNSUPPORTED, "limit+offset %llu > %u", (unsigned long long)n_keep64, OC_MAX_TOPK);
+    const uint32_t n_keep = (uint32_t)n_keep64;
+    const uint32_t vlimit = p->limit;  // limit_hint = limit, NOT limit+offset (search.rs:330-336)
+    if (p->sharded && !c->comm.ready()) return fail(OC_ERR_COMM, "sharded search without oc_comm_init");
+
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    begin_call(c);
+
+    // ------------------------------------------------------------ host: descriptors
+    const bool filter = p->filter_bits != nullptr;
+    const bool tombs = has_ft && str->n_deleted > 0;
+    const uint32_t n_tiles = has_ft ? (uint32_t)((str->n_rows + BM25_TILE - 1) / BM25_TILE) : 0;
+    std::vector<TermDesc> terms;
+    std::vector<TokenDesc> tokens;
+    std::vector<QueryDesc> queries;
+    std::vector<uint8_t> tok_need_df;
+    bool any_multi = false, need_df = false;
+    uint64_t postings_walked = 0;
+    const bool thr = p->threshold >= 0.0f;
+    if (has_ft) {
+        const float N = (float)str->document_count;  // token_score.rs:221
+        queries.resize(B);
+        for (uint32_t q = 0; q < B; q++) {
+            const uint32_t t0 = p->q_token_offsets[q], t1 = p->q_token_offsets[q + 1];
+            QueryDesc qd{};
+            qd.token_begin = (uint32_t)tokens.size();
+            const uint32_t ntok = t1 - t0;
+            qd.required = thr ? (uint32_t)floorf((float)ntok * p->threshold) : 0;  // token_score.rs:211-218
+            qd.flags = thr ? QF_THRESHOLD : 0;
+            for (uint32_t t = t0; t < t1; t++) {
+                TokenDesc tk{};
+                tk.term_begin = (uint32_t)terms.size();
+                tk.bit = 1u << ((t - t0) & 31u);
+                uint64_t df_known = 0;
+                for (uint32_t e = p->token_term_offsets[t]; e < p->token_term_offsets[t + 1]; e++) {
+                    const uint32_t fi = p->term_field[e], ti = p->term_id[e];
+                    if (fi >= str->fields.size()) return fail(OC_ERR_INVALID, "term field %u out of range", fi);
+                    const StrField &f = str->fields[fi];
+                    if (ti >= f.n_terms) continue;  // unknown term: no postings
+                    TermDesc td{};
+                    td.ptr = f.post + f.term_offsets[ti];
+                    td.len = (uint32_t)(f.term_offsets[ti + 1] - f.term_offsets[ti]);
+                    td.weight = p->term_weight ? p->term_weight[e] : 1.0f;
+                    td.avg_len = f.avg_len;
+                    df_known = f.global_df.empty() ? td.len : f.global_df[ti];
+                    postings_walked += td.len;
+                    terms.push_back(td);
+                }
+                tk.term_end = (uint32_t)terms.size();
+                const uint32_t nt = tk.term_end - tk.term_begin;
+                uint8_t need = 0;
+                if (nt == 1 && !filter && !tombs) tk.idf = host_idf(N, std::max<uint64_t>(1, df_known));
+                else if (nt == 0) tk.idf = host_idf(N, 1);
+                else { need = 1; need_df = true; tk.idf = 0.f; }
+                if (nt != 1) { any_multi = any_multi || nt > 1; }
+                tokens.push_back(tk);
+                tok_need_df.push_back(need);
+            }
+            qd.token_end = (uint32_t)tokens.size();
+            queries[q] = qd;
+        }
+        if (need_df && p->sharded) return fail(OC_ERR_UNSUPPORTED, "sharded search with filters/multi-term tokens needs a df all-reduce (not built)");
+    }
+    // OMC rows for the tile kernel (string rows, ascending)
+    std::vector<uint32_t> omc_rows; std::vector<float> omc_row_mult;
+    const uint32_t n_omc = (uint32_t)p->n_omc;
+    if (n_omc && (!p->omc_doc_ids || !p->omc_mult)) return fail(OC_ERR_INVALID, "omc arrays are NULL");
+    if (n_omc && has_ft) {
+        for (uint32_t i = 0; i < n_omc; i++) {
+            if (i && p->omc_doc_ids[i] <= p->omc_doc_ids[i - 1]) return fail(OC_ERR_INVALID, "omc_doc_ids must be ascending");
+            uint64_t r;
+            if (str->row_doc_host.empty()) { r = p->omc_doc_ids[i]; if (r >= str->n_rows) continue; }
+            else {
+                auto it = std::lower_bound(str->row_doc_host.begin(), str->row_doc_host.end(), p->omc_doc_ids[i]);
+                if (it == str->row_doc_host.end() || *it != p->omc_doc_ids[i]) continue;
+                r = uint64_t(it - str->row_doc_host.begin());
+            }
+            omc_rows.push_back((uint32_t)r); omc_row_mult.push_back(p->omc_mult[i]);
+        }
+    }
+    const bool omc_tile = !omc_rows.empty();
+
+    // ------------------------------------------------------------ H2D: one packed blob
+    Packer pk;
+    const size_t o_qv = has_v ? pk.add(p->q_vecs, size_t(B) * emb->dim * 4) : 0;
+    const size_t fwords = filter ? (p->filter_nbits + 63) / 64 : 0;
+    const size_t o_flt = filter ? pk.add(p->filter_bits, fwords * 8) : 0;
+    const size_t o_terms = has_ft ? pk.add(terms.data(), terms.size() * sizeof(TermDesc)) : 0;
+    const size_t o_tokens = has_ft ? pk.add(tokens.data(), tokens.size() * sizeof(TokenDesc)) : 0;
+    const size_t o_queries = has_ft ? pk.add(queries.data(), queries.size() * sizeof(QueryDesc)) : 0;
+    const size_t o_omcd = n_omc ? pk.add(p->omc_doc_ids, size_t(n_omc) * 8) : 0;
+    const size_t o_omcm = n_omc ? pk.add(p->omc_mult, size_t(n_omc) * 4) : 0;
+    const size_t o_omcr = omc_tile ? pk.add(omc_rows.data(), omc_rows.size() * 4) : 0;
+    const size_t o_omcrm = omc_tile ? pk.add(omc_row_mult.data(), omc_row_mult.size() * 4) : 0;
+    OCTRY(c->h_in.ensure(pk.blob.size() + 256));
+    OCTRY(c->in_blob.ensure(pk.blob.size() + 256));
+    memcpy(c->h_in.p, pk.blob.data(), pk.blob.size());
+    CU(cudaEventRecord(c->ev[EV_START], c->stream));
+    if (!pk.blob.empty()) CU(cudaMemcpyAsync(c->in_blob.p, c->h_in.p, pk.blob.size(), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaEventRecord(c->ev[EV_H2D], c->stream));
+    c->timing.h2d_bytes = pk.blob.size();
+    uint8_t *din = c->in_blob.as<uint8_t>();
+    const uint64_t *filter_dev = filter ? reinterpret_cast<const uint64_t *>(din + o_flt) : nullptr;
+
+    // ------------------------------------------------------------ vector stage
+    if (has_v) {
+        OCTRY(run_vector_stage(c, emb, reinterpret_cast<const float *>(din + o_qv), B, vlimit, p->similarity, filter_dev,
+                               p->filter_nbits));
+    }
+
+    // ------------------------------------------------------------ fulltext stage
+    const uint32_t cap = next_pow2(n_keep + BM25_CHUNK);
+    Bm25Params bp{};
+    float *min_hint_dev = nullptr;
+    if (has_ft) {
+        CU(cudaEventRecord(c->ev[EV_BM0], c->stream));
+        const uint64_t ok_words = uint64_t(n_tiles) * (BM25_TILE / 32);
+        const uint32_t *row_ok = nullptr;
+        if (filter || tombs) {
+            OCTRY(c->row_ok.ensure(ok_words * 4));
+            rows_ok_kernel<<<(unsigned)((ok_words + 255) / 256), 256, 0, c->stream>>>(
+                str->row_doc, str->n_rows, tombs ? str->alive : nullptr, filter_dev, p->filter_nbits,
+                c->row_ok.as<uint32_t>(), ok_words);
+            launched(c);
+            row_ok = c->row_ok.as<uint32_t>();
+        }
+        const size_t n_td = terms.size();
+        OCTRY(c->seg.ensure((n_td * (size_t(n_tiles) + 1) + 1) * 4));
+        if (n_td) {
+            const uint64_t work = uint64_t(n_td) * (n_tiles + 1);
+            bm25_plan_kernel<<<(unsigned)((work + 255) / 256), 256, 0, c->stream>>>(
+                reinterpret_cast<const TermDesc *>(din + o_terms), (uint32_t)n_td, n_tiles, c->seg.as<uint32_t>());
+            launched(c);
+        }
+        if (need_df) {
+            // corpus_df by counting (token_score.rs:262-275), then idf on the host
+            const size_t ntok = tokens.size();
+            OCTRY(c->df_dev.ensure(ntok * 4));
+            CU(cudaMemsetAsync(c->df_dev.p, 0, ntok * 4, c->stream));
+            DfParams dp{};
+            dp.terms = reinterpret_cast<const TermDesc *>(din + o_terms);
+            dp.tokens = reinterpret_cast<const TokenDesc *>(din + o_tokens);
+            dp.n_tokens = (uint32_t)ntok; dp.n_tiles = n_tiles; dp.seg = c->seg.as<uint32_t>();
+            dp.row_ok_bits = row_ok; dp.df = c->df_dev.as<unsigned int>();
+            if (n_tiles) {
+                bm25_df_kernel<<<(unsigned)(uint64_t(n_tiles) * ntok), BM25_THREADS, 0, c->stream>>>(dp);
+                launched(c);
+            }
+            std::vector<uint32_t> dfh(ntok);
+            CU(cudaMemcpyAsync(dfh.data(), c->df_dev.p, ntok * 4, cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+            const float N = (float)str->document_count;
+            for (size_t t = 0; t < ntok; t++)
+                if (tok_need_df[t]) tokens[t].idf = host_idf(N, std::max<uint32_t>(1u, dfh[t]));
+            CU(cudaMemcpyAsync(din + o_tokens, tokens.data(), ntok * sizeof(TokenDesc), cudaMemcpyHostToDevice, c->stream));
+        }
+        // hybrid: vector hits -> string rows
+        if (has_v) {
+            OCTRY(c->v_srow.ensure(size_t(B) * vlimit * 4));
+            OCTRY(c->v_ft.ensure(size_t(B) * vlimit * 4));
+            OCTRY(c->v_present.ensure(size_t(B) * vlimit));
+            map_docs_to_rows_kernel<<<(B * vlimit + 255) / 256, 256, 0, c->stream>>>(
+                c->v_doc.as<uint64_t>(), c->v_cnt.as<uint32_t>(), vlimit, B, str->row_doc, str->n_rows, c->v_srow.as<uint32_t>());
+            launched(c);
+            CU(cudaMemsetAsync(c->v_ft.p, 0, size_t(B) * vlimit * 4, c->stream));
+            CU(cudaMemsetAsync(c->v_present.p, 0, size_t(B) * vlimit, c->stream));
+        }
+        const size_t slots = size_t(B) * std::max<uint32_t>(n_tiles, 1);
+        OCTRY(c->tau.ensure(size_t(B) * 8));
+        OCTRY(c->cand_key.ensure(slots * n_keep * 8));
+        OCTRY(c->cand_ft.ensure(slots * n_keep * 4));
+        OCTRY(c->cand_cnt.ensure(slots * 4));
+        OCTRY(c->tile_cnt.ensure(slots * 4));
+        OCTRY(c->tile_max.ensure(slots * 4));
+        OCTRY(c->tile_min.ensure(slots * 4));
+        OCTRY(c->min_hint.ensure(size_t(B) * 8));
+        min_hint_dev = c->min_hint.as<float>();
+        CU(cudaMemsetAsync(c->min_hint.p, 0, size_t(B) * 8, c->stream));
+        bp.terms = reinterpret_cast<const TermDesc *>(din + o_terms);
+        bp.tokens = reinterpret_cast<const TokenDesc *>(din + o_tokens);
+        bp.queries = reinterpret_cast<const QueryDesc *>(din + o_queries);
+        bp.seg = c->seg.as<uint32_t>();
+        bp.n_queries = B; bp.n_tiles = n_tiles; bp.n_rows = str->n_rows;
+        bp.k = p->bm25_k; bp.b = p->bm25_b;
+        bp.row_ok_bits = row_ok;
+        bp.omc_row = omc_tile ? reinterpret_cast<const uint32_t *>(din + o_omcr) : nullptr;
+        bp.omc_mult = omc_tile ? reinterpret_cast<const float *>(din + o_omcrm) : nullptr;
+        bp.n_omc = (uint32_t)omc_rows.size();
+        bp.v_row = has_v ? c->v_srow.as<uint32_t>() : nullptr;
+        bp.v_stride = vlimit;
+        bp.v_ft = c->v_ft.as<float>(); bp.v_present = c->v_present.as<uint8_t>();
+        bp.min_hint = min_hint_dev;
+        bp.n_keep = n_keep; bp.cap = cap;
+        bp.tau = c->tau.as<unsigned long long>();
+        bp.cand_key = c->cand_key.as<uint64_t>(); bp.cand_ft = c->cand_ft.as<float>();
+        bp.cand_cnt = c->cand_cnt.as<uint32_t>(); bp.tile_count = c->tile_cnt.as<uint32_t>();
+        bp.tile_max = c->tile_max.as<float>(); bp.tile_min = c->tile_min.as<float>();
+        bp.tile_first = 0;
+        CU(cudaMemsetAsync(c->tau.p, 0, size_t(B) * 8, c->stream));
+        if (n_tiles) OCTRY(launch_tile(c, bp, n_tiles * B, any_multi, thr, omc_tile));
+        CU(cudaEventRecord(c->ev[EV_BM1], c->stream));
+        c->timing.bm25_postings = postings_walked;
+    }
+
+    // ------------------------------------------------------------ fusion + top-n (+ shard exchange)
+    const size_t o_doc = 0, o_sc = size_t(B) * p->limit * 8, o_n = o_sc + size_t(B) * p->limit * 4;
+    const size_t o_cnt = (o_n + size_t(B) * 4 + 7) & ~size_t(7), o_min = o_cnt + size_t(B) * 8;
+    const size_t out_bytes = o_min + size_t(B) * 4;
+    OCTRY(c->out_blob.ensure(out_bytes));
+    OCTRY(c->h_out.ensure(out_bytes));
+    uint8_t *dout = c->out_blob.as<uint8_t>();
+    FuseParams fp{};
+    fp.mode = p->mode; fp.n_tiles = n_tiles; fp.n_keep = n_keep; fp.limit = p->limit; fp.offset = p->offset;
+    fp.capb = std::max<uint32_t>(2048, next_pow2(2 * n_keep));
+    if (has_ft) {
+        fp.cand_key = bp.cand_key; fp.cand_ft = bp.cand_ft; fp.cand_cnt = bp.cand_cnt; fp.tile_count = bp.tile_count;
+        fp.tile_max = bp.tile_max; fp.tile_min = bp.tile_min; fp.str_row_doc_ids = str->row_doc;
+    }
+    if (has_v) {
+        fp.v_doc = c->v_doc.as<uint64_t>(); fp.v_score = c->v_score.as<float>(); fp.v_count = c->v_cnt.as<uint32_t>();
+        fp.v_row = has_ft ? c->v_srow.as<uint32_t>() : nullptr;
+        fp.v_ft = c->v_ft.as<float>(); fp.v_present = c->v_present.as<uint8_t>();
+    }
+    fp.v_stride = vlimit;
+    fp.omc_doc = n_omc ? reinterpret_cast<const uint64_t *>(din + o_omcd) : nullptr;
+    fp.omc_mult = n_omc ? reinterpret_cast<const float *>(din + o_omcm) : nullptr;
+    fp.n_omc = n_omc;
+    fp.out_doc = reinterpret_cast<uint64_t *>(dout + o_doc); fp.out_score = reinterpret_cast<float *>(dout + o_sc);
+    fp.out_n = reinterpret_cast<uint32_t *>(dout + o_n); fp.out_count = reinterpret_cast<unsigned long long *>(dout + o_cnt);
+    fp.out_min = reinterpret_cast<float *>(dout + o_min);
+    const size_t fuse_smem = size_t(fp.capb) * 8 + size_t(vlimit) * 8 + 64;
+    static bool fuse_cfg = false;
+    if (!fuse_cfg) { CU(cudaFuncSetAttribute(fuse_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); fuse_cfg = true; }
+
+    bool did_comm = false;
+    if (p->sharded && c->comm.world > 1) {
+        CU(cudaEventRecord(c->ev[EV_FUSE0], c->stream));
+        OCTRY(run_sharded_merge(c, p, fp, bp, has_ft, has_v, B, n_keep, vlimit));
+        CU(cudaEventRecord(c->ev[EV_FUSE1], c->stream));
+        did_comm = true;
+    } else {
+        CU(cudaEventRecord(c->ev[EV_FUSE0], c->stream));
+        fuse_topk_kernel<<<B, 256, fuse_smem, c->stream>>>(fp);
+        launched(c);
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(c->ev[EV_FUSE1], c->stream));
+    }
+    CU(cudaEventRecord(c->ev[EV_DEV], c->stream));
+    CU(cudaMemcpyAsync(c->h_out.p, dout, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaEventRecord(c->ev[EV_D2H], c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    uint8_t *h = c->h_out.as<uint8_t>();
+
+    // rank-proxy validation: with OMC multipliers the tile ranking assumed min == min_hint (0);
+    // a negative global min changes the order of (ft - min) * omc -> rerun with the real min.
+    if (!did_comm && p->mode == OC_MODE_HYBRID && omc_tile && n_tiles) {
+        const float *mins = reinterpret_cast<const float *>(h + o_min);
+        bool redo = false;
+        for (uint32_t q = 0; q < B; q++) redo = redo || mins[q] < 0.f;
+        if (redo) {
+            CU(cudaMemcpyAsync(min_hint_dev, mins, size_t(B) * 4, cudaMemcpyHostToDevice, c->stream));
+            CU(cudaMemsetAsync(c->tau.p, 0, size_t(B) * 8, c->stream));
+            OCTRY(launch_tile(c, bp, n_tiles * B, any_multi, thr, omc_tile));
+            fuse_topk_kernel<<<B, 256, fuse_smem, c->stream>>>(fp);
+            launched(c);
+            CU(cudaMemcpyAsync(c->h_out.p, dout, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+        }
+    }
+    c->timing.d2h_bytes = out_bytes;
+    memcpy(out_doc_ids, h + o_doc, size_t(B) * p->limit * 8);
+    memcpy(out_scores, h + o_sc, size_t(B) * p->limit * 4);
+    memcpy(out_n, h + o_n, size_t(B) * 4);
+    memcpy(out_count, h + o_cnt, size_t(B) * 8);
+    return finish_timing(c, has_v && emb->n_rows > 0, has_ft, true, did_comm);
+}

@@ -1,0 +1,287 @@
+"""Host-side mirror of the reference's read-side scoring interface over the C ABI.
+
+Names and argument meaning follow the reference (oramasearch/oramacore @ 666ab48):
+  * EmbeddingFieldStorage  — read/index/embedding_field.rs:29-34 (insert :232, delete :240,
+                             search :250-278, info/stats :303-310)
+  * VectorSearchParams     — read/index/committed_field/vector.rs:10-15
+  * StringFieldStorage set — read/index/string_field.rs (one oc_str per Index)
+  * TokenScoreParams / TokenScoreContext.execute — read/index/token_score.rs:31-41, 460-509
+  * search()               — the CollectionManager search surface restricted to the hot path
+                             (read/search.rs:283-501): mode = fulltext | vector | hybrid.
+All compute happens in liboramacore_b200.so on the GPU; nothing here scores on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import OcError, SearchParams, Timing, check, lib
+from .types import (BM25_B, BM25_K, MODE_FULLTEXT, MODE_HYBRID, MODE_VECTOR, SearchHits, StringIndexData,
+                    TextQuery)
+
+# Model::dimensions / rescale_score (python/embeddings.rs:52-92)
+MODEL_DIMS = {
+    "BGESmall": 384, "BGEBase": 768, "BGELarge": 1024, "JinaEmbeddingsV2BaseCode": 768,
+    "MultilingualE5Small": 384, "MultilingualE5Base": 768, "MultilingualE5Large": 1024,
+    "MultilingualMiniLML12V2": 384,
+}
+E5_MODELS = {"MultilingualE5Small", "MultilingualE5Base", "MultilingualE5Large"}
+
+
+def _p(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One GPU + stream + workspace (oc_ctx). One per process, like one rank per GPU."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        check(lib().oc_init(device, C.byref(self._h)))
+        self.device = device
+
+    def close(self):
+        if self._h:
+            lib().oc_shutdown(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def device_info(self):
+        sm = C.c_int()
+        mem = C.c_size_t()
+        name = C.create_string_buffer(256)
+        check(lib().oc_device_info(self._h, C.byref(sm), C.byref(mem), name, 256))
+        return {"sm_count": sm.value, "hbm_bytes": mem.value, "name": name.value.decode()}
+
+    def last_timing(self) -> dict:
+        t = Timing()
+        check(lib().oc_last_timing(self._h, C.byref(t)))
+        return t.as_dict()
+
+    def launch_count(self) -> int:
+        return int(lib().oc_launch_count(self._h))
+
+    # ---- document-sharded multi-GPU
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = (C.c_uint8 * _lib.OC_COMM_ID_BYTES)()
+        check(lib().oc_comm_unique_id(buf))
+        return bytes(buf)
+
+    def comm_init(self, world_size: int, rank: int, unique_id: bytes):
+        buf = (C.c_uint8 * _lib.OC_COMM_ID_BYTES).from_buffer_copy(unique_id)
+        check(lib().oc_comm_init(self._h, world_size, rank, buf))
+
+
+@dataclass
+class VectorSearchParams:
+    """committed_field/vector.rs:10-15"""
+    target: np.ndarray
+    similarity: float
+    limit: int
+    filtered_doc_ids: Optional[np.ndarray] = None  # bitmap over DocumentId (uint64 words)
+    filter_nbits: int = 0
+
+
+class EmbeddingFieldStorage:
+    """embedding_field.rs:29-34 — cosine metric, device resident."""
+
+    def __init__(self, ctx: Context, model: str = "BGEBase", dim: Optional[int] = None):
+        self.ctx = ctx
+        self.model = model
+        self.dim = int(dim if dim is not None else MODEL_DIMS[model])
+        self._h = C.c_void_p()
+        check(lib().oc_emb_create(ctx._h, self.dim, 0, 1 if model in E5_MODELS else 0, C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().oc_emb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def reserve(self, n_rows: int):
+        check(lib().oc_emb_reserve(self._h, n_rows))
+
+    def insert(self, doc_id: int, vectors: Sequence[Sequence[float]]):
+        """insert(DocumentId, Vec<Vec<f32>>) — several chunks per document (embedding_field.rs:232-237)."""
+        v = np.ascontiguousarray(np.asarray(vectors, np.float32).reshape(-1, self.dim))
+        self.insert_batch(np.full(v.shape[0], doc_id, np.uint64), v)
+
+    def insert_batch(self, doc_ids: np.ndarray, rows: np.ndarray):
+        d = np.ascontiguousarray(doc_ids, np.uint64)
+        r = np.ascontiguousarray(rows, np.float32)
+        assert r.ndim == 2 and r.shape[1] == self.dim and r.shape[0] == d.shape[0]
+        check(lib().oc_emb_insert(self._h, _p(d), _p(r), d.shape[0]))
+
+    def delete(self, doc_id: int):
+        d = np.asarray([doc_id], np.uint64)
+        check(lib().oc_emb_delete(self._h, _p(d), 1))
+
+    def info(self) -> dict:
+        i = _lib.EmbInfo()
+        check(lib().oc_emb_info(self._h, C.byref(i)))
+        return {"num_embeddings": i.num_embeddings, "num_rows": i.num_rows, "dimensions": i.dimensions,
+                "device_bytes": i.device_bytes}
+
+    def search_batch(self, targets: np.ndarray, limit: int, similarity: float,
+                     filter_bits: Optional[np.ndarray] = None, filter_nbits: int = 0):
+        q = np.ascontiguousarray(targets, np.float32).reshape(-1, self.dim)
+        B = q.shape[0]
+        docs = np.zeros((B, limit), np.uint64)
+        scores = np.zeros((B, limit), np.float32)
+        counts = np.zeros(B, np.uint32)
+        fb = None if filter_bits is None else np.ascontiguousarray(filter_bits, np.uint64)
+        check(lib().oc_emb_search(self._h, _p(q), B, limit, similarity, _p(fb), int(filter_nbits),
+                                  _p(docs), _p(scores), _p(counts)))
+        return docs, scores, counts
+
+    def search(self, params: VectorSearchParams, output: Dict[int, float]) -> None:
+        """EmbeddingFieldStorage::search(&VectorSearchParams, &mut HashMap) — `output[doc] += score`."""
+        docs, scores, counts = self.search_batch(params.target, params.limit, params.similarity,
+                                                 params.filtered_doc_ids, params.filter_nbits)
+        for i in range(int(counts[0])):
+            d = int(docs[0, i])
+            output[d] = np.float32(output.get(d, np.float32(0.0)) + scores[0, i])
+
+
+class StringFieldStorage:
+    """All string fields of one Index on the device (string_field.rs:32-36); built from
+    committed postings (`StringIndexData`)."""
+
+    def __init__(self, ctx: Context, data: StringIndexData, global_df: Optional[List[np.ndarray]] = None):
+        self.ctx = ctx
+        self.data = data
+        self._h = C.c_void_p()
+        check(lib().oc_str_create(ctx._h, len(data.fields), C.byref(self._h)))
+        rd = None if data.row_doc_ids is None else np.ascontiguousarray(data.row_doc_ids, np.uint64)
+        check(lib().oc_str_set_rows(self._h, int(data.n_rows), _p(rd), int(data.document_count)))
+        for i, f in enumerate(data.fields):
+            f.validate()
+            gdf = None if global_df is None else np.ascontiguousarray(global_df[i], np.uint32)
+            check(lib().oc_str_load_field(self._h, i, float(f.avg_field_len), f.n_terms,
+                                          _p(np.ascontiguousarray(f.term_offsets)), _p(np.ascontiguousarray(f.post_row)),
+                                          _p(np.ascontiguousarray(f.post_tf)), _p(np.ascontiguousarray(f.post_len)),
+                                          _p(gdf)))
+
+    def close(self):
+        if self._h:
+            lib().oc_str_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def delete(self, doc_id: int):
+        d = np.asarray([doc_id], np.uint64)
+        check(lib().oc_str_delete(self._h, _p(d), 1))
+
+    def info(self) -> dict:
+        i = _lib.StrInfo()
+        check(lib().oc_str_info(self._h, C.byref(i)))
+        return {"total_documents": i.total_documents, "total_postings": i.total_postings,
+                "unique_terms_count": i.unique_terms_count, "n_fields": i.n_fields, "device_bytes": i.device_bytes}
+
+
+@dataclass
+class TokenScoreParams:
+    """token_score.rs:31-41 (mode already resolved; boost/properties are folded into the
+    resolved TextQuery by the host-side term resolution)."""
+    mode: int
+    limit_hint: int = 10
+    offset: int = 0
+    similarity: float = 0.7          # types.rs:881-885
+    threshold: Optional[float] = None
+    filtered_doc_ids: Optional[np.ndarray] = None
+    filter_nbits: int = 0
+    omc_doc_ids: Optional[np.ndarray] = None   # ascending
+    omc_mult: Optional[np.ndarray] = None
+    sharded: bool = False
+
+
+class TokenScoreContext:
+    """token_score.rs:49-57 + execute :460-509, fused with OMC, count and top-N.
+
+    execute_batch() is the GPU drop-in: it returns, per query, the top (limit) hits after
+    offset and the total match count — what search_on_indexes derives from the score map
+    (search.rs:482-498) — instead of materialising the whole HashMap on the host."""
+
+    def __init__(self, ctx: Context, embedding_field: Optional[EmbeddingFieldStorage],
+                 string_fields: Optional[StringFieldStorage]):
+        self.ctx, self.emb, self.str = ctx, embedding_field, string_fields
+
+    def execute_batch(self, params: TokenScoreParams, texts: Optional[Sequence[TextQuery]] = None,
+                      q_vecs: Optional[np.ndarray] = None) -> List[SearchHits]:
+        B = len(texts) if texts is not None else int(np.asarray(q_vecs).reshape(-1, self.emb.dim).shape[0])
+        sp = SearchParams()
+        sp.mode = params.mode
+        sp.n_queries = B
+        sp.limit, sp.offset = params.limit_hint, params.offset
+        sp.similarity = params.similarity
+        sp.threshold = -1.0 if params.threshold is None else params.threshold
+        sp.bm25_k, sp.bm25_b = BM25_K, BM25_B
+        keep = []
+        if params.mode in (MODE_VECTOR, MODE_HYBRID):
+            qv = np.ascontiguousarray(q_vecs, np.float32).reshape(B, self.emb.dim)
+            keep.append(qv)
+            sp.q_vecs = _p(qv)
+        if params.mode in (MODE_FULLTEXT, MODE_HYBRID):
+            qoff = np.zeros(B + 1, np.uint32)
+            tto, tf_, tid, tw = [np.zeros(1, np.uint32)], [], [], []
+            ntok = 0
+            nterm = 0
+            for i, t in enumerate(texts):
+                ntok += t.n_tokens
+                qoff[i + 1] = ntok
+                tto.append(t.token_term_offsets[1:].astype(np.uint32) + np.uint32(nterm))
+                nterm += int(t.token_term_offsets[-1])
+                tf_.append(t.term_field); tid.append(t.term_id); tw.append(t.term_weight)
+            a_tto = np.ascontiguousarray(np.concatenate(tto), np.uint32)
+            a_tf = np.ascontiguousarray(np.concatenate(tf_) if tf_ else np.zeros(0), np.uint32)
+            a_tid = np.ascontiguousarray(np.concatenate(tid) if tid else np.zeros(0), np.uint32)
+            a_tw = np.ascontiguousarray(np.concatenate(tw) if tw else np.zeros(0), np.float32)
+            keep += [qoff, a_tto, a_tf, a_tid, a_tw]
+            sp.q_token_offsets, sp.token_term_offsets = _p(qoff), _p(a_tto)
+            sp.term_field, sp.term_id, sp.term_weight = _p(a_tf), _p(a_tid), _p(a_tw)
+        if params.filtered_doc_ids is not None:
+            fb = np.ascontiguousarray(params.filtered_doc_ids, np.uint64)
+            keep.append(fb)
+            sp.filter_bits, sp.filter_nbits = _p(fb), int(params.filter_nbits)
+        if params.omc_doc_ids is not None and len(params.omc_doc_ids):
+            od = np.ascontiguousarray(params.omc_doc_ids, np.uint64)
+            om = np.ascontiguousarray(params.omc_mult, np.float32)
+            keep += [od, om]
+            sp.omc_doc_ids, sp.omc_mult, sp.n_omc = _p(od), _p(om), od.shape[0]
+        sp.sharded = 1 if params.sharded else 0
+        docs = np.zeros((B, params.limit_hint), np.uint64)
+        scores = np.zeros((B, params.limit_hint), np.float32)
+        n = np.zeros(B, np.uint32)
+        cnt = np.zeros(B, np.uint64)
+        check(lib().oc_search(self.ctx._h, self.emb._h if self.emb else None, self.str._h if self.str else None,
+                              C.byref(sp), _p(docs), _p(scores), _p(n), _p(cnt)))
+        self.last_raw = (docs, scores, n, cnt)
+        return [SearchHits(docs[i, :n[i]].copy(), scores[i, :n[i]].copy(), int(cnt[i])) for i in range(B)]
+
+    def execute(self, params: TokenScoreParams, results: Dict[int, float], text: Optional[TextQuery] = None,
+                q_vec: Optional[np.ndarray] = None) -> int:
+        """Reference-shaped call: `results.extend(scores)` for one query; returns the match count.
+        Only the top (limit_hint + offset) entries are materialised (the rest never leave the GPU)."""
+        p = TokenScoreParams(**{**params.__dict__, "limit_hint": params.limit_hint + params.offset, "offset": 0})
+        hits = self.execute_batch(p, None if text is None else [text], q_vec)[0]
+        for d, s in zip(hits.doc_ids, hits.scores):
+            results[int(d)] = np.float32(s)
+        return hits.count
+
+
+def search(ctx: Context, emb: Optional[EmbeddingFieldStorage], strs: Optional[StringFieldStorage], mode: str,
+           texts: Optional[Sequence[TextQuery]] = None, q_vecs: Optional[np.ndarray] = None, limit: int = 10,
+           offset: int = 0, similarity: float = 0.7, threshold: Optional[float] = None, **kw) -> List[SearchHits]:
+    """search() surface of the hot path: mode = "fulltext" | "vector" | "hybrid" (types.rs:924-999;
+    "default" == fulltext)."""
+    m = {"fulltext": MODE_FULLTEXT, "default": MODE_FULLTEXT, "vector": MODE_VECTOR, "hybrid": MODE_HYBRID}[mode]
+    p = TokenScoreParams(mode=m, limit_hint=limit, offset=offset, similarity=similarity, threshold=threshold, **kw)
+    return TokenScoreContext(ctx, emb, strs).execute_batch(p, texts, q_vecs)
