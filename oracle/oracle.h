@@ -99,7 +99,10 @@ typedef struct {
     const uint64_t *row_doc_ids;/* NULL => doc_id == row                */
     const uint8_t *deleted;     /* NULL or n_rows flags                 */
     int is_e5;
+    const float *row_norms;     /* NULL or precomputed |x| per row (orc_row_norms) */
 } orc_emb_store;
+/* |x| per row with the same fp32 blocked summation the scan uses. */
+void orc_row_norms(const float *rows, uint64_t n_rows, uint32_t dim, float *out);
 
 /* EmbeddingFieldStorage::search: exact top-`limit` by cosine distance, then
  * similarity = 1 - distance, rescale, keep >= similarity, output[doc] += score. */

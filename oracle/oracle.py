@@ -55,7 +55,8 @@ class _Map(C.Structure):
 
 class _EmbStore(C.Structure):
     _fields_ = [("dim", C.c_uint32), ("n_rows", C.c_uint64), ("rows", C.c_void_p),
-                ("row_doc_ids", C.c_void_p), ("deleted", C.c_void_p), ("is_e5", C.c_int)]
+                ("row_doc_ids", C.c_void_p), ("deleted", C.c_void_p), ("is_e5", C.c_int),
+                ("row_norms", C.c_void_p)]
 
 
 class _SearchReq(C.Structure):
@@ -83,6 +84,8 @@ def lib():
                                           C.c_float, C.c_float, C.c_float, C.c_float]
         L.orc_rescale_score.restype = C.c_float
         L.orc_rescale_score.argtypes = [C.c_float, C.c_int]
+        L.orc_row_norms.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]
+        L.orc_row_norms.restype = None
         L.orc_map_free.argtypes = [C.POINTER(_Map)]
         L.orc_fulltext.argtypes = [C.POINTER(_StrIndex), C.POINTER(_TextQuery), C.POINTER(_TextParams), C.POINTER(_Map)]
         L.orc_vector.argtypes = [C.POINTER(_EmbStore), C.c_void_p, C.c_uint32, C.c_float, C.c_void_p, C.c_uint64, C.POINTER(_Map)]
@@ -151,7 +154,9 @@ class EmbStore:
         self.rd = None if row_doc_ids is None else np.ascontiguousarray(row_doc_ids, np.uint64)
         self.dl = None if deleted is None else np.ascontiguousarray(deleted, np.uint8)
         n, d = self.rows.shape
-        self.c = _EmbStore(d, n, _p(self.rows), _p(self.rd), _p(self.dl), int(is_e5))
+        self.norms = np.zeros(n, np.float32)  # cached |x| (what any real store precomputes)
+        lib().orc_row_norms(_p(self.rows), n, d, _p(self.norms))
+        self.c = _EmbStore(d, n, _p(self.rows), _p(self.rd), _p(self.dl), int(is_e5), _p(self.norms))
 
 
 class _TQ:
