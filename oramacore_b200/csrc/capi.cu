@@ -308,10 +308,10 @@ extern "C" int oc_emb_info(oc_emb *e, oc_emb_info_t *out) {
 // ---- scan launch plumbing
 template <int NCH, int QB>
 static int launch_scan_t(oc_ctx *c, const ScanParams &sp, uint32_t grid, size_t smem) {
-    static bool configured = false;  // per instantiation
-    if (!configured) {
-        CU(cudaFuncSetAttribute(emb_scan_kernel<NCH, QB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        configured = true;
+    static size_t configured = 0;  // per instantiation
+    if (smem > configured) {
+        CU(cudaFuncSetAttribute(emb_scan_kernel<NCH, QB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
     }
     emb_scan_kernel<NCH, QB><<<grid, SCAN_THREADS, smem, c->stream>>>(sp);
     launched(c, true);
@@ -332,16 +332,19 @@ static int launch_scan_q(oc_ctx *c, const ScanParams &sp, uint32_t grid, size_t 
 }
 
 struct ScanPlan {
-    uint32_t rows_per_stage, n_stages, wcap, grid;
+    uint32_t rows_per_stage, n_stages, wcap, grid, qb_max;
 };
-static ScanPlan plan_scan(const oc_ctx *c, const oc_emb *e, uint32_t n_keep, uint32_t qb) {
+static ScanPlan plan_scan(const oc_ctx *c, const oc_emb *e, uint32_t n_keep) {
     ScanPlan pl;
+    uint32_t qb = 4;
     const uint32_t row_bytes = e->stride * 4;
     uint32_t R = (32768 / row_bytes) / 8 * 8;
     if (R < 8) R = 8;
     pl.rows_per_stage = R;
     pl.wcap = std::max<uint32_t>(32, next_pow2(2 * n_keep));
     const size_t budget = 227 * 1024 - 1024;
+    while (qb > 1 && size_t(SCAN_CONSUMER_WARPS) * qb * pl.wcap * 8 > budget / 2) qb >>= 1;
+    pl.qb_max = qb;
     const size_t fixed = size_t(SCAN_CONSUMER_WARPS) * qb * pl.wcap * 8 + 256;
     const size_t per_stage = size_t(R) * row_bytes + R * 4 + 16;
     uint32_t S = (uint32_t)std::min<size_t>(8, fixed < budget ? (budget - fixed) / per_stage : 0);
@@ -378,14 +381,14 @@ static int run_vector_stage(oc_ctx *c, oc_emb *e, const float *q_dev, uint32_t B
         launched(c);
         inv_norm = c->eff_norm.as<float>();
     }
-    ScanPlan pl = plan_scan(c, e, limit, 4);
+    ScanPlan pl = plan_scan(c, e, limit);
     if (pl.n_stages < 2) return fail(OC_ERR_UNSUPPORTED, "limit %u leaves no shared memory for the scan ring", limit);
     OCTRY(c->scan_cand.ensure(size_t(B) * pl.grid * limit * 8));
     CU(cudaEventRecord(c->ev[EV_SCAN0], c->stream));
     uint32_t q0 = 0;
     while (q0 < B) {
         const uint32_t rem = B - q0;
-        const uint32_t qb = rem >= 4 ? 4 : (rem >= 2 ? 2 : 1);
+        const uint32_t qb = std::min<uint32_t>(pl.qb_max, rem >= 4 ? 4 : (rem >= 2 ? 2 : 1));
         ScanParams sp{};
         sp.rows = e->rows; sp.inv_norm = inv_norm; sp.n_rows = e->n_rows; sp.stride = e->stride;
         sp.queries = c->q_pad.as<float>() + size_t(q0) * e->stride;
@@ -407,6 +410,11 @@ static int run_vector_stage(oc_ctx *c, oc_emb *e, const float *q_dev, uint32_t B
     mp.row_doc_ids = e->row_doc; mp.rescale_e5 = e->e5; mp.similarity = similarity;
     mp.out_doc = c->v_doc.as<uint64_t>(); mp.out_score = c->v_score.as<float>(); mp.out_row = c->v_row.as<uint32_t>();
     mp.out_count = c->v_cnt.as<uint32_t>();
+    static size_t merge_cfg = 0;
+    if (size_t(mp.capb) * 8 > merge_cfg) {
+        CU(cudaFuncSetAttribute(emb_scan_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(mp.capb * 8)));
+        merge_cfg = size_t(mp.capb) * 8;
+    }
     emb_scan_merge_kernel<<<B, 256, mp.capb * 8, c->stream>>>(mp);
     launched(c);
     CU(cudaGetLastError());
@@ -607,10 +615,10 @@ static inline float host_idf(float total_documents, uint64_t corpus_df) {
 
 template <bool MULTI, bool THRESH, bool OMC>
 static int launch_tile_t(oc_ctx *c, const Bm25Params &bp, uint32_t grid, size_t smem) {
-    static bool configured = false;
-    if (!configured) {
-        CU(cudaFuncSetAttribute(bm25_tile_kernel<MULTI, THRESH, OMC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        configured = true;
+    static size_t configured = 0;  // per instantiation; static smem counts against the 227 KB cap
+    if (smem > configured) {
+        CU(cudaFuncSetAttribute(bm25_tile_kernel<MULTI, THRESH, OMC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
     }
     bm25_tile_kernel<MULTI, THRESH, OMC><<<grid, BM25_THREADS, smem, c->stream>>>(bp);
     launched(c);
@@ -880,8 +888,8 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
     fp.out_n = reinterpret_cast<uint32_t *>(dout + o_n); fp.out_count = reinterpret_cast<unsigned long long *>(dout + o_cnt);
     fp.out_min = reinterpret_cast<float *>(dout + o_min);
     const size_t fuse_smem = size_t(fp.capb) * 8 + size_t(vlimit) * 8 + 64;
-    static bool fuse_cfg = false;
-    if (!fuse_cfg) { CU(cudaFuncSetAttribute(fuse_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); fuse_cfg = true; }
+    static size_t fuse_cfg = 0;
+    if (fuse_smem > fuse_cfg) { CU(cudaFuncSetAttribute(fuse_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fuse_smem)); fuse_cfg = fuse_smem; }
 
     bool did_comm = false;
     if (p->sharded && c->comm.world > 1) {
