@@ -112,22 +112,6 @@ def make_workload(w, n_docs, batch, rank, world):
     return out
 
 
-def shard_text(data, lo, hi):
-    """Postings restricted to rows [lo,hi) with shard-local rows, global N / avg_len / df."""
-    from oramacore_b200.types import FieldPostings, StringIndexData
-    fields, gdf = [], []
-    for f in data.fields:
-        df = np.diff(f.term_offsets.astype(np.int64)).astype(np.uint32)
-        sel = (f.post_row >= lo) & (f.post_row < hi)
-        term_of = np.repeat(np.arange(f.n_terms, dtype=np.int64), df.astype(np.int64))[sel]
-        offs = np.zeros(f.n_terms + 1, np.uint64)
-        offs[1:] = np.cumsum(np.bincount(term_of, minlength=f.n_terms)).astype(np.uint64)
-        fields.append(FieldPostings(f.avg_field_len, offs, (f.post_row[sel] - np.uint32(lo)).astype(np.uint32),
-                                    f.post_tf[sel], f.post_len[sel]))
-        gdf.append(df)
-    return StringIndexData(fields, hi - lo, data.document_count, np.arange(lo, hi, dtype=np.uint64)), gdf
-
-
 def run_reference(args, w, batch, n_docs):
     """--impl reference: the reference's CPU algorithm (oracle port; the Rust reference cannot be
     built here) on all host cores, each step a bounded sample of the same workload."""
@@ -210,7 +194,8 @@ def main():
         if world == 1:
             strs = ob.StringFieldStorage(ctx, wl["data_all"])
         else:
-            sd, gdf = shard_text(wl["data_all"], lo, hi)
+            from oramacore_b200.sharding import shard_string_index
+            sd, gdf = shard_string_index(wl["data_all"], lo, hi)
             strs = ob.StringFieldStorage(ctx, sd, global_df=gdf)
     mode = {"fulltext": ob.MODE_FULLTEXT, "vector": ob.MODE_VECTOR, "hybrid": ob.MODE_HYBRID}[w["mode"]]
     tsc = ob.TokenScoreContext(ctx, emb, strs)

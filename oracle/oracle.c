@@ -179,6 +179,12 @@ static int fulltext_core(const orc_str_index *ix, const orc_text_query *q, const
 
     for (uint32_t ti = 0; ti < q->n_tokens; ti++) {
         hmap_clear(&cur); /* scorer.reset_term()/next_term() */
+        uint64_t shard_df = 0; /* sharded corpus: df of a single-term token comes from the global table */
+        if (q->token_term_offsets[ti + 1] - q->token_term_offsets[ti] == 1) {
+            uint32_t e0 = q->token_term_offsets[ti];
+            const orc_field *f0 = &ix->fields[q->term_field[e0]];
+            if (f0->global_df && q->term_id[e0] < f0->n_terms) shard_df = f0->global_df[q->term_id[e0]];
+        }
         for (uint32_t e = q->token_term_offsets[ti]; e < q->token_term_offsets[ti + 1]; e++) {
             const orc_field *f = &ix->fields[q->term_field[e]];
             uint32_t tid = q->term_id[e];
@@ -197,6 +203,7 @@ static int fulltext_core(const orc_str_index *ix, const orc_text_query *q, const
             }
         }
         uint64_t corpus_df = cur.n > 1 ? cur.n : 1; /* corpus_docs.len().max(1), token_score.rs:275 */
+        if (shard_df) corpus_df = shard_df;
         float idf = orc_idf(total_documents, corpus_df);
         uint32_t bit = 1u << (ti & 31u); /* 1 << term_index (release-mode wrapping), token_score.rs:293 */
         for (size_t i = 0; i < cur.cap; i++) {

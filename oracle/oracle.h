@@ -51,6 +51,8 @@ typedef struct {
     const uint32_t *post_row;     /* row index into row_doc_ids         */
     const uint16_t *post_tf;      /* term frequency in this field       */
     const uint16_t *post_len;     /* field_length (u16, string_field.rs:162) */
+    const uint32_t *global_df;    /* NULL, or per-term corpus df when this index is one shard of a
+                                     document-sharded corpus (single-term tokens only)          */
 } orc_field;
 
 typedef struct {

@@ -30,7 +30,7 @@ def build(force: bool = False) -> str:
 class _Field(C.Structure):
     _fields_ = [("avg_field_len", C.c_float), ("n_terms", C.c_uint32),
                 ("term_offsets", C.c_void_p), ("post_row", C.c_void_p),
-                ("post_tf", C.c_void_p), ("post_len", C.c_void_p)]
+                ("post_tf", C.c_void_p), ("post_len", C.c_void_p), ("global_df", C.c_void_p)]
 
 
 class _StrIndex(C.Structure):
@@ -131,7 +131,7 @@ def rescale_score(s: float, is_e5: bool) -> float:
 class StrIndex:
     """Keeps numpy arrays alive behind an orc_str_index."""
 
-    def __init__(self, data):  # data: oramacore_b200.types.StringIndexData (duck-typed)
+    def __init__(self, data, global_df=None):  # data: oramacore_b200.types.StringIndexData (duck-typed)
         self._keep = []
         arr = (_Field * max(1, len(data.fields)))()
         for i, f in enumerate(data.fields):
@@ -139,8 +139,9 @@ class StrIndex:
             pr = np.ascontiguousarray(f.post_row, np.uint32)
             pt = np.ascontiguousarray(f.post_tf, np.uint16)
             pl = np.ascontiguousarray(f.post_len, np.uint16)
-            self._keep += [to, pr, pt, pl]
-            arr[i] = _Field(float(f.avg_field_len), to.shape[0] - 1, _p(to), _p(pr), _p(pt), _p(pl))
+            gd = None if global_df is None else np.ascontiguousarray(global_df[i], np.uint32)
+            self._keep += [to, pr, pt, pl, gd]
+            arr[i] = _Field(float(f.avg_field_len), to.shape[0] - 1, _p(to), _p(pr), _p(pt), _p(pl), _p(gd))
         self._fields = arr
         rd = None if data.row_doc_ids is None else np.ascontiguousarray(data.row_doc_ids, np.uint64)
         self._keep.append(rd)

@@ -108,7 +108,7 @@ struct oc_ctx {
     uint64_t launches = 0;
     uint32_t call_launches = 0, call_scan_launches = 0;
     // workspaces
-    DevBuf in_blob, q_pad, q_inv, eff_norm, filter_dev, scan_cand, v_doc, v_score, v_row, v_cnt, v_srow, v_ft, v_present;
+    DevBuf in_blob, q_pad, q_inv, eff_norm, filter_dev, scan_cand, v_doc, v_score, v_row, v_cnt, v_srow, v_ft, v_present, v_raw;
     DevBuf seg, df_dev, row_ok, tau, cand_key, cand_ft, cand_cnt, tile_cnt, tile_max, tile_min, min_hint;
     DevBuf out_blob, shard_send, shard_recv;
     HostBuf h_in, h_out;
@@ -148,7 +148,7 @@ extern "C" void oc_shutdown(oc_ctx *c) {
     cudaStreamSynchronize(c->stream);
     c->comm.destroy();
     DevBuf *bufs[] = {&c->in_blob, &c->q_pad, &c->q_inv, &c->eff_norm, &c->filter_dev, &c->scan_cand, &c->v_doc,
-                      &c->v_score, &c->v_row, &c->v_cnt, &c->v_srow, &c->v_ft, &c->v_present, &c->seg, &c->df_dev,
+                      &c->v_score, &c->v_row, &c->v_cnt, &c->v_srow, &c->v_ft, &c->v_present, &c->v_raw, &c->seg, &c->df_dev,
                       &c->row_ok, &c->tau, &c->cand_key, &c->cand_ft, &c->cand_cnt, &c->tile_cnt, &c->tile_max,
                       &c->tile_min, &c->min_hint, &c->out_blob, &c->shard_send, &c->shard_recv};
     for (DevBuf *b : bufs) b->release();
@@ -362,6 +362,7 @@ static int run_vector_stage(oc_ctx *c, oc_emb *e, const float *q_dev, uint32_t B
     OCTRY(c->v_score.ensure(size_t(B) * limit * 4));
     OCTRY(c->v_row.ensure(size_t(B) * limit * 4));
     OCTRY(c->v_cnt.ensure(size_t(B) * 4));
+    OCTRY(c->v_raw.ensure(size_t(B) * limit * 4));
     if (e->n_rows == 0) {
         CU(cudaMemsetAsync(c->v_cnt.p, 0, size_t(B) * 4, c->stream));
         CU(cudaMemsetAsync(c->v_doc.p, 0, size_t(B) * limit * 8, c->stream));
@@ -409,7 +410,7 @@ static int run_vector_stage(oc_ctx *c, oc_emb *e, const float *q_dev, uint32_t B
     mp.capb = std::max<uint32_t>(2048, next_pow2(2 * limit));
     mp.row_doc_ids = e->row_doc; mp.rescale_e5 = e->e5; mp.similarity = similarity;
     mp.out_doc = c->v_doc.as<uint64_t>(); mp.out_score = c->v_score.as<float>(); mp.out_row = c->v_row.as<uint32_t>();
-    mp.out_count = c->v_cnt.as<uint32_t>();
+    mp.out_count = c->v_cnt.as<uint32_t>(); mp.out_raw = c->v_raw.as<float>();
     static size_t merge_cfg = 0;
     if (size_t(mp.capb) * 8 > merge_cfg) {
         CU(cudaFuncSetAttribute(emb_scan_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(mp.capb * 8)));
@@ -718,7 +719,7 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
             qd.token_end = (uint32_t)tokens.size();
             queries[q] = qd;
         }
-        if (need_df && p->sharded) return fail(OC_ERR_UNSUPPORTED, "sharded search with filters/multi-term tokens needs a df all-reduce (not built)");
+        if (need_df && p->sharded && c->comm.world > 1) return fail(OC_ERR_UNSUPPORTED, "sharded search with filters/multi-term tokens needs a df all-reduce (not built)");
     }
     // OMC rows for the tile kernel (string rows, ascending)
     std::vector<uint32_t> omc_rows; std::vector<float> omc_row_mult;
@@ -894,7 +895,7 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
     bool did_comm = false;
     if (p->sharded && c->comm.world > 1) {
         CU(cudaEventRecord(c->ev[EV_FUSE0], c->stream));
-        OCTRY(run_sharded_merge(c, p, fp, bp, has_ft, has_v, B, n_keep, vlimit));
+        OCTRY(run_sharded_merge(c, p, fp, has_ft ? (uint32_t)str->n_rows : 0, has_v ? (uint32_t)emb->n_rows : 0, B));
         CU(cudaEventRecord(c->ev[EV_FUSE1], c->stream));
         did_comm = true;
     } else {

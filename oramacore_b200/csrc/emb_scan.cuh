@@ -269,6 +269,7 @@ struct ScanMergeParams {
     float *out_score;    // [nq][limit]
     uint32_t *out_row;   // [nq][limit] (row index, for hybrid fusion); may be NULL
     uint32_t *out_count; // [nq]
+    float *out_raw;      // [nq][limit] rank key (-distance) of each kept hit; may be NULL
 };
 
 // Model::rescale_score (python/embeddings.rs:71-92)
@@ -309,6 +310,7 @@ __global__ void __launch_bounds__(256) emb_scan_merge_kernel(const ScanMergePara
         p.out_doc[size_t(q) * p.limit + i] = doc;
         p.out_score[size_t(q) * p.limit + i] = score;
         if (p.out_row) p.out_row[size_t(q) * p.limit + i] = row;
+        if (p.out_raw) p.out_raw[size_t(q) * p.limit + i] = (i < got && row != 0xffffffffu) ? key_score(buf[i]) : 0.f;
     }
     __syncthreads();
     if (threadIdx.x == 0) p.out_count[q] = s_cnt;

@@ -1,0 +1,52 @@
+"""Python statement of the cross-shard merge (the specification K5 / shard.cuh implements):
+inputs are per-shard oracle products, output must equal the unsharded oracle search."""
+import numpy as np
+
+f32 = np.float32
+
+
+def local_products(orc, ix, st, mode, text, qv, limit, similarity, threshold=None):
+    """What one shard contributes for one query (restated with the oracle's pieces)."""
+    out = {"count_ft": 0, "max_ft": f32(0), "min_ft": f32(0), "ft": {}, "v": []}
+    if mode in (0, 2):
+        d, s = orc.fulltext(ix, text, threshold=threshold)
+        out["count_ft"] = len(d)
+        out["ft"] = {int(a): f32(b) for a, b in zip(d, s)}
+        if len(s):
+            out["max_ft"] = max(f32(0), f32(s.max()))
+            out["min_ft"] = min(f32(0), f32(s.min()))
+    if mode in (1, 2):
+        # local top-`limit` by distance with the rank key, then rescale / threshold (kept prefix)
+        dv, sv = orc.vector(st, qv, limit, similarity)
+        for doc, score in zip(dv, sv):
+            out["v"].append((int(doc), f32(score)))
+    return out
+
+
+def merge(shards, mode, limit, offset, n_keep):
+    """shards: list of local_products (non-E5 model: rank key order == score order)."""
+    allv = sorted([v for s in shards for v in s["v"]], key=lambda t: (-t[1], t[0]))[:limit] if mode != 0 else []
+    vmap = {}
+    for d, sc in allv:
+        vmap[d] = f32(vmap.get(d, f32(0)) + sc)
+    ftall = {}
+    for s in shards:
+        ftall.update(s["ft"])
+    count = sum(s["count_ft"] for s in shards) + sum(1 for d in vmap if d not in ftall)
+    mx = max([f32(0)] + [s["max_ft"] for s in shards] + list(vmap.values()))
+    mn = min([f32(0)] + [s["min_ft"] for s in shards] + list(vmap.values()))
+    final = {}
+    if mode == 0:
+        final = dict(ftall)
+    elif mode == 1:
+        final = dict(vmap)
+    else:
+        with np.errstate(invalid="ignore", divide="ignore"):
+            den = f32(mx - mn)
+            for d, v in ftall.items():
+                final[d] = f32(f32(v - mn) / den)
+            for d, v in vmap.items():
+                final[d] = f32(final.get(d, f32(0)) + f32(f32(v - mn) / den))
+    items = sorted([(d, s) for d, s in final.items() if not np.isnan(s)], key=lambda t: (-t[1], t[0]))[:n_keep]
+    items = items[offset:offset + limit]
+    return [d for d, _ in items], [s for _, s in items], count
