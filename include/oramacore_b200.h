@@ -175,6 +175,9 @@ typedef struct {
     uint64_t scan_bytes;     /* algorithmic bytes swept by the scan kernels (rows x stride x elem) */
     uint64_t bm25_postings;  /* postings walked by the scorer (x8 B = algorithmic bytes)    */
     uint64_t h2d_bytes, d2h_bytes;
+    uint32_t scan_tensor_core;   /* 1 => the batched tcgen05 (tf32 select + exact re-score) scan ran */
+    uint32_t scan_unproven;      /* queries whose tensor-core result failed the exactness proof and were
+                                    re-run through the exact sweep                                      */
 } oc_timing;
 int oc_last_timing(oc_ctx *ctx, oc_timing *out);
 /* Total kernels this library has launched on ctx since oc_init. */

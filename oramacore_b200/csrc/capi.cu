@@ -15,6 +15,7 @@
 
 #include "bm25.cuh"
 #include "comm.h"
+#include "emb_gemm.cuh"
 #include "emb_scan.cuh"
 #include "fuse.cuh"
 #include "oramacore_b200.h"
@@ -111,6 +112,8 @@ struct oc_ctx {
     DevBuf in_blob, q_pad, q_inv, eff_norm, filter_dev, scan_cand, v_doc, v_score, v_row, v_cnt, v_srow, v_ft, v_present, v_raw;
     DevBuf seg, df_dev, row_ok, tau, cand_key, cand_ft, cand_cnt, tile_cnt, tile_max, tile_min, min_hint;
     DevBuf out_blob, shard_send, shard_recv;
+    DevBuf g_tau, g_cand, g_cnt, g_flag, r_qpad, r_qinv, r_map, r_doc, r_score, r_row, r_cnt, r_raw;
+
     HostBuf h_in, h_out;
     OcComm comm;
 };
@@ -150,7 +153,8 @@ extern "C" void oc_shutdown(oc_ctx *c) {
     DevBuf *bufs[] = {&c->in_blob, &c->q_pad, &c->q_inv, &c->eff_norm, &c->filter_dev, &c->scan_cand, &c->v_doc,
                       &c->v_score, &c->v_row, &c->v_cnt, &c->v_srow, &c->v_ft, &c->v_present, &c->v_raw, &c->seg, &c->df_dev,
                       &c->row_ok, &c->tau, &c->cand_key, &c->cand_ft, &c->cand_cnt, &c->tile_cnt, &c->tile_max,
-                      &c->tile_min, &c->min_hint, &c->out_blob, &c->shard_send, &c->shard_recv};
+                      &c->tile_min, &c->min_hint, &c->out_blob, &c->shard_send, &c->shard_recv, &c->g_tau, &c->g_cand, &c->g_cnt,
+                      &c->g_flag, &c->r_qpad, &c->r_qinv, &c->r_map, &c->r_doc, &c->r_score, &c->r_row, &c->r_cnt, &c->r_raw};
     for (DevBuf *b : bufs) b->release();
     c->h_in.release(); c->h_out.release();
     for (int i = 0; i < EV_N; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -354,46 +358,21 @@ static ScanPlan plan_scan(const oc_ctx *c, const oc_emb *e, uint32_t n_keep) {
     return pl;
 }
 
-// Runs prep + scan sweeps + merge for B queries already in device memory (q_dev: B x dim).
-// Leaves hits in c->v_doc / v_score / v_row / v_cnt ([B][limit]).
-static int run_vector_stage(oc_ctx *c, oc_emb *e, const float *q_dev, uint32_t B, uint32_t limit, float similarity,
-                            const uint64_t *filter_dev, uint64_t filter_nbits) {
-    OCTRY(c->v_doc.ensure(size_t(B) * limit * 8));
-    OCTRY(c->v_score.ensure(size_t(B) * limit * 4));
-    OCTRY(c->v_row.ensure(size_t(B) * limit * 4));
-    OCTRY(c->v_cnt.ensure(size_t(B) * 4));
-    OCTRY(c->v_raw.ensure(size_t(B) * limit * 4));
-    if (e->n_rows == 0) {
-        CU(cudaMemsetAsync(c->v_cnt.p, 0, size_t(B) * 4, c->stream));
-        CU(cudaMemsetAsync(c->v_doc.p, 0, size_t(B) * limit * 8, c->stream));
-        CU(cudaMemsetAsync(c->v_score.p, 0, size_t(B) * limit * 4, c->stream));
-        CU(cudaMemsetAsync(c->v_row.p, 0xff, size_t(B) * limit * 4, c->stream));
-        return OC_OK;
-    }
-    OCTRY(c->q_pad.ensure(size_t(B) * e->stride * 4));
-    OCTRY(c->q_inv.ensure(size_t(B) * 4));
-    emb_prep_queries_kernel<<<(B + 7) / 8, 256, 0, c->stream>>>(q_dev, e->dim, e->stride, B, c->q_pad.as<float>(), c->q_inv.as<float>());
-    launched(c);
-    const float *inv_norm = e->inv_norm;
-    if (filter_dev) {
-        OCTRY(c->eff_norm.ensure((e->n_rows + 64) * 4));
-        emb_apply_filter_kernel<<<(unsigned)((e->n_rows + 255) / 256), 256, 0, c->stream>>>(
-            e->inv_norm, e->row_doc, e->n_rows, filter_dev, filter_nbits, c->eff_norm.as<float>());
-        launched(c);
-        inv_norm = c->eff_norm.as<float>();
-    }
+// ---- exact sweeps (K1) + merge for nq prepared queries; results into the given buffers
+struct VecOut { uint64_t *doc; float *score; uint32_t *row; uint32_t *cnt; float *raw; };
+static int run_exact_sweeps(oc_ctx *c, oc_emb *e, const float *inv_norm, const float *qpad, const float *qinv,
+                            uint32_t nq, uint32_t limit, float similarity, const VecOut &o) {
     ScanPlan pl = plan_scan(c, e, limit);
     if (pl.n_stages < 2) return fail(OC_ERR_UNSUPPORTED, "limit %u leaves no shared memory for the scan ring", limit);
-    OCTRY(c->scan_cand.ensure(size_t(B) * pl.grid * limit * 8));
-    CU(cudaEventRecord(c->ev[EV_SCAN0], c->stream));
+    OCTRY(c->scan_cand.ensure(size_t(nq) * pl.grid * limit * 8));
     uint32_t q0 = 0;
-    while (q0 < B) {
-        const uint32_t rem = B - q0;
+    while (q0 < nq) {
+        const uint32_t rem = nq - q0;
         const uint32_t qb = std::min<uint32_t>(pl.qb_max, rem >= 4 ? 4 : (rem >= 2 ? 2 : 1));
         ScanParams sp{};
         sp.rows = e->rows; sp.inv_norm = inv_norm; sp.n_rows = e->n_rows; sp.stride = e->stride;
-        sp.queries = c->q_pad.as<float>() + size_t(q0) * e->stride;
-        sp.inv_qnorm = c->q_inv.as<float>() + q0;
+        sp.queries = qpad + size_t(q0) * e->stride;
+        sp.inv_qnorm = qinv + q0;
         sp.n_keep = limit; sp.wcap = pl.wcap; sp.rows_per_stage = pl.rows_per_stage; sp.n_stages = pl.n_stages;
         sp.n_ctas_total = pl.grid;
         sp.cand = c->scan_cand.as<uint64_t>() + size_t(q0) * pl.grid * limit;
@@ -409,14 +388,144 @@ static int run_vector_stage(oc_ctx *c, oc_emb *e, const float *q_dev, uint32_t B
     mp.cand = c->scan_cand.as<uint64_t>(); mp.n_lists = pl.grid; mp.n_keep = limit; mp.limit = limit;
     mp.capb = std::max<uint32_t>(2048, next_pow2(2 * limit));
     mp.row_doc_ids = e->row_doc; mp.rescale_e5 = e->e5; mp.similarity = similarity;
-    mp.out_doc = c->v_doc.as<uint64_t>(); mp.out_score = c->v_score.as<float>(); mp.out_row = c->v_row.as<uint32_t>();
-    mp.out_count = c->v_cnt.as<uint32_t>(); mp.out_raw = c->v_raw.as<float>();
+    mp.out_doc = o.doc; mp.out_score = o.score; mp.out_row = o.row; mp.out_count = o.cnt; mp.out_raw = o.raw;
     static size_t merge_cfg = 0;
     if (size_t(mp.capb) * 8 > merge_cfg) {
         CU(cudaFuncSetAttribute(emb_scan_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(mp.capb * 8)));
         merge_cfg = size_t(mp.capb) * 8;
     }
-    emb_scan_merge_kernel<<<B, 256, mp.capb * 8, c->stream>>>(mp);
+    emb_scan_merge_kernel<<<nq, 256, mp.capb * 8, c->stream>>>(mp);
+    launched(c);
+    CU(cudaGetLastError());
+    return OC_OK;
+}
+
+// ---- TMA descriptors (driver entry point fetched through the runtime: no -lcuda link)
+typedef CUresult (*EncodeTiled_t)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int make_tmap_2d(CUtensorMap *m, const float *base, uint64_t n_rows, uint32_t stride, uint32_t box_rows) {
+    static EncodeTiled_t fn = nullptr;
+    if (!fn) {
+        void *f = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qr));
+        if (!f || qr != cudaDriverEntryPointSuccess) return fail(OC_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
+        fn = (EncodeTiled_t)f;
+    }
+    cuuint64_t dims[2] = {stride, n_rows};
+    cuuint64_t strides[1] = {cuuint64_t(stride) * 4};
+    cuuint32_t box[2] = {GEMM_KB, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(OC_ERR_CUDA, "cuTensorMapEncodeTiled failed: %d", (int)r);
+    return OC_OK;
+}
+
+static bool g_disable_gemm = false;   // OC_DISABLE_GEMM=1: force the exact sweep path (A/B testing)
+
+// Runs prep + (tensor-core batched scan | exact sweeps) + merge for B queries already in device
+// memory (q_dev: B x dim).  Leaves hits in c->v_doc / v_score / v_row / v_cnt / v_raw ([B][limit]).
+static int run_vector_stage(oc_ctx *c, oc_emb *e, const float *q_dev, uint32_t B, uint32_t limit, float similarity,
+                            const uint64_t *filter_dev, uint64_t filter_nbits) {
+    OCTRY(c->v_doc.ensure(size_t(B) * limit * 8));
+    OCTRY(c->v_score.ensure(size_t(B) * limit * 4));
+    OCTRY(c->v_row.ensure(size_t(B) * limit * 4));
+    OCTRY(c->v_cnt.ensure(size_t(B) * 4));
+    OCTRY(c->v_raw.ensure(size_t(B) * limit * 4));
+    if (e->n_rows == 0) {
+        CU(cudaMemsetAsync(c->v_cnt.p, 0, size_t(B) * 4, c->stream));
+        CU(cudaMemsetAsync(c->v_doc.p, 0, size_t(B) * limit * 8, c->stream));
+        CU(cudaMemsetAsync(c->v_score.p, 0, size_t(B) * limit * 4, c->stream));
+        CU(cudaMemsetAsync(c->v_row.p, 0xff, size_t(B) * limit * 4, c->stream));
+        return OC_OK;
+    }
+    const uint32_t n_qgroups = (B + GEMM_M - 1) / GEMM_M, Bpad = n_qgroups * GEMM_M;
+    OCTRY(c->q_pad.ensure(size_t(Bpad) * e->stride * 4));
+    OCTRY(c->q_inv.ensure(size_t(Bpad) * 4));
+    const char *env = getenv("OC_DISABLE_GEMM");
+    g_disable_gemm = env && env[0] == '1';
+    const bool use_gemm = !g_disable_gemm && B >= 8 && limit <= 32 && e->n_rows >= 4096;
+    if (use_gemm) CU(cudaMemsetAsync(c->q_pad.p, 0, size_t(Bpad) * e->stride * 4, c->stream));
+    emb_prep_queries_kernel<<<(B + 7) / 8, 256, 0, c->stream>>>(q_dev, e->dim, e->stride, B, c->q_pad.as<float>(), c->q_inv.as<float>());
+    launched(c);
+    const float *inv_norm = e->inv_norm;
+    if (filter_dev) {
+        OCTRY(c->eff_norm.ensure((e->n_rows + 64) * 4));
+        emb_apply_filter_kernel<<<(unsigned)((e->n_rows + 255) / 256), 256, 0, c->stream>>>(
+            e->inv_norm, e->row_doc, e->n_rows, filter_dev, filter_nbits, c->eff_norm.as<float>());
+        launched(c);
+        inv_norm = c->eff_norm.as<float>();
+    }
+    VecOut out{c->v_doc.as<uint64_t>(), c->v_score.as<float>(), c->v_row.as<uint32_t>(), c->v_cnt.as<uint32_t>(), c->v_raw.as<float>()};
+    CU(cudaEventRecord(c->ev[EV_SCAN0], c->stream));
+    if (!use_gemm) return run_exact_sweeps(c, e, inv_norm, c->q_pad.as<float>(), c->q_inv.as<float>(), B, limit, similarity, out);
+
+    // ---------------- K2: tcgen05 tf32 batched scan ----------------
+    const uint32_t keep = limit <= 16 ? 32 : 64, cap = 2 * keep;
+    const uint32_t cpg = std::max<uint32_t>(1, c->prop.multiProcessorCount / n_qgroups);
+    const uint32_t grid = cpg * n_qgroups;
+    CUtensorMap tm_q, tm_x;
+    OCTRY(make_tmap_2d(&tm_q, c->q_pad.as<float>(), Bpad, e->stride, GEMM_M));
+    OCTRY(make_tmap_2d(&tm_x, e->rows, e->n_rows, e->stride, GEMM_N));
+    OCTRY(c->g_tau.ensure(size_t(Bpad) * 4));
+    OCTRY(c->g_cand.ensure(size_t(Bpad) * cpg * cap * 8));
+    OCTRY(c->g_cnt.ensure(size_t(Bpad) * cpg * 4));
+    OCTRY(c->g_flag.ensure(B));
+    CU(cudaMemsetAsync(c->g_tau.p, 0, size_t(Bpad) * 4, c->stream));
+    GemmParams gp{};
+    gp.n_rows = e->n_rows; gp.n_kblocks = e->stride / GEMM_KB; gp.inv_norm = inv_norm; gp.n_queries = B;
+    gp.n_qgroups = n_qgroups; gp.ctas_per_group = cpg; gp.keep = keep; gp.cap = cap;
+    gp.tau = c->g_tau.as<unsigned int>(); gp.cand = c->g_cand.as<uint64_t>(); gp.cand_cnt = c->g_cnt.as<uint32_t>();
+    static bool gemm_cfg = false;
+    if (!gemm_cfg) {
+        CU(cudaFuncSetAttribute(emb_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes()));
+        gemm_cfg = true;
+    }
+    emb_gemm_kernel<<<grid, GEMM_THREADS, gemm_smem_bytes(), c->stream>>>(tm_q, tm_x, gp);
+    launched(c, true);
+    CU(cudaGetLastError());
+    c->timing.scan_bytes += e->n_rows * (uint64_t(e->stride) * 4 + 4);
+    CU(cudaEventRecord(c->ev[EV_SCAN1], c->stream));
+    GemmMergeParams mp{};
+    mp.cand = gp.cand; mp.cand_cnt = gp.cand_cnt; mp.ctas_per_group = cpg; mp.cap = cap; mp.keep = keep; mp.limit = limit;
+    mp.rows = e->rows; mp.stride = e->stride; mp.inv_norm = inv_norm; mp.queries = c->q_pad.as<float>();
+    mp.inv_qnorm = c->q_inv.as<float>(); mp.row_doc_ids = e->row_doc; mp.rescale_e5 = e->e5; mp.similarity = similarity;
+    mp.out_doc = out.doc; mp.out_score = out.score; mp.out_row = out.row; mp.out_count = out.cnt; mp.out_raw = out.raw;
+    mp.out_unproven = c->g_flag.as<uint8_t>();
+    emb_gemm_merge_kernel<<<B, 256, (2048 + 64) * 8, c->stream>>>(mp);
+    launched(c);
+    CU(cudaGetLastError());
+    // the proof flags decide whether any query must be re-run through the exact sweep
+    std::vector<uint8_t> flags(B);
+    CU(cudaMemcpyAsync(flags.data(), c->g_flag.p, B, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    std::vector<uint32_t> redo;
+    for (uint32_t q = 0; q < B; q++) if (flags[q]) redo.push_back(q);
+    c->timing.scan_tensor_core = 1;
+    c->timing.scan_unproven = (uint32_t)redo.size();
+    if (redo.empty()) return OC_OK;
+    const uint32_t nr = (uint32_t)redo.size();
+    OCTRY(c->r_qpad.ensure(size_t(nr) * e->stride * 4));
+    OCTRY(c->r_qinv.ensure(size_t(nr) * 4));
+    OCTRY(c->r_map.ensure(size_t(nr) * 4));
+    OCTRY(c->r_doc.ensure(size_t(nr) * limit * 8));
+    OCTRY(c->r_score.ensure(size_t(nr) * limit * 4));
+    OCTRY(c->r_row.ensure(size_t(nr) * limit * 4));
+    OCTRY(c->r_cnt.ensure(size_t(nr) * 4));
+    OCTRY(c->r_raw.ensure(size_t(nr) * limit * 4));
+    for (uint32_t i = 0; i < nr; i++) {
+        CU(cudaMemcpyAsync(c->r_qpad.as<float>() + size_t(i) * e->stride, c->q_pad.as<float>() + size_t(redo[i]) * e->stride,
+                           size_t(e->stride) * 4, cudaMemcpyDeviceToDevice, c->stream));
+        CU(cudaMemcpyAsync(c->r_qinv.as<float>() + i, c->q_inv.as<float>() + redo[i], 4, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    CU(cudaMemcpyAsync(c->r_map.p, redo.data(), size_t(nr) * 4, cudaMemcpyHostToDevice, c->stream));
+    VecOut ro{c->r_doc.as<uint64_t>(), c->r_score.as<float>(), c->r_row.as<uint32_t>(), c->r_cnt.as<uint32_t>(), c->r_raw.as<float>()};
+    OCTRY(run_exact_sweeps(c, e, inv_norm, c->r_qpad.as<float>(), c->r_qinv.as<float>(), nr, limit, similarity, ro));
+    scatter_rows_kernel<<<nr, 64, 0, c->stream>>>(c->r_map.as<uint32_t>(), nr, limit, ro.doc, ro.score, ro.row, ro.cnt, ro.raw,
+                                                   out.doc, out.score, out.row, out.cnt, out.raw);
     launched(c);
     CU(cudaGetLastError());
     return OC_OK;

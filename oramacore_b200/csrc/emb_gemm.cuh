@@ -1,0 +1,367 @@
+// emb_gemm.cuh — K2: batched-query embedding scan on the 5th-gen tensor cores.
+//
+// Same contract as K1 (EmbeddingFieldStorage::search, read/index/embedding_field.rs:250-278)
+// but for a BATCH of queries, where the distance computation is a true dense GEMM
+// S[q][r] = sum_k Q[q][k] * X[r][k] (north_star: "tensor cores used only when batched
+// queries make the distance a true dense GEMM").  One matrix sweep serves the whole batch.
+//
+//   * operands: fp32 rows straight from HBM, consumed by tcgen05.mma kind::tf32 (the tensor
+//     core reads the fp32 bits and drops the low 13 mantissa bits) — no converted copy of
+//     the store, algorithmic bytes = n_rows * stride * 4 per batch;
+//   * CTA tile: M = 128 queries (A operand) x N = 256 rows (B operand), K-blocks of 32 floats
+//     = one 128-byte swizzle row; TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) fills a
+//     4-stage ring (16 KB of Q + 32 KB of X per stage), a single thread issues 4
+//     tcgen05.mma per K-block into a 128-lane x 256-column fp32 accumulator in TMEM,
+//     double buffered (2 x 256 = all 512 TMEM columns) so the epilogue of tile i overlaps the
+//     MMAs of tile i+1;
+//   * query groups of 128 run as separate CTAs that walk the same row tiles at the same
+//     time, so the second group's reads hit L2 and HBM traffic stays one sweep per batch;
+//   * epilogue: 4 warps, thread = TMEM lane = ONE QUERY: tcgen05.ld the 256 scores of the
+//     tile, scale by the row's inverse norm, threshold-gated push into that query's private
+//     candidate buffer; the threshold is the query's running K'-th best, shared across CTAs
+//     through an atomicMax'd global array (any subset's K'-th best bounds the global one);
+//   * tf32 scores are only used to SELECT candidates.  The merge kernel re-scores the best
+//     K' candidates per query in exact fp32 with K1's arithmetic (bit-identical scores) and
+//     PROVES the answer: every non-candidate row has approx <= a_K', and
+//     |approx - exact| <= eps_tf32 (both operands truncated to 11 significant bits:
+//     2*2^-10 of |x||q|, plus fp32 accumulation), so when the limit-th exact score is
+//     >= a_K' + eps the exact top-`limit` is inside the candidate set.  Queries that fail
+//     the proof are re-run through the exact K1 sweep by the host (rare).
+#pragma once
+#include <cuda.h>
+
+#include "emb_scan.cuh"
+
+namespace oc {
+
+constexpr int GEMM_THREADS = 192;      // warp0: TMA producer, warp1: MMA issuer, warps 2-5: epilogue
+constexpr uint32_t GEMM_M = 128;       // queries per CTA
+constexpr uint32_t GEMM_N = 256;       // rows per tile
+constexpr uint32_t GEMM_KB = 32;       // floats per K-block (128 B swizzle row)
+constexpr uint32_t GEMM_STAGES = 4;
+constexpr uint32_t GEMM_A_BYTES = GEMM_M * 128;   // 16 KB
+constexpr uint32_t GEMM_B_BYTES = GEMM_N * 128;   // 32 KB
+constexpr uint32_t GEMM_STAGE_BYTES = GEMM_A_BYTES + GEMM_B_BYTES;
+constexpr uint32_t GEMM_MAX_KEEP = 64;            // K' upper bound (candidate buffer = 2 K')
+constexpr float GEMM_EPS_TF32 = 2.1e-3f;          // rigorous |approx - exact| bound on the cosine
+
+struct GemmParams {
+    uint64_t n_rows;
+    uint32_t n_kblocks;        // stride / 32
+    const float *inv_norm;     // [n_rows] (NaN => skipped)
+    uint32_t n_queries;        // B (real queries)
+    uint32_t n_qgroups;        // ceil(B / 128)
+    uint32_t ctas_per_group;   // gridDim.x / n_qgroups
+    uint32_t keep;             // K'
+    uint32_t cap;              // 2 K'
+    unsigned int *tau;         // [n_qgroups*128] ordered-uint running thresholds (init 0)
+    uint64_t *cand;            // [n_qgroups*128][ctas_per_group][cap]
+    uint32_t *cand_cnt;        // [n_qgroups*128][ctas_per_group]
+};
+
+__host__ __device__ inline size_t gemm_smem_bytes() {
+    return 1024 /*align slack*/ + size_t(GEMM_STAGES) * GEMM_STAGE_BYTES + 2 * GEMM_N * 4 /*inv norms*/ +
+           4 * 128 * 8 /*warp sort scratch*/ + 256 /*barriers, tmem ptr*/;
+}
+
+// ---- tcgen05 / TMA PTX wrappers ------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int32_t c0, int32_t c1,
+                                            uint64_t hint) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(hint)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32, issued by one thread
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+// start>>4 [0,14) | LBO>>4 [16,30) = 1 | SBO>>4 [32,46) = 1024/16 | version [46,48) = 1 | layout [61,64) = 2
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    const uint32_t lo = ((smem_addr >> 4) & 0x3fffu) | (1u << 16);
+    const uint32_t hi = 64u | (1u << 14) | (2u << 29);
+    return (uint64_t(hi) << 32) | lo;
+}
+// instruction descriptor: D=f32 (1<<4), A=B=tf32 (2<<7, 2<<10), K-major both, N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(uint32_t m, uint32_t n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+constexpr uint64_t TMA_EVICT_FIRST = 0x12F0000000000000ull;
+constexpr uint64_t TMA_EVICT_LAST = 0x14F0000000000000ull;
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+emb_gemm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_x, const GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    // SWIZZLE_128B tiles need 1024-byte alignment
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *ring = smem;
+    float *inr_s = reinterpret_cast<float *>(ring + GEMM_STAGES * GEMM_STAGE_BYTES);   // [2][256]
+    uint64_t *scratch = reinterpret_cast<uint64_t *>(inr_s + 2 * GEMM_N);              // [4 warps][128]
+    uint64_t *bars = scratch + 4 * 128;
+    uint64_t *full = bars, *empty = bars + GEMM_STAGES;
+    uint64_t *tfull = bars + 2 * GEMM_STAGES, *tempty = tfull + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t g = blockIdx.x % p.n_qgroups;       // query group
+    const uint32_t c = blockIdx.x / p.n_qgroups;       // row partition
+    const uint64_t n_tiles = (p.n_rows + GEMM_N - 1) / GEMM_N;
+    const uint64_t my_tiles = (n_tiles > c) ? (n_tiles - c + p.ctas_per_group - 1) / p.ctas_per_group : 0;
+    const uint32_t nkb = p.n_kblocks;
+
+    if (threadIdx.x == 0) {
+        for (uint32_t s = 0; s < GEMM_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (uint32_t a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 128); }
+        fence_mbar_init();
+        tma_prefetch_desc(&tm_q);
+        tma_prefetch_desc(&tm_x);
+    }
+    if (warp == 1) {   // TMEM: all 512 columns (2 accumulator stages x 256 fp32 columns)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint64_t n = 0;
+            for (uint64_t it = 0; it < my_tiles; it++) {
+                const uint64_t row0 = (c + it * p.ctas_per_group) * GEMM_N;
+                for (uint32_t kb = 0; kb < nkb; kb++, n++) {
+                    const uint32_t s = uint32_t(n % GEMM_STAGES), ph = uint32_t((n / GEMM_STAGES) & 1);
+                    mbar_wait(&empty[s], ph ^ 1);
+                    uint8_t *a_dst = ring + s * GEMM_STAGE_BYTES, *b_dst = a_dst + GEMM_A_BYTES;
+                    mbar_expect_tx(&full[s], GEMM_STAGE_BYTES);
+                    tma_load_2d(a_dst, &tm_q, &full[s], int32_t(kb * GEMM_KB), int32_t(g * GEMM_M), TMA_EVICT_LAST);
+                    tma_load_2d(b_dst, &tm_x, &full[s], int32_t(kb * GEMM_KB), int32_t(row0), TMA_EVICT_FIRST);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one thread) =====================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_tf32(GEMM_M, GEMM_N);
+            uint64_t n = 0;
+            for (uint64_t it = 0; it < my_tiles; it++) {
+                const uint32_t acc = uint32_t(it & 1), aph = uint32_t((it >> 1) & 1);
+                mbar_wait(&tempty[acc], aph ^ 1);          // epilogue drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * GEMM_N;
+                for (uint32_t kb = 0; kb < nkb; kb++, n++) {
+                    const uint32_t s = uint32_t(n % GEMM_STAGES), ph = uint32_t((n / GEMM_STAGES) & 1);
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(ring + s * GEMM_STAGE_BYTES);
+                    const uint64_t adesc = umma_desc_sw128(a_addr), bdesc = umma_desc_sw128(a_addr + GEMM_A_BYTES);
+#pragma unroll
+                    for (uint32_t k = 0; k < 4; k++)      // UMMA_K = 8 tf32 = 32 B: advance start address by 32 B
+                        tc_mma_tf32(d_tmem, adesc + k * 2, bdesc + k * 2, idesc, (kb | k) != 0);
+                    tc_commit(&empty[s]);                  // frees the smem stage when these MMAs retire
+                }
+                tc_commit(&tfull[acc]);                    // accumulator complete -> epilogue
+            }
+        }
+    } else {
+        // ===================== epilogue: thread = TMEM lane = one query =====================
+        const uint32_t quad = warp & 3;                    // TMEM lane quadrant this warp may access
+        const uint32_t m = quad * 32 + lane;
+        const uint32_t q = g * GEMM_M + m;
+        const bool live = q < p.n_queries;
+        const uint32_t et = (warp - 2) * 32 + lane;        // 0..127 among epilogue threads
+        uint64_t *mybuf = p.cand + (size_t(q) * p.ctas_per_group + c) * p.cap;
+        uint64_t *wscr = scratch + (warp - 2) * 128;
+        uint32_t cnt = 0;
+        float tau = live ? -INFINITY : INFINITY;
+        for (uint64_t it = 0; it < my_tiles; it++) {
+            const uint32_t acc = uint32_t(it & 1), aph = uint32_t((it >> 1) & 1);
+            const uint64_t row0 = (c + it * p.ctas_per_group) * GEMM_N;
+            float *inr = inr_s + acc * GEMM_N;
+#pragma unroll
+            for (uint32_t h = 0; h < 2; h++) {
+                const uint64_t r = row0 + et + h * 128;
+                inr[et + h * 128] = r < p.n_rows ? __ldg(p.inv_norm + r) : __int_as_float(0x7fc00000);
+            }
+            if (live) {   // the query's threshold as raised by every CTA so far
+                const unsigned int tg = *reinterpret_cast<volatile unsigned int *>(p.tau + q);
+                if (tg) tau = fmaxf(tau, f32_unordered(tg));
+            }
+            named_bar_sync(1, 128);
+            mbar_wait(&tfull[acc], aph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((quad * 32u) << 16) + acc * GEMM_N;
+            for (uint32_t ch = 0; ch < GEMM_N / 32; ch++) {
+                uint32_t d[32];
+                tmem_ld32(taddr + ch * 32, d);
+                tmem_ld_wait();
+#pragma unroll
+                for (uint32_t j = 0; j < 32; j++) {
+                    const float v = __uint_as_float(d[j]) * inr[ch * 32 + j];   // cos * |q|
+                    if (v > tau) { mybuf[cnt] = make_key(v, uint32_t(row0 + ch * 32 + j)); cnt++; }
+                }
+                // warp-cooperative compress of every lane whose buffer could overflow in the next chunk
+                uint32_t need = __ballot_sync(0xffffffffu, cnt + 32 > p.cap);
+                while (need) {
+                    const uint32_t l = __ffs(need) - 1;
+                    need &= need - 1;
+                    const uint32_t lq = g * GEMM_M + quad * 32 + l;
+                    uint64_t *lbuf = p.cand + (size_t(lq) * p.ctas_per_group + c) * p.cap;
+                    const uint32_t lcnt = __shfl_sync(0xffffffffu, cnt, l);
+                    __syncwarp();
+                    for (uint32_t i = lane; i < 128; i += 32) wscr[i] = i < lcnt ? lbuf[i] : KEY_NONE;
+                    warp_bitonic_desc(wscr, 128, lane);
+                    for (uint32_t i = lane; i < p.keep; i += 32) lbuf[i] = wscr[i];
+                    __syncwarp();
+                    if (lane == l) {
+                        cnt = p.keep;
+                        tau = fmaxf(tau, key_score(wscr[p.keep - 1]));
+                        atomicMax(p.tau + q, f32_ordered(tau));
+                    }
+                    __syncwarp();
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tempty[acc]);
+        }
+        if (live || true) p.cand_cnt[size_t(q) * p.ctas_per_group + c] = live ? cnt : 0;
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Merge: best K' candidates by tf32 score -> exact fp32 re-score (K1 arithmetic) -> proof.
+// ---------------------------------------------------------------------------------------
+struct GemmMergeParams {
+    const uint64_t *cand; const uint32_t *cand_cnt;
+    uint32_t ctas_per_group, cap, keep, limit;
+    const float *rows; uint32_t stride; const float *inv_norm;
+    const float *queries;        // [B][stride] padded
+    const float *inv_qnorm;      // [B]
+    const uint64_t *row_doc_ids;
+    int rescale_e5; float similarity;
+    uint64_t *out_doc; float *out_score; uint32_t *out_row; uint32_t *out_count; float *out_raw;
+    uint8_t *out_unproven;       // [B] 1 => host must re-run this query through the exact sweep
+};
+
+__global__ void __launch_bounds__(256) emb_gemm_merge_kernel(const GemmMergeParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint64_t *buf = reinterpret_cast<uint64_t *>(smem);          // [2048]
+    uint64_t *exact = buf + 2048;                                 // [64]
+    __shared__ uint32_t s_cnt;
+    const uint32_t q = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint64_t total = uint64_t(p.ctas_per_group) * p.cap;
+    const uint64_t *src = p.cand + size_t(q) * total;
+    const uint32_t *cnts = p.cand_cnt + size_t(q) * p.ctas_per_group;
+    const uint32_t got = block_topn_stream(buf, 2048, p.keep, total, [&](uint64_t i) -> uint64_t {
+        const uint32_t cta = uint32_t(i / p.cap), k = uint32_t(i % p.cap);
+        return k < cnts[cta] ? src[i] : KEY_NONE;
+    });
+    const float iqn = p.inv_qnorm[q];
+    const float a_keep = got == p.keep ? key_score(buf[p.keep - 1]) * iqn : -INFINITY;   // approx cosine of the K'-th
+    // exact fp32 re-score, one warp per candidate, K1's lane layout and FMA order
+    for (uint32_t i = tid; i < 64; i += blockDim.x) exact[i] = KEY_NONE;
+    if (tid == 0) s_cnt = 0;
+    __syncthreads();
+    const float4 *qp = reinterpret_cast<const float4 *>(p.queries + size_t(q) * p.stride);
+    for (uint32_t i = warp; i < got; i += 8) {
+        const uint32_t row = key_idx(buf[i]);
+        const float4 *rp = reinterpret_cast<const float4 *>(p.rows + size_t(row) * p.stride);
+        float acc = 0.f;
+        for (uint32_t j = 0; j < p.stride / 128; j++) {
+            const float4 x = rp[lane + 32 * j], y = qp[lane + 32 * j];
+            acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc); acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
+        }
+        const float dot = warp_sum(acc);
+        const float cosv = dot * p.inv_norm[row] * iqn;
+        const float kf = -(1.0f - cosv);
+        if (lane == 0) exact[i] = make_key(kf, row);
+    }
+    __syncthreads();
+    if (warp == 0) warp_bitonic_desc(exact, 64, lane);
+    __syncthreads();
+    const uint32_t n_top = min(got, p.limit);
+    // proof: limit-th exact cosine >= a_K' + eps  (or every live row is already a candidate)
+    bool proven = got < p.keep;
+    if (!proven && n_top == p.limit) {
+        const float c_lim = 1.0f + key_score(exact[p.limit - 1]);   // cos = 1 - distance
+        proven = c_lim >= a_keep + GEMM_EPS_TF32;
+    }
+    for (uint32_t i = tid; i < p.limit; i += blockDim.x) {
+        uint64_t doc = 0; float score = 0.f, raw = 0.f; uint32_t row = 0xffffffffu;
+        if (i < n_top) {
+            const uint64_t k = exact[i];
+            const uint32_t r = key_idx(k);
+            const float distance = -key_score(k);
+            const float sim = 1.0f - distance;
+            const float sc = rescale_score(sim, p.rescale_e5);
+            if (sc >= p.similarity) {
+                doc = p.row_doc_ids ? p.row_doc_ids[r] : uint64_t(r);
+                score = sc; row = r; raw = key_score(k);
+                atomicAdd(&s_cnt, 1u);
+            }
+        }
+        p.out_doc[size_t(q) * p.limit + i] = doc;
+        p.out_score[size_t(q) * p.limit + i] = score;
+        if (p.out_row) p.out_row[size_t(q) * p.limit + i] = row;
+        if (p.out_raw) p.out_raw[size_t(q) * p.limit + i] = raw;
+    }
+    __syncthreads();
+    if (tid == 0) { p.out_count[q] = s_cnt; p.out_unproven[q] = proven ? 0 : 1; }
+}
+
+// copies the exact-path results of re-run queries into their slots of the batch outputs
+__global__ void scatter_rows_kernel(const uint32_t *qmap, uint32_t n, uint32_t limit, const uint64_t *sdoc,
+                                    const float *sscore, const uint32_t *srow, const uint32_t *scnt, const float *sraw,
+                                    uint64_t *ddoc, float *dscore, uint32_t *drow, uint32_t *dcnt, float *draw) {
+    const uint32_t i = blockIdx.x, t = threadIdx.x;
+    if (i >= n) return;
+    const uint32_t q = qmap[i];
+    for (uint32_t k = t; k < limit; k += blockDim.x) {
+        ddoc[size_t(q) * limit + k] = sdoc[size_t(i) * limit + k];
+        dscore[size_t(q) * limit + k] = sscore[size_t(i) * limit + k];
+        drow[size_t(q) * limit + k] = srow[size_t(i) * limit + k];
+        draw[size_t(q) * limit + k] = sraw[size_t(i) * limit + k];
+    }
+    if (t == 0) dcnt[q] = scnt[i];
+}
+
+}  // namespace oc

@@ -1,0 +1,84 @@
+"""K2 (tcgen05 tf32 batched scan + exact re-score + proof) against K1 (exact sweep) and the oracle.
+The tensor-core path must return bit-identical hits to the exact path: tf32 only selects
+candidates; every returned score is re-computed with K1's fp32 arithmetic."""
+import os
+
+import numpy as np
+import pytest
+
+import oramacore_b200 as ob
+from helpers import assert_topk_equal
+from oramacore_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _both_paths(ctx, emb, qv, limit, sim, fb=None, nb=0):
+    os.environ.pop("OC_DISABLE_GEMM", None)
+    d1, s1, c1 = emb.search_batch(qv, limit, sim, fb, nb)
+    t1 = ctx.last_timing()
+    return (d1, s1, c1), t1
+
+
+@pytest.mark.parametrize("n,dim,model,B", [(20000, 768, "BGEBase", 32), (70001, 384, "BGESmall", 130),
+                                            (9000, 1024, "BGELarge", 8), (50000, 768, "MultilingualE5Base", 256)])
+def test_gemm_path_matches_oracle(gpu_ctx, orc, n, dim, model, B):
+    rows = synth.make_vectors(n, dim, seed=n)
+    qv, planted = synth.make_vector_queries(rows, B, seed=n + 1)
+    emb = ob.EmbeddingFieldStorage(gpu_ctx, model)
+    emb.insert_batch(np.arange(n, dtype=np.uint64), rows)
+    st = orc.EmbStore(rows, is_e5=model.startswith("MultilingualE5"))
+    for limit, sim in ((10, -1.0), (25, 0.0)):
+        (docs, scores, counts), t = _both_paths(gpu_ctx, emb, qv, limit, sim)
+        assert t["scan_tensor_core"] == 1, t
+        assert t["scan_launches"] >= 1
+        for i in list(range(0, B, max(1, B // 16))):
+            ed, es = orc.vector(st, qv[i], limit, sim)
+            order = np.argsort(-es, kind="stable")
+            assert counts[i] == len(ed), (i, counts[i], len(ed))
+            assert_topk_equal(docs[i, :counts[i]], scores[i, :counts[i]], ed[order], es[order], atol=1e-5)
+        if limit == 10 and sim < 0:
+            assert np.all(docs[:, 0] == planted)
+    emb.close()
+
+
+def test_gemm_path_with_filter_delete_and_zero_query(gpu_ctx, orc):
+    n, dim, B = 30000, 768, 16
+    rows = synth.make_vectors(n, dim, seed=3)
+    qv, _ = synth.make_vector_queries(rows, B, seed=4)
+    qv[5] = 0.0                                   # zero query: fails the proof -> exact re-run
+    emb = ob.EmbeddingFieldStorage(gpu_ctx, "BGEBase")
+    emb.insert_batch(np.arange(n, dtype=np.uint64), rows)
+    deleted = np.zeros(n, np.uint8)
+    for d in (7, 8, 9):
+        emb.delete(d)
+        deleted[d] = 1
+    rng = np.random.default_rng(0)
+    allowed = np.flatnonzero(rng.random(n) < 0.4)
+    fb = orc.make_filter_bits(allowed.tolist(), n)
+    (docs, scores, counts), t = _both_paths(gpu_ctx, emb, qv, 10, -1.0, fb, n)
+    assert t["scan_tensor_core"] == 1 and t["scan_unproven"] >= 1
+    st = orc.EmbStore(rows, deleted=deleted)
+    for i in range(B):
+        ed, es = orc.vector(st, qv[i], 10, -1.0, fb, n)
+        order = np.argsort(-es, kind="stable")
+        assert_topk_equal(docs[i, :counts[i]], scores[i, :counts[i]], ed[order], es[order], atol=1e-5)
+    emb.close()
+
+
+def test_gemm_equals_exact_sweep_bitwise(gpu_ctx):
+    n, dim, B = 120000, 768, 64
+    rows = synth.make_vectors(n, dim, seed=13)
+    qv, _ = synth.make_vector_queries(rows, B, seed=14)
+    emb = ob.EmbeddingFieldStorage(gpu_ctx, "BGEBase")
+    emb.insert_batch(np.arange(n, dtype=np.uint64), rows)
+    d1, s1, c1 = emb.search_batch(qv, 10, 0.0)
+    assert gpu_ctx.last_timing()["scan_tensor_core"] == 1
+    os.environ["OC_DISABLE_GEMM"] = "1"
+    try:
+        d2, s2, c2 = emb.search_batch(qv, 10, 0.0)
+        assert gpu_ctx.last_timing()["scan_tensor_core"] == 0
+    finally:
+        os.environ.pop("OC_DISABLE_GEMM", None)
+    assert np.array_equal(d1, d2) and np.array_equal(s1, s2) and np.array_equal(c1, c2)
+    emb.close()
