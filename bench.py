@@ -219,7 +219,7 @@ def main():
     if rank == 0:
         sampler.start()
     dev_ms = scan_ms = bm_ms = fuse_ms = comm_ms = 0.0
-    scan_bytes = scan_launches = postings = h2d = d2h = 0
+    scan_bytes = scan_launches = postings = h2d = d2h = unproven = tensor_core = 0
     sync_all()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -228,6 +228,7 @@ def main():
         dev_ms += t["device_ms"]; scan_ms += t["scan_ms"]; bm_ms += t["bm25_ms"]; fuse_ms += t["fuse_ms"]
         comm_ms += t["comm_ms"]; scan_bytes += t["scan_bytes"]; scan_launches += t["scan_launches"]
         postings += t["bm25_postings"]; h2d, d2h = t["h2d_bytes"], t["d2h_bytes"]
+        unproven += t["scan_unproven"]; tensor_core = max(tensor_core, t["scan_tensor_core"])
     sync_all()
     wall = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
@@ -273,7 +274,10 @@ def main():
         traffic = json.load(open(tpath)).get(args.workload)
     if w["dim"] and scan_ms >= bm_ms:
         ach = (scan_bytes / 1e9) / (scan_ms * 1e-3)
-        line["roofline"] = {"kernel": "emb_scan_kernel", "bound": "hbm", "achieved": ach, "peak": peak,
+        line["scan"] = {"kernel": "emb_gemm_kernel (tcgen05 kind::tf32 + exact fp32 re-score)" if tensor_core else "emb_scan_kernel (exact fp32 sweep)",
+                        "unproven_queries_rerun_exact_per_step": unproven / K,
+                        "tf32_tflops": (2.0 * B * n_docs * w["dim"] * scan_launches / max(scan_launches, 1) / 1e12) / (scan_ms / K * 1e-3) if tensor_core else None}
+        line["roofline"] = {"kernel": "emb_gemm_kernel" if tensor_core else "emb_scan_kernel", "bound": "hbm", "achieved": ach, "peak": peak,
                             "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "peak_source": f"of {peak_src}",
                             "launches_per_step": scan_launches / K,
                             "algorithmic_bytes_per_launch": scan_bytes / max(scan_launches, 1),

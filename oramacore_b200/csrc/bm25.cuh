@@ -32,9 +32,13 @@ constexpr uint32_t BM25_TILE = 16384;          // rows per tile
 constexpr uint32_t BM25_THREADS = 256;
 constexpr uint32_t BM25_CHUNK = BM25_THREADS * 4;
 
-struct Posting {       // 8 bytes
+struct PostingRaw {    // 8 bytes, as handed over by the host (string_field.rs:162: field_length is u16)
     uint32_t row;
     uint16_t tf, len;
+};
+struct Posting {       // 8 bytes, what the scorer streams: row + tf' = tf / (1 - b + b*len/avglen)
+    uint32_t row;
+    float ntf;         // bm25.rs:99-110, computed once per (field, b) at load time with the same rounded ops
 };
 
 struct TermDesc {      // one expanded index term of one token of one query
@@ -85,6 +89,17 @@ __device__ __forceinline__ float bm25_ntf(uint32_t tf, uint32_t len, float avg, 
     const float den = __fadd_rn(one_minus_b, __fmul_rn(b, r));
     return __fmul_rn(w, __fdiv_rn(float(tf), den));
 }
+// load-time derivation of the streamed posting format (re-run only if b or avg_field_len change)
+__global__ void bm25_derive_postings_kernel(const PostingRaw *raw, uint64_t n, float avg, float b, Posting *out) {
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const PostingRaw r = raw[i];
+    Posting o;
+    o.row = r.row;
+    o.ntf = bm25_ntf(r.tf, r.len, avg, b, __fsub_rn(1.0f, b), 1.0f);   // w = 1: x*1.0 is exact
+    out[i] = o;
+}
+
 // bm25.rs:124-126: idf * (k + 1) * S / (k + S)
 __device__ __forceinline__ float bm25_sat(float S, float k, float kp1, float idf) {
     return __fdiv_rn(__fmul_rn(__fmul_rn(idf, kp1), S), __fadd_rn(k, S));
@@ -194,14 +209,13 @@ __global__ void __launch_bounds__(BM25_THREADS) bm25_tile_kernel(const Bm25Param
     const uint32_t row0 = tile * BM25_TILE;
     const uint32_t tid = threadIdx.x;
     const QueryDesc qd = p.queries[q];
-    const float one_minus_b = __fsub_rn(1.0f, p.b);
     const float kp1 = __fadd_rn(p.k, 1.0f);
     const bool use_ok = p.row_ok_bits != nullptr;
 
-    for (uint32_t i = tid; i < BM25_TILE; i += BM25_THREADS) {
-        score[i] = 0.f;
-        if (MULTI) aux[i] = 0.f;
-        if (THRESH) mask[i] = 0u;
+    for (uint32_t i = tid; i < BM25_TILE / 4; i += BM25_THREADS) {
+        reinterpret_cast<float4 *>(score)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (MULTI) reinterpret_cast<float4 *>(aux)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (THRESH) reinterpret_cast<uint4 *>(mask)[i] = make_uint4(0u, 0u, 0u, 0u);
     }
     if (use_ok)
         for (uint32_t i = tid; i < BM25_TILE / 32; i += BM25_THREADS) okb[i] = p.row_ok_bits[row0 / 32 + i];
@@ -229,8 +243,7 @@ __global__ void __launch_bounds__(BM25_THREADS) bm25_tile_kernel(const Bm25Param
                     if (rec[u].x == 0xffffffffu) continue;
                     const uint32_t l = rec[u].x - row0;
                     if (use_ok && !((okb[l >> 5] >> (l & 31)) & 1u)) continue;
-                    const float ntf = bm25_ntf(rec[u].y & 0xffffu, rec[u].y >> 16, td.avg_len, p.b, one_minus_b,
-                                               td.weight);
+                    const float ntf = __fmul_rn(td.weight, __uint_as_float(rec[u].y));   // w * tf'
                     if (single) {
                         // S = 0.0 + 1.0*ntf; skip unless is_normal (bm25.rs:387,501)
                         if (f32_is_normal(ntf)) {
@@ -306,31 +319,42 @@ __global__ void __launch_bounds__(BM25_THREADS) bm25_tile_kernel(const Bm25Param
     uint32_t matched = 0;
     float lmax = 0.f, lmin = 0.f;
     const uint64_t rows_here = min(uint64_t(BM25_TILE), p.n_rows - row0);
+    const float tau_f0 = tau ? key_score(tau) : -INFINITY;   // cheap float pre-filter for the rank key compare
+    float tau_f = tau_f0;
     for (uint32_t base = 0; base < rows_here; base += BM25_CHUNK) {
+        const uint32_t l0 = base + tid * 4;                   // 4 consecutive rows per thread: one LDS.128
+        bool pushed = false;
+        if (l0 < rows_here) {
+            const float4 s4 = *reinterpret_cast<const float4 *>(score + l0);
+            uint4 m4 = make_uint4(0u, 0u, 0u, 0u);
+            if (THRESH) m4 = *reinterpret_cast<const uint4 *>(mask + l0);
+            const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+            const uint32_t mv[4] = {m4.x, m4.y, m4.z, m4.w};
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const uint32_t l = base + tid + u * BM25_THREADS;
-            if (l >= rows_here) continue;
-            const float s = score[l];
-            bool present;
-            if (THRESH) present = mask[l] != 0u && uint32_t(__popc(mask[l])) >= qd.required;  // bm25.rs:416-428
-            else present = s != 0.f;
-            if (!present) continue;
-            matched++;
-            lmax = fmaxf(lmax, s);
-            lmin = fminf(lmin, s);
-            float proxy = __fsub_rn(s, mh);
-            if (OMC) proxy = __fmul_rn(proxy, aux[l]);
-            if (proxy == proxy) {
-                const unsigned long long key = make_key(proxy, row0 + l);
-                if (key > tau) {
-                    const uint32_t slot = atomicAdd(&s_cnt, 1u);
-                    tbuf[slot] = key;   // slot < cap guaranteed by the compress rule below
-                    tft[slot] = s;
+            for (int u = 0; u < 4; u++) {
+                const uint32_t l = l0 + u;
+                const float s = sv[u];
+                bool present;
+                if (THRESH) present = mv[u] != 0u && uint32_t(__popc(mv[u])) >= qd.required;  // bm25.rs:416-428
+                else present = s != 0.f;
+                if (!present || l >= rows_here) continue;
+                matched++;
+                lmax = fmaxf(lmax, s);
+                lmin = fminf(lmin, s);
+                float proxy = __fsub_rn(s, mh);
+                if (OMC) proxy = __fmul_rn(proxy, aux[l]);
+                if (proxy >= tau_f) {                          // NaN fails; ties re-checked on the full key
+                    const unsigned long long key = make_key(proxy, row0 + l);
+                    if (key > tau) {
+                        const uint32_t slot = atomicAdd(&s_cnt, 1u);
+                        tbuf[slot] = key;   // slot < cap guaranteed by the compress rule below
+                        tft[slot] = s;
+                        pushed = true;
+                    }
                 }
             }
         }
-        __syncthreads();
+        if (!__syncthreads_or(pushed)) continue;               // nothing pushed in this chunk: no overflow risk
         const uint32_t c = s_cnt;   // snapshot, then barrier, so the branch is block-uniform
         __syncthreads();
         if (c + BM25_CHUNK > p.cap && base + BM25_CHUNK < rows_here) {
@@ -340,11 +364,12 @@ __global__ void __launch_bounds__(BM25_THREADS) bm25_tile_kernel(const Bm25Param
             group_bitonic_desc(tbuf, p.cap, tid, BM25_THREADS, 0);
             const uint32_t kept = min(c, p.n_keep);
             if (tid == 0) s_cnt = kept;
-            if (kept == p.n_keep) tau = max(tau, (unsigned long long)tbuf[p.n_keep - 1]);
+            if (kept == p.n_keep) { tau = max(tau, (unsigned long long)tbuf[p.n_keep - 1]); tau_f = key_score(tau); }
             for (uint32_t i = tid; i < kept; i += BM25_THREADS) tft[i] = score[key_idx(tbuf[i]) - row0];
             __syncthreads();
         }
     }
+    __syncthreads();
     // ---- block reductions of count / extrema
     matched = __reduce_add_sync(0xffffffffu, matched);
     for (int o = 16; o > 0; o >>= 1) {

@@ -464,17 +464,20 @@ static int run_vector_stage(oc_ctx *c, oc_emb *e, const float *q_dev, uint32_t B
     if (!use_gemm) return run_exact_sweeps(c, e, inv_norm, c->q_pad.as<float>(), c->q_inv.as<float>(), B, limit, similarity, out);
 
     // ---------------- K2: tcgen05 tf32 batched scan ----------------
-    const uint32_t keep = limit <= 16 ? 32 : 64, cap = 2 * keep;
+    const uint32_t keep = limit <= 16 ? 32 : 64, cap = 128;   // cap == warp sort scratch; compress when > 96
     const uint32_t cpg = std::max<uint32_t>(1, c->prop.multiProcessorCount / n_qgroups);
     const uint32_t grid = cpg * n_qgroups;
     CUtensorMap tm_q, tm_x;
     OCTRY(make_tmap_2d(&tm_q, c->q_pad.as<float>(), Bpad, e->stride, GEMM_M));
     OCTRY(make_tmap_2d(&tm_x, e->rows, e->n_rows, e->stride, GEMM_N));
     OCTRY(c->g_tau.ensure(size_t(Bpad) * 4));
-    OCTRY(c->g_cand.ensure(size_t(Bpad) * cpg * cap * 8));
-    OCTRY(c->g_cnt.ensure(size_t(Bpad) * cpg * 4));
+    OCTRY(c->g_cand.ensure(size_t(Bpad) * cpg * 2 * cap * 8));
+    OCTRY(c->g_cnt.ensure(size_t(Bpad) * cpg * 2 * 4));
     OCTRY(c->g_flag.ensure(B));
     CU(cudaMemsetAsync(c->g_tau.p, 0, size_t(Bpad) * 4, c->stream));
+    gemm_seed_tau_kernel<<<B, 256, 0, c->stream>>>(e->rows, inv_norm, e->stride, 1024, c->q_pad.as<float>(),
+                                                   c->q_inv.as<float>(), keep, c->g_tau.as<unsigned int>());
+    launched(c);
     GemmParams gp{};
     gp.n_rows = e->n_rows; gp.n_kblocks = e->stride / GEMM_KB; gp.inv_norm = inv_norm; gp.n_queries = B;
     gp.n_qgroups = n_qgroups; gp.ctas_per_group = cpg; gp.keep = keep; gp.cap = cap;
@@ -490,7 +493,7 @@ static int run_vector_stage(oc_ctx *c, oc_emb *e, const float *q_dev, uint32_t B
     c->timing.scan_bytes += e->n_rows * (uint64_t(e->stride) * 4 + 4);
     CU(cudaEventRecord(c->ev[EV_SCAN1], c->stream));
     GemmMergeParams mp{};
-    mp.cand = gp.cand; mp.cand_cnt = gp.cand_cnt; mp.ctas_per_group = cpg; mp.cap = cap; mp.keep = keep; mp.limit = limit;
+    mp.cand = gp.cand; mp.cand_cnt = gp.cand_cnt; mp.ctas_per_group = cpg * 2; mp.cap = cap; mp.keep = keep; mp.limit = limit;
     mp.rows = e->rows; mp.stride = e->stride; mp.inv_norm = inv_norm; mp.queries = c->q_pad.as<float>();
     mp.inv_qnorm = c->q_inv.as<float>(); mp.row_doc_ids = e->row_doc; mp.rescale_e5 = e->e5; mp.similarity = similarity;
     mp.out_doc = out.doc; mp.out_score = out.score; mp.out_row = out.row; mp.out_count = out.cnt; mp.out_raw = out.raw;
@@ -594,7 +597,9 @@ struct StrField {
     uint32_t n_terms = 0;
     std::vector<uint64_t> term_offsets;  // host copy (n_terms+1)
     std::vector<uint32_t> global_df;     // optional
-    Posting *post = nullptr;             // device
+    PostingRaw *raw = nullptr;           // device: (row, tf, field_len) as loaded
+    Posting *post = nullptr;             // device: (row, tf') derived for b_cached
+    float b_cached = -1.f;
     uint64_t n_post = 0;
 };
 struct oc_str {
@@ -620,7 +625,7 @@ extern "C" void oc_str_destroy(oc_str *s) {
     if (!s) return;
     cudaSetDevice(s->ctx->device);
     cudaStreamSynchronize(s->ctx->stream);
-    for (auto &f : s->fields) cudaFree(f.post);
+    for (auto &f : s->fields) { cudaFree(f.post); cudaFree(f.raw); }
     cudaFree(s->row_doc); cudaFree(s->alive);
     delete s;
 }
@@ -652,7 +657,7 @@ extern "C" int oc_str_load_field(oc_str *s, uint32_t field, float avg_field_len,
     std::lock_guard<std::mutex> g(c->mu);
     CU(cudaSetDevice(c->device));
     StrField &f = s->fields[field];
-    cudaFree(f.post); f.post = nullptr;
+    cudaFree(f.post); f.post = nullptr; cudaFree(f.raw); f.raw = nullptr; f.b_cached = -1.f;
     const uint64_t np = term_offsets[n_terms];
     if (np && (!post_row || !post_tf || !post_len)) return fail(OC_ERR_INVALID, "posting arrays are NULL");
     for (uint32_t t = 0; t < n_terms; t++) {
@@ -665,17 +670,18 @@ extern "C" int oc_str_load_field(oc_str *s, uint32_t field, float avg_field_len,
     if (global_df) f.global_df.assign(global_df, global_df + n_terms);
     if (np) {
         CU(cudaMalloc(&f.post, (np + 4) * sizeof(Posting)));
+        CU(cudaMalloc(&f.raw, (np + 4) * sizeof(PostingRaw)));
         // interleave (row, tf, len) into 8-byte records through a bounded pinned staging buffer
         const uint64_t CH = 8u << 20;
-        OCTRY(c->h_in.ensure(std::min<uint64_t>(np, CH) * sizeof(Posting)));
+        OCTRY(c->h_in.ensure(std::min<uint64_t>(np, CH) * sizeof(PostingRaw)));
         for (uint64_t off = 0; off < np; off += CH) {
             const uint64_t m = std::min<uint64_t>(CH, np - off);
-            Posting *h = c->h_in.as<Posting>();
+            PostingRaw *h = c->h_in.as<PostingRaw>();
             for (uint64_t i = 0; i < m; i++) {
                 if (post_row[off + i] >= s->n_rows && s->n_rows) return fail(OC_ERR_INVALID, "posting row %u >= n_rows", post_row[off + i]);
                 h[i].row = post_row[off + i]; h[i].tf = post_tf[off + i]; h[i].len = post_len[off + i];
             }
-            CU(cudaMemcpyAsync(f.post + off, h, m * sizeof(Posting), cudaMemcpyHostToDevice, c->stream));
+            CU(cudaMemcpyAsync(f.raw + off, h, m * sizeof(PostingRaw), cudaMemcpyHostToDevice, c->stream));
             CU(cudaStreamSynchronize(c->stream));
         }
     }
@@ -711,7 +717,7 @@ extern "C" int oc_str_info(oc_str *s, oc_str_info_t *out) {
     out->total_documents = s->n_rows - s->n_deleted; out->n_fields = (uint32_t)s->fields.size();
     out->total_postings = 0; out->unique_terms_count = 0;
     for (auto &f : s->fields) { out->total_postings += f.n_post; out->unique_terms_count += f.n_terms; }
-    out->device_bytes = out->total_postings * 8 + (s->row_doc ? s->n_rows * 8 : 0);
+    out->device_bytes = out->total_postings * 16 + (s->row_doc ? s->n_rows * 8 : 0);
     return OC_OK;
 }
 
@@ -787,6 +793,13 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
     uint64_t postings_walked = 0;
     const bool thr = p->threshold >= 0.0f;
     if (has_ft) {
+        for (auto &f : str->fields)   // streamed posting format depends on (avg_field_len, b): derive once
+            if (f.n_post && f.b_cached != p->bm25_b) {
+                bm25_derive_postings_kernel<<<(unsigned)((f.n_post + 255) / 256), 256, 0, c->stream>>>(f.raw, f.n_post, f.avg_len, p->bm25_b, f.post);
+                launched(c);
+                CU(cudaGetLastError());
+                f.b_cached = p->bm25_b;
+            }
         const float N = (float)str->document_count;  // token_score.rs:221
         queries.resize(B);
         for (uint32_t q = 0; q < B; q++) {
@@ -980,7 +993,11 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
     uint8_t *dout = c->out_blob.as<uint8_t>();
     FuseParams fp{};
     fp.mode = p->mode; fp.n_tiles = n_tiles; fp.n_keep = n_keep; fp.limit = p->limit; fp.offset = p->offset;
-    fp.capb = std::max<uint32_t>(2048, next_pow2(2 * n_keep));
+    {   // smallest power-of-two key buffer that takes the candidates in one round (sort cost ~ capb log^2 capb)
+        const uint64_t total = (has_ft ? uint64_t(n_tiles) * n_keep : 0) + (has_v ? vlimit : 0);
+        fp.capb = next_pow2((uint32_t)std::min<uint64_t>(2048, std::max<uint64_t>(total, 2 * n_keep)));
+        fp.capb = std::max<uint32_t>(fp.capb, std::max<uint32_t>(64, next_pow2(2 * n_keep)));
+    }
     if (has_ft) {
         fp.cand_key = bp.cand_key; fp.cand_ft = bp.cand_ft; fp.cand_cnt = bp.cand_cnt; fp.tile_count = bp.tile_count;
         fp.tile_max = bp.tile_max; fp.tile_min = bp.tile_min; fp.str_row_doc_ids = str->row_doc;

@@ -34,7 +34,8 @@
 
 namespace oc {
 
-constexpr int GEMM_THREADS = 192;      // warp0: TMA producer, warp1: MMA issuer, warps 2-5: epilogue
+constexpr uint32_t GEMM_EPI_WARPS = 8;  // two warps per TMEM lane quadrant, each takes half of the tile's rows
+constexpr int GEMM_THREADS = 64 + GEMM_EPI_WARPS * 32;   // warp0: TMA producer, warp1: MMA issuer, warps 2-9: epilogue
 constexpr uint32_t GEMM_M = 128;       // queries per CTA
 constexpr uint32_t GEMM_N = 256;       // rows per tile
 constexpr uint32_t GEMM_KB = 32;       // floats per K-block (128 B swizzle row)
@@ -55,13 +56,13 @@ struct GemmParams {
     uint32_t keep;             // K'
     uint32_t cap;              // 2 K'
     unsigned int *tau;         // [n_qgroups*128] ordered-uint running thresholds (init 0)
-    uint64_t *cand;            // [n_qgroups*128][ctas_per_group][cap]
-    uint32_t *cand_cnt;        // [n_qgroups*128][ctas_per_group]
+    uint64_t *cand;            // [n_qgroups*128][ctas_per_group*2][cap]  (two column halves per CTA)
+    uint32_t *cand_cnt;        // [n_qgroups*128][ctas_per_group*2]
 };
 
 __host__ __device__ inline size_t gemm_smem_bytes() {
     return 1024 /*align slack*/ + size_t(GEMM_STAGES) * GEMM_STAGE_BYTES + 2 * GEMM_N * 4 /*inv norms*/ +
-           4 * 128 * 8 /*warp sort scratch*/ + 256 /*barriers, tmem ptr*/;
+           GEMM_EPI_WARPS * 128 * 8 /*warp sort scratch*/ + 256 /*barriers, tmem ptr*/;
 }
 
 // ---- tcgen05 / TMA PTX wrappers ------------------------------------------------------
@@ -122,13 +123,13 @@ constexpr uint64_t TMA_EVICT_LAST = 0x14F0000000000000ull;
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 emb_gemm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_x, const GemmParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    // SWIZZLE_128B tiles need 1024-byte alignment
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t *ring = smem;
-    float *inr_s = reinterpret_cast<float *>(ring + GEMM_STAGES * GEMM_STAGE_BYTES);   // [2][256]
-    uint64_t *scratch = reinterpret_cast<uint64_t *>(inr_s + 2 * GEMM_N);              // [4 warps][128]
-    uint64_t *bars = scratch + 4 * 128;
+    // SWIZZLE_128B tiles need 1024-byte alignment; every pointer below is derived from the
+    // __shared__ array itself so loads/stores stay in the shared address space (LDS/STS).
+    extern __shared__ __align__(1024) uint8_t smem_gemm[];
+    uint8_t *ring = smem_gemm;
+    float *inr_s = reinterpret_cast<float *>(smem_gemm + GEMM_STAGES * GEMM_STAGE_BYTES);   // [2][256]
+    uint64_t *scratch = reinterpret_cast<uint64_t *>(inr_s + 2 * GEMM_N);                  // [8 warps][128]
+    uint64_t *bars = scratch + GEMM_EPI_WARPS * 128;
     uint64_t *full = bars, *empty = bars + GEMM_STAGES;
     uint64_t *tfull = bars + 2 * GEMM_STAGES, *tempty = tfull + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
@@ -142,7 +143,7 @@ emb_gemm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < GEMM_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (uint32_t a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 128); }
+        for (uint32_t a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], GEMM_EPI_WARPS * 32); }
         fence_mbar_init();
         tma_prefetch_desc(&tm_q);
         tma_prefetch_desc(&tm_x);
@@ -198,41 +199,57 @@ emb_gemm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             }
         }
     } else {
-        // ===================== epilogue: thread = TMEM lane = one query =====================
+        // ===================== epilogue: thread = (TMEM lane = one query, one half of the tile's rows) ====
+        const uint32_t ew = warp - 2;                      // 0..7
         const uint32_t quad = warp & 3;                    // TMEM lane quadrant this warp may access
+        const uint32_t half = ew >> 2;                     // columns [128*half, 128*half+128)
         const uint32_t m = quad * 32 + lane;
         const uint32_t q = g * GEMM_M + m;
         const bool live = q < p.n_queries;
-        const uint32_t et = (warp - 2) * 32 + lane;        // 0..127 among epilogue threads
-        uint64_t *mybuf = p.cand + (size_t(q) * p.ctas_per_group + c) * p.cap;
-        uint64_t *wscr = scratch + (warp - 2) * 128;
+        const uint32_t et = ew * 32 + lane;                // 0..255 among epilogue threads
+        const uint32_t lists = p.ctas_per_group * 2;
+        uint64_t *__restrict__ mybuf = p.cand + (size_t(q) * lists + c * 2 + half) * p.cap;
+        uint64_t *wscr = scratch + ew * 128;
         uint32_t cnt = 0;
         float tau = live ? -INFINITY : INFINITY;
         for (uint64_t it = 0; it < my_tiles; it++) {
             const uint32_t acc = uint32_t(it & 1), aph = uint32_t((it >> 1) & 1);
             const uint64_t row0 = (c + it * p.ctas_per_group) * GEMM_N;
             float *inr = inr_s + acc * GEMM_N;
-#pragma unroll
-            for (uint32_t h = 0; h < 2; h++) {
-                const uint64_t r = row0 + et + h * 128;
-                inr[et + h * 128] = r < p.n_rows ? __ldg(p.inv_norm + r) : __int_as_float(0x7fc00000);
+            {
+                const uint64_t r = row0 + et;
+                inr[et] = r < p.n_rows ? __ldg(p.inv_norm + r) : __int_as_float(0x7fc00000);
             }
             if (live) {   // the query's threshold as raised by every CTA so far
                 const unsigned int tg = *reinterpret_cast<volatile unsigned int *>(p.tau + q);
                 if (tg) tau = fmaxf(tau, f32_unordered(tg));
             }
-            named_bar_sync(1, 128);
+            named_bar_sync(1, GEMM_EPI_WARPS * 32);
             mbar_wait(&tfull[acc], aph);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((quad * 32u) << 16) + acc * GEMM_N;
-            for (uint32_t ch = 0; ch < GEMM_N / 32; ch++) {
+            const uint32_t col0 = half * 128;
+            const uint32_t taddr = tmem_base + ((quad * 32u) << 16) + acc * GEMM_N + col0;
+            const float4 *inr4 = reinterpret_cast<const float4 *>(inr + col0);
+            for (uint32_t ch = 0; ch < 4; ch++) {
                 uint32_t d[32];
                 tmem_ld32(taddr + ch * 32, d);
                 tmem_ld_wait();
+                float v[32];
+                uint32_t mask = 0;
 #pragma unroll
-                for (uint32_t j = 0; j < 32; j++) {
-                    const float v = __uint_as_float(d[j]) * inr[ch * 32 + j];   // cos * |q|
-                    if (v > tau) { mybuf[cnt] = make_key(v, uint32_t(row0 + ch * 32 + j)); cnt++; }
+                for (uint32_t j4 = 0; j4 < 8; j4++) {
+                    const float4 w = inr4[ch * 8 + j4];          // LDS.128, warp-wide broadcast
+                    v[4 * j4 + 0] = __uint_as_float(d[4 * j4 + 0]) * w.x;   // cos * |q|
+                    v[4 * j4 + 1] = __uint_as_float(d[4 * j4 + 1]) * w.y;
+                    v[4 * j4 + 2] = __uint_as_float(d[4 * j4 + 2]) * w.z;
+                    v[4 * j4 + 3] = __uint_as_float(d[4 * j4 + 3]) * w.w;
+                }
+#pragma unroll
+                for (uint32_t j = 0; j < 32; j++) mask |= (v[j] > tau ? 1u : 0u) << j;
+                if (mask) {   // rare once the threshold has warmed up
+#pragma unroll
+                    for (uint32_t j = 0; j < 32; j++)
+                        if ((mask >> j) & 1u) { mybuf[cnt] = make_key(v[j], uint32_t(row0 + col0 + ch * 32 + j)); cnt++; }
                 }
                 // warp-cooperative compress of every lane whose buffer could overflow in the next chunk
                 uint32_t need = __ballot_sync(0xffffffffu, cnt + 32 > p.cap);
@@ -240,7 +257,7 @@ emb_gemm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                     const uint32_t l = __ffs(need) - 1;
                     need &= need - 1;
                     const uint32_t lq = g * GEMM_M + quad * 32 + l;
-                    uint64_t *lbuf = p.cand + (size_t(lq) * p.ctas_per_group + c) * p.cap;
+                    uint64_t *lbuf = p.cand + (size_t(lq) * lists + c * 2 + half) * p.cap;
                     const uint32_t lcnt = __shfl_sync(0xffffffffu, cnt, l);
                     __syncwarp();
                     for (uint32_t i = lane; i < 128; i += 32) wscr[i] = i < lcnt ? lbuf[i] : KEY_NONE;
@@ -258,7 +275,7 @@ emb_gemm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             tc_fence_before();
             mbar_arrive(&tempty[acc]);
         }
-        if (live || true) p.cand_cnt[size_t(q) * p.ctas_per_group + c] = live ? cnt : 0;
+        p.cand_cnt[size_t(q) * lists + c * 2 + half] = live ? cnt : 0;
     }
     __syncthreads();
     if (warp == 1) {
@@ -346,6 +363,43 @@ __global__ void __launch_bounds__(256) emb_gemm_merge_kernel(const GemmMergePara
     }
     __syncthreads();
     if (tid == 0) { p.out_count[q] = s_cnt; p.out_unproven[q] = proven ? 0 : 1; }
+}
+
+// Seeds the per-query thresholds before the sweep: exact fp32 scores of the first `n_sample`
+// rows, split into `keep` groups; the minimum of the group maxima is a valid lower bound of
+// the sample's keep-th best score, hence of the global one (minus the tf32 error bound, since
+// the sweep compares tf32 scores).  Without it every CTA starts at -inf and floods its buffers.
+__global__ void __launch_bounds__(256) gemm_seed_tau_kernel(const float *rows, const float *inv_norm, uint32_t stride,
+                                                            uint32_t n_sample, const float *queries, const float *inv_qnorm,
+                                                            uint32_t keep, unsigned int *tau) {
+    __shared__ float gmax[64];
+    const uint32_t q = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t per = n_sample / keep;                 // rows per group
+    const float4 *qp = reinterpret_cast<const float4 *>(queries + size_t(q) * stride);
+    for (uint32_t gidx = warp; gidx < keep; gidx += 8) {
+        float mx = -INFINITY;
+        for (uint32_t r = gidx * per; r < (gidx + 1) * per; r++) {
+            const float4 *rp = reinterpret_cast<const float4 *>(rows + size_t(r) * stride);
+            float acc = 0.f;
+            for (uint32_t j = 0; j < stride / 128; j++) {
+                const float4 x = __ldg(rp + lane + 32 * j), y = __ldg(qp + lane + 32 * j);
+                acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc); acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
+            }
+            const float v = warp_sum(acc) * inv_norm[r];   // cos * |q| ; NaN rows are ignored by fmaxf
+            mx = fmaxf(mx, v);
+        }
+        if (lane == 0) gmax[gidx] = mx;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float mn = INFINITY;
+        for (uint32_t i = 0; i < keep; i++) mn = fminf(mn, gmax[i]);
+        const float iqn = inv_qnorm[q];
+        if (iqn > 0.f && mn > -INFINITY && mn < INFINITY) {
+            const float seed = mn - GEMM_EPS_TF32 / iqn;   // tf32 score of those rows is >= exact - eps*|q|
+            tau[q] = f32_ordered(seed);
+        }
+    }
 }
 
 // copies the exact-path results of re-run queries into their slots of the batch outputs
