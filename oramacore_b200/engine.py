@@ -187,6 +187,28 @@ class StringFieldStorage:
                 "unique_terms_count": i.unique_terms_count, "n_fields": i.n_fields, "device_bytes": i.device_bytes}
 
 
+class TextQueryBatch:
+    """B resolved queries packed as the CSR arrays oc_search takes (q -> tokens -> expanded terms)."""
+
+    def __init__(self, texts: Sequence[TextQuery]):
+        B = len(texts)
+        self.n_queries = B
+        qoff = np.zeros(B + 1, np.uint32)
+        tto, tf_, tid, tw = [np.zeros(1, np.uint32)], [], [], []
+        ntok = nterm = 0
+        for i, t in enumerate(texts):
+            ntok += t.n_tokens
+            qoff[i + 1] = ntok
+            tto.append(t.token_term_offsets[1:].astype(np.uint32) + np.uint32(nterm))
+            nterm += int(t.token_term_offsets[-1])
+            tf_.append(t.term_field); tid.append(t.term_id); tw.append(t.term_weight)
+        self.q_token_offsets = qoff
+        self.token_term_offsets = np.ascontiguousarray(np.concatenate(tto), np.uint32)
+        self.term_field = np.ascontiguousarray(np.concatenate(tf_) if tf_ else np.zeros(0), np.uint32)
+        self.term_id = np.ascontiguousarray(np.concatenate(tid) if tid else np.zeros(0), np.uint32)
+        self.term_weight = np.ascontiguousarray(np.concatenate(tw) if tw else np.zeros(0), np.float32)
+
+
 @dataclass
 class TokenScoreParams:
     """token_score.rs:31-41 (mode already resolved; boost/properties are folded into the
@@ -214,9 +236,18 @@ class TokenScoreContext:
                  string_fields: Optional[StringFieldStorage]):
         self.ctx, self.emb, self.str = ctx, embedding_field, string_fields
 
-    def execute_batch(self, params: TokenScoreParams, texts: Optional[Sequence[TextQuery]] = None,
+    def execute_batch(self, params: TokenScoreParams, texts=None,
                       q_vecs: Optional[np.ndarray] = None) -> List[SearchHits]:
-        B = len(texts) if texts is not None else int(np.asarray(q_vecs).reshape(-1, self.emb.dim).shape[0])
+        docs, scores, n, cnt = self.execute_batch_arrays(params, texts, q_vecs)
+        return [SearchHits(docs[i, :n[i]].copy(), scores[i, :n[i]].copy(), int(cnt[i])) for i in range(docs.shape[0])]
+
+    def execute_batch_arrays(self, params: TokenScoreParams, texts=None, q_vecs: Optional[np.ndarray] = None):
+        """Same call, results as arrays: (doc_ids [B,limit], scores [B,limit], n [B], count [B]).
+        `texts` is a sequence of TextQuery or a pre-packed TextQueryBatch (term resolution happens
+        before the hot path in the reference as well: token_score.rs:196-209)."""
+        if texts is not None and not isinstance(texts, TextQueryBatch):
+            texts = TextQueryBatch(texts)
+        B = texts.n_queries if texts is not None else int(np.asarray(q_vecs).reshape(-1, self.emb.dim).shape[0])
         sp = SearchParams()
         sp.mode = params.mode
         sp.n_queries = B
@@ -230,23 +261,9 @@ class TokenScoreContext:
             keep.append(qv)
             sp.q_vecs = _p(qv)
         if params.mode in (MODE_FULLTEXT, MODE_HYBRID):
-            qoff = np.zeros(B + 1, np.uint32)
-            tto, tf_, tid, tw = [np.zeros(1, np.uint32)], [], [], []
-            ntok = 0
-            nterm = 0
-            for i, t in enumerate(texts):
-                ntok += t.n_tokens
-                qoff[i + 1] = ntok
-                tto.append(t.token_term_offsets[1:].astype(np.uint32) + np.uint32(nterm))
-                nterm += int(t.token_term_offsets[-1])
-                tf_.append(t.term_field); tid.append(t.term_id); tw.append(t.term_weight)
-            a_tto = np.ascontiguousarray(np.concatenate(tto), np.uint32)
-            a_tf = np.ascontiguousarray(np.concatenate(tf_) if tf_ else np.zeros(0), np.uint32)
-            a_tid = np.ascontiguousarray(np.concatenate(tid) if tid else np.zeros(0), np.uint32)
-            a_tw = np.ascontiguousarray(np.concatenate(tw) if tw else np.zeros(0), np.float32)
-            keep += [qoff, a_tto, a_tf, a_tid, a_tw]
-            sp.q_token_offsets, sp.token_term_offsets = _p(qoff), _p(a_tto)
-            sp.term_field, sp.term_id, sp.term_weight = _p(a_tf), _p(a_tid), _p(a_tw)
+            keep.append(texts)
+            sp.q_token_offsets, sp.token_term_offsets = _p(texts.q_token_offsets), _p(texts.token_term_offsets)
+            sp.term_field, sp.term_id, sp.term_weight = _p(texts.term_field), _p(texts.term_id), _p(texts.term_weight)
         if params.filtered_doc_ids is not None:
             fb = np.ascontiguousarray(params.filtered_doc_ids, np.uint64)
             keep.append(fb)
@@ -257,14 +274,13 @@ class TokenScoreContext:
             keep += [od, om]
             sp.omc_doc_ids, sp.omc_mult, sp.n_omc = _p(od), _p(om), od.shape[0]
         sp.sharded = 1 if params.sharded else 0
-        docs = np.zeros((B, params.limit_hint), np.uint64)
-        scores = np.zeros((B, params.limit_hint), np.float32)
-        n = np.zeros(B, np.uint32)
-        cnt = np.zeros(B, np.uint64)
+        docs = np.empty((B, params.limit_hint), np.uint64)
+        scores = np.empty((B, params.limit_hint), np.float32)
+        n = np.empty(B, np.uint32)
+        cnt = np.empty(B, np.uint64)
         check(lib().oc_search(self.ctx._h, self.emb._h if self.emb else None, self.str._h if self.str else None,
                               C.byref(sp), _p(docs), _p(scores), _p(n), _p(cnt)))
-        self.last_raw = (docs, scores, n, cnt)
-        return [SearchHits(docs[i, :n[i]].copy(), scores[i, :n[i]].copy(), int(cnt[i])) for i in range(B)]
+        return docs, scores, n, cnt
 
     def execute(self, params: TokenScoreParams, results: Dict[int, float], text: Optional[TextQuery] = None,
                 q_vec: Optional[np.ndarray] = None) -> int:
