@@ -1,0 +1,119 @@
+//! Bindings for `include/oramacore_b200.h` (C ABI of the B200-native search hot path) and safe
+//! wrappers shaped like the reference types they replace:
+//!   * `EmbeddingField`  ~ `EmbeddingFieldStorage` (read/index/embedding_field.rs:29-34)
+//!   * `StringFields`    ~ the `StringFieldStorage` set of an Index (read/index/string_field.rs:32-36)
+//!   * `Ctx::search`     ~ `TokenScoreContext::execute` + OMC + count + top-N
+//!                         (token_score.rs:460-509, search.rs:39-48, 482-498, sort.rs:260-279)
+//! SOURCE ONLY: the build image has no Rust toolchain; the identical ABI is exercised by the
+//! ctypes mirror (`oramacore_b200/_lib.py`) and the GPU parity tests.
+use std::ffi::{c_char, c_int, c_void, CStr};
+
+#[repr(C)] pub struct OcCtx { _p: [u8; 0] }
+#[repr(C)] pub struct OcEmb { _p: [u8; 0] }
+#[repr(C)] pub struct OcStr { _p: [u8; 0] }
+
+pub const OC_MODE_FULLTEXT: c_int = 0;
+pub const OC_MODE_VECTOR: c_int = 1;
+pub const OC_MODE_HYBRID: c_int = 2;
+
+#[repr(C)]
+pub struct OcSearchParams {
+    pub mode: c_int,
+    pub n_queries: u32,
+    pub limit: u32,
+    pub offset: u32,
+    pub similarity: f32,
+    pub threshold: f32, // < 0 => None
+    pub bm25_k: f32,
+    pub bm25_b: f32,
+    pub q_vecs: *const f32,
+    pub q_token_offsets: *const u32,
+    pub token_term_offsets: *const u32,
+    pub term_field: *const u32,
+    pub term_id: *const u32,
+    pub term_weight: *const f32,
+    pub filter_bits: *const u64,
+    pub filter_nbits: u64,
+    pub omc_doc_ids: *const u64,
+    pub omc_mult: *const f32,
+    pub n_omc: u64,
+    pub sharded: c_int,
+}
+
+extern "C" {
+    pub fn oc_last_error() -> *const c_char;
+    pub fn oc_abi_sizes(out: *mut usize);
+    pub fn oc_init(device_id: c_int, out: *mut *mut OcCtx) -> c_int;
+    pub fn oc_shutdown(ctx: *mut OcCtx);
+    pub fn oc_comm_unique_id(out_id: *mut u8) -> c_int;
+    pub fn oc_comm_init(ctx: *mut OcCtx, world: c_int, rank: c_int, id: *const u8) -> c_int;
+    pub fn oc_emb_create(ctx: *mut OcCtx, dim: u32, dtype: c_int, rescale_e5: c_int, out: *mut *mut OcEmb) -> c_int;
+    pub fn oc_emb_destroy(emb: *mut OcEmb);
+    pub fn oc_emb_insert(emb: *mut OcEmb, doc_ids: *const u64, rows: *const c_void, n: u64) -> c_int;
+    pub fn oc_emb_delete(emb: *mut OcEmb, doc_ids: *const u64, n: u64) -> c_int;
+    pub fn oc_emb_search(emb: *mut OcEmb, queries: *const f32, b: u32, limit: u32, similarity: f32,
+                         filter_bits: *const u64, filter_nbits: u64, out_doc_ids: *mut u64,
+                         out_scores: *mut f32, out_counts: *mut u32) -> c_int;
+    pub fn oc_str_create(ctx: *mut OcCtx, n_fields: u32, out: *mut *mut OcStr) -> c_int;
+    pub fn oc_str_destroy(s: *mut OcStr);
+    pub fn oc_str_set_rows(s: *mut OcStr, n_rows: u64, row_doc_ids: *const u64, document_count: u64) -> c_int;
+    pub fn oc_str_load_field(s: *mut OcStr, field: u32, avg_field_len: f32, n_terms: u32, term_offsets: *const u64,
+                             post_row: *const u32, post_tf: *const u16, post_len: *const u16,
+                             global_df: *const u32) -> c_int;
+    pub fn oc_str_delete(s: *mut OcStr, doc_ids: *const u64, n: u64) -> c_int;
+    pub fn oc_search(ctx: *mut OcCtx, emb: *mut OcEmb, s: *mut OcStr, p: *const OcSearchParams,
+                     out_doc_ids: *mut u64, out_scores: *mut f32, out_n: *mut u32, out_count: *mut u64) -> c_int;
+}
+
+fn check(rc: c_int) -> anyhow::Result<()> {
+    if rc == 0 { return Ok(()); }
+    let msg = unsafe { CStr::from_ptr(oc_last_error()) }.to_string_lossy().into_owned();
+    anyhow::bail!("oramacore_b200 error {rc}: {msg}")
+}
+
+pub struct Ctx(*mut OcCtx);
+unsafe impl Send for Ctx {}
+unsafe impl Sync for Ctx {}
+impl Ctx {
+    pub fn new(device: i32) -> anyhow::Result<Self> {
+        let mut sizes = [0usize; 4];
+        unsafe { oc_abi_sizes(sizes.as_mut_ptr()) };
+        assert_eq!(sizes[0], std::mem::size_of::<OcSearchParams>(), "oc_search_params layout drift");
+        let mut p = std::ptr::null_mut();
+        check(unsafe { oc_init(device, &mut p) })?;
+        Ok(Ctx(p))
+    }
+}
+impl Drop for Ctx { fn drop(&mut self) { unsafe { oc_shutdown(self.0) } } }
+
+/// `EmbeddingFieldStorage` (embedding_field.rs): same method shapes.
+pub struct EmbeddingField { h: *mut OcEmb, dim: usize }
+unsafe impl Send for EmbeddingField {}
+unsafe impl Sync for EmbeddingField {}
+impl EmbeddingField {
+    pub fn new(ctx: &Ctx, dimensions: usize, is_e5: bool) -> anyhow::Result<Self> {
+        let mut h = std::ptr::null_mut();
+        check(unsafe { oc_emb_create(ctx.0, dimensions as u32, 0, is_e5 as c_int, &mut h) })?;
+        Ok(Self { h, dim: dimensions })
+    }
+    /// insert(DocumentId, Vec<Vec<f32>>)  (embedding_field.rs:232-237)
+    pub fn insert(&self, doc_id: u64, vectors: &[Vec<f32>]) -> anyhow::Result<()> {
+        let flat: Vec<f32> = vectors.iter().flat_map(|v| v.iter().copied()).collect();
+        debug_assert_eq!(flat.len(), vectors.len() * self.dim);
+        let ids = vec![doc_id; vectors.len()];
+        check(unsafe { oc_emb_insert(self.h, ids.as_ptr(), flat.as_ptr() as *const c_void, ids.len() as u64) })
+    }
+    /// delete(DocumentId)  (embedding_field.rs:240-242)
+    pub fn delete(&self, doc_id: u64) -> anyhow::Result<()> { check(unsafe { oc_emb_delete(self.h, &doc_id, 1) }) }
+    /// search(&VectorSearchParams, &mut HashMap)  (embedding_field.rs:250-278): `output[doc] += score`
+    pub fn search(&self, target: &[f32], similarity: f32, limit: usize, filter: Option<(&[u64], u64)>,
+                  output: &mut std::collections::HashMap<u64, f32>) -> anyhow::Result<()> {
+        let (mut docs, mut scores, mut n) = (vec![0u64; limit], vec![0f32; limit], 0u32);
+        let (fb, nb) = filter.map(|(b, n)| (b.as_ptr(), n)).unwrap_or((std::ptr::null(), 0));
+        check(unsafe { oc_emb_search(self.h, target.as_ptr(), 1, limit as u32, similarity, fb, nb,
+                                     docs.as_mut_ptr(), scores.as_mut_ptr(), &mut n) })?;
+        for i in 0..n as usize { *output.entry(docs[i]).or_insert(0.0) += scores[i]; }
+        Ok(())
+    }
+}
+impl Drop for EmbeddingField { fn drop(&mut self) { unsafe { oc_emb_destroy(self.h) } } }
