@@ -29,7 +29,7 @@
 namespace oc {
 
 constexpr uint32_t BM25_TILE = 16384;          // rows per tile
-constexpr uint32_t BM25_THREADS = 256;
+constexpr uint32_t BM25_THREADS = 512;
 constexpr uint32_t BM25_CHUNK = BM25_THREADS * 4;
 
 struct PostingRaw {    // 8 bytes, as handed over by the host (string_field.rs:162: field_length is u16)
@@ -145,7 +145,7 @@ __host__ __device__ inline size_t bm25_smem_bytes(bool multi, bool threshold, bo
     if (multi || omc) b += size_t(BM25_TILE) * 4;     // S / omc multipliers
     if (threshold) b += size_t(BM25_TILE) * 4;        // token masks
     b += size_t(BM25_TILE) / 8;                       // row_ok bits
-    b += size_t(cap) * 12;                            // top buffer keys + ft
+    b += size_t(cap) * 8;                             // top buffer keys (ft is re-read from score[])
     return b + 64;
 }
 
@@ -237,7 +237,6 @@ __global__ void __launch_bounds__(BM25_THREADS) bm25_tile_kernel(const Bm25Param
     uint32_t *mask = reinterpret_cast<uint32_t *>(score + BM25_TILE * ((MULTI || OMC) ? 2 : 1));
     uint32_t *okb = mask + (THRESH ? BM25_TILE : 0);
     uint64_t *tbuf = reinterpret_cast<uint64_t *>(okb + BM25_TILE / 32);
-    float *tft = reinterpret_cast<float *>(tbuf + p.cap);
     __shared__ uint32_t s_cnt, s_matched;
     __shared__ unsigned int s_maxo, s_mino;   // extrema in order-preserving uint space
     __shared__ unsigned long long s_tau;
@@ -260,22 +259,56 @@ __global__ void __launch_bounds__(BM25_THREADS) bm25_tile_kernel(const Bm25Param
     if (tid == 0) { s_cnt = 0; s_matched = 0; s_maxo = f32_ordered(0.f); s_mino = f32_ordered(0.f); s_tau = p.tau[q]; }
     __syncthreads();
 
-    // ------------------------------------------------ accumulate, token by token
-    for (uint32_t t = qd.token_begin; t < qd.token_end; t++) {
-        const TokenDesc tk = p.tokens[t];
-        const bool single = !MULTI || (tk.term_end - tk.term_begin == 1);
-        for (uint32_t e = tk.term_begin; e < tk.term_end; e++) {
-            const TermDesc td = p.terms[e];
-            const uint32_t *sg = p.seg + size_t(e) * (p.n_tiles + 1);
-            const uint32_t lo = sg[tile], hi = sg[tile + 1];
-            const uint2 *pp = reinterpret_cast<const uint2 *>(td.ptr);
-            for (uint32_t base = lo; base < hi; base += BM25_THREADS * 4) {
-                uint2 rec[4];
+    // ------------------------------------------------ accumulate, token by token, term by term.
+    // Software pipelined: the next term's sub-range bounds and its first batch of postings are
+    // requested before the barrier that closes the current term, so their latency hides behind it.
+    {
+        uint32_t t = qd.token_begin, e = 0;
+        TokenDesc tk{};
+        bool have = false;
+        for (; t < qd.token_end; t++) {
+            tk = p.tokens[t];
+            if (tk.term_begin < tk.term_end) { e = tk.term_begin; have = true; break; }
+        }
+        TermDesc td{};
+        uint32_t lo = 0, hi = 0;
+        uint2 rec[4];
+        auto fetch = [&](const TermDesc &d, uint32_t base, uint32_t end, uint2 (&r)[4]) {
+            const uint2 *pp = reinterpret_cast<const uint2 *>(d.ptr);
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const uint32_t pi = base + tid + u * BM25_THREADS;
-                    rec[u] = pi < hi ? __ldg(pp + pi) : make_uint2(0xffffffffu, 0u);
+            for (int u = 0; u < 4; u++) {
+                const uint32_t pi = base + tid + u * BM25_THREADS;
+                r[u] = pi < end ? __ldg(pp + pi) : make_uint2(0xffffffffu, 0u);
+            }
+        };
+        if (have) {
+            td = p.terms[e];
+            const uint32_t *sg = p.seg + size_t(e) * (p.n_tiles + 1);
+            lo = sg[tile]; hi = sg[tile + 1];
+            fetch(td, lo, hi, rec);
+        }
+        while (have) {
+            // successor term (block-uniform control flow)
+            uint32_t nt = t, ne = e + 1;
+            TokenDesc ntk = tk;
+            bool nhave = true;
+            if (ne >= tk.term_end) {
+                nhave = false;
+                for (nt = t + 1; nt < qd.token_end; nt++) {
+                    ntk = p.tokens[nt];
+                    if (ntk.term_begin < ntk.term_end) { ne = ntk.term_begin; nhave = true; break; }
                 }
+            }
+            TermDesc nd{};
+            uint32_t nlo = 0, nhi = 0;
+            if (nhave) {
+                nd = p.terms[ne];
+                const uint32_t *nsg = p.seg + size_t(ne) * (p.n_tiles + 1);
+                nlo = nsg[tile]; nhi = nsg[tile + 1];
+            }
+            const bool single = !MULTI || (tk.term_end - tk.term_begin == 1);
+            for (uint32_t base = lo; base < hi; base += BM25_THREADS * 4) {
+                if (base != lo) fetch(td, base, hi, rec);
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
                     if (rec[u].x == 0xffffffffu) continue;
@@ -296,27 +329,32 @@ __global__ void __launch_bounds__(BM25_THREADS) bm25_tile_kernel(const Bm25Param
                     }
                 }
             }
+            uint2 nrec[4];
+            if (nhave) fetch(nd, nlo, nhi, nrec);
             __syncthreads();  // next term / token may touch the same rows
-        }
-        if (MULTI && !single) {
-            // finalize_term: drain S over the rows this token touched (second walk, L2-hot)
-            for (uint32_t e = tk.term_begin; e < tk.term_end; e++) {
-                const TermDesc td = p.terms[e];
-                const uint32_t *sg = p.seg + size_t(e) * (p.n_tiles + 1);
-                const uint32_t lo = sg[tile], hi = sg[tile + 1];
-                for (uint32_t pi = lo + tid; pi < hi; pi += BM25_THREADS) {
-                    const uint32_t l = td.ptr[pi].row - row0;
-                    const float S = __uint_as_float(atomicExch(reinterpret_cast<unsigned int *>(&aux[l]), 0u));
-                    if (f32_is_normal(S)) {
-                        const float c = bm25_sat(S, p.k, kp1, tk.idf);
-                        if (c == c) {
-                            score[l] = __fadd_rn(score[l], c);
-                            if (THRESH) mask[l] |= tk.bit;
+            if (MULTI && !single && e + 1 == tk.term_end) {
+                // finalize_term: drain S over the rows this token touched (second walk, L2-hot)
+                for (uint32_t fe = tk.term_begin; fe < tk.term_end; fe++) {
+                    const TermDesc fd = p.terms[fe];
+                    const uint32_t *sg = p.seg + size_t(fe) * (p.n_tiles + 1);
+                    const uint32_t flo = sg[tile], fhi = sg[tile + 1];
+                    for (uint32_t pi = flo + tid; pi < fhi; pi += BM25_THREADS) {
+                        const uint32_t l = fd.ptr[pi].row - row0;
+                        const float S = __uint_as_float(atomicExch(reinterpret_cast<unsigned int *>(&aux[l]), 0u));
+                        if (f32_is_normal(S)) {
+                            const float c = bm25_sat(S, p.k, kp1, tk.idf);
+                            if (c == c) {
+                                score[l] = __fadd_rn(score[l], c);
+                                if (THRESH) mask[l] |= tk.bit;
+                            }
                         }
                     }
+                    __syncthreads();
                 }
-                __syncthreads();
             }
+            t = nt; e = ne; tk = ntk; td = nd; lo = nlo; hi = nhi; have = nhave;
+#pragma unroll
+            for (int u = 0; u < 4; u++) rec[u] = nrec[u];
         }
     }
 
@@ -386,7 +424,6 @@ __global__ void __launch_bounds__(BM25_THREADS) bm25_tile_kernel(const Bm25Param
                     if (key > tau) {
                         const uint32_t slot = atomicAdd(&s_cnt, 1u);
                         tbuf[slot] = key;   // slot < cap guaranteed by the compress rule below
-                        tft[slot] = s;
                         pushed = true;
                     }
                 }
@@ -402,7 +439,6 @@ __global__ void __launch_bounds__(BM25_THREADS) bm25_tile_kernel(const Bm25Param
             const uint32_t kept = min(c, p.n_keep);
             if (tid == 0) s_cnt = kept;
             if (kept == p.n_keep) { tau = max(tau, (unsigned long long)tbuf[p.n_keep - 1]); tau_f = key_score(tau); }
-            for (uint32_t i = tid; i < kept; i += BM25_THREADS) tft[i] = score[key_idx(tbuf[i]) - row0];
             __syncthreads();
         }
     }
@@ -426,13 +462,11 @@ __global__ void __launch_bounds__(BM25_THREADS) bm25_tile_kernel(const Bm25Param
     if (c >= p.n_keep && c > 0) {
         block_keep_top(tbuf, c, p.cap, p.n_keep, tid);
         c = p.n_keep;
-        for (uint32_t i = tid; i < c; i += BM25_THREADS) tft[i] = score[key_idx(tbuf[i]) - row0];
-        __syncthreads();
         if (tid == 0) atomicMax(p.tau + q, (unsigned long long)tbuf[p.n_keep - 1]);
     }
     for (uint32_t i = tid; i < c; i += BM25_THREADS) {
         p.cand_key[slot_base * p.n_keep + i] = tbuf[i];
-        p.cand_ft[slot_base * p.n_keep + i] = tft[i];
+        p.cand_ft[slot_base * p.n_keep + i] = score[key_idx(tbuf[i]) - row0];
     }
     if (tid == 0) {
         p.cand_cnt[slot_base] = c;

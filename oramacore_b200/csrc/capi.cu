@@ -926,7 +926,8 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
     }
 
     // ------------------------------------------------------------ fulltext stage + fusion (re-runnable)
-    const uint32_t cap = next_pow2(n_keep + BM25_CHUNK);
+    // arg-max selection (n_keep <= 32) needs no power-of-two buffer; the bitonic fallback does
+    const uint32_t cap = n_keep <= 32 ? n_keep + BM25_CHUNK : next_pow2(n_keep + BM25_CHUNK);
     Bm25Params bp{};
     float *min_hint_dev = nullptr;
     const size_t o_doc = 0, o_sc = size_t(B) * p->limit * 8, o_n = o_sc + size_t(B) * p->limit * 4;

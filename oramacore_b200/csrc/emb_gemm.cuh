@@ -308,10 +308,33 @@ __global__ void __launch_bounds__(256) emb_gemm_merge_kernel(const GemmMergePara
     const uint64_t total = uint64_t(p.ctas_per_group) * p.cap;
     const uint64_t *src = p.cand + size_t(q) * total;
     const uint32_t *cnts = p.cand_cnt + size_t(q) * p.ctas_per_group;
-    const uint32_t got = block_topn_stream(buf, 2048, p.keep, total, [&](uint64_t i) -> uint64_t {
-        const uint32_t cta = uint32_t(i / p.cap), k = uint32_t(i % p.cap);
-        return k < cnts[cta] ? src[i] : KEY_NONE;
-    });
+    // the lists are mostly empty once the thresholds have warmed up: gather the valid keys into a
+    // dense array (exclusive scan of the counts) and sort just that; stream only if it overflows
+    __shared__ uint32_t s_off[512];
+    __shared__ uint32_t s_valid;
+    uint32_t got;
+    if (tid == 0) {
+        uint32_t acc = 0;
+        for (uint32_t l = 0; l < p.ctas_per_group && l < 512; l++) { s_off[l] = acc; acc += min(cnts[l], p.cap); }
+        s_valid = p.ctas_per_group <= 512 ? acc : 0xffffffffu;
+    }
+    __syncthreads();
+    if (s_valid <= 2048u) {
+        const uint32_t nv = s_valid;
+        const uint32_t np2 = max(64u, next_pow2(nv));
+        for (uint32_t l = tid; l < p.ctas_per_group; l += blockDim.x) {
+            const uint32_t c = min(cnts[l], p.cap), o = s_off[l];
+            for (uint32_t k = 0; k < c; k++) buf[o + k] = src[size_t(l) * p.cap + k];
+        }
+        for (uint32_t i = nv + tid; i < np2; i += blockDim.x) buf[i] = KEY_NONE;
+        group_bitonic_desc(buf, np2, tid, blockDim.x, 0);
+        got = min(nv, p.keep);
+    } else {
+        got = block_topn_stream(buf, 2048, p.keep, total, [&](uint64_t i) -> uint64_t {
+            const uint32_t cta = uint32_t(i / p.cap), k = uint32_t(i % p.cap);
+            return k < cnts[cta] ? src[i] : KEY_NONE;
+        });
+    }
     const float iqn = p.inv_qnorm[q];
     const float a_keep = got == p.keep ? key_score(buf[p.keep - 1]) * iqn : -INFINITY;   // approx cosine of the K'-th
     // exact fp32 re-score, one warp per candidate, K1's lane layout and FMA order

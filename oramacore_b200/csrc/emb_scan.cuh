@@ -288,7 +288,35 @@ __global__ void __launch_bounds__(256) emb_scan_merge_kernel(const ScanMergePara
     const uint32_t q = blockIdx.x;
     const uint64_t total = uint64_t(p.n_lists) * p.n_keep;
     const uint64_t *src = p.cand + size_t(q) * total;
-    const uint32_t got = block_topn_stream(buf, p.capb, p.limit, total, [&](uint64_t i) { return src[i]; });
+    uint32_t got;
+    if (p.limit <= 32 && p.n_lists <= blockDim.x) {
+        // the per-CTA lists are already sorted: `limit` rounds of a block arg-max over the list heads
+        __shared__ uint64_t s_wk[8];
+        __shared__ uint32_t s_wt[8];
+        uint32_t head = 0;
+        const uint64_t *mine = src + size_t(threadIdx.x) * p.n_keep;
+        uint32_t n_real = 0;
+        for (uint32_t r = 0; r < p.limit; r++) {
+            uint64_t best = (threadIdx.x < p.n_lists && head < p.n_keep) ? mine[head] : KEY_NONE;
+            uint32_t who = threadIdx.x;
+            for (int o = 16; o > 0; o >>= 1) {
+                const uint64_t ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const uint32_t ow = __shfl_xor_sync(0xffffffffu, who, o);
+                if (ob > best) { best = ob; who = ow; }
+            }
+            if ((threadIdx.x & 31) == 0) { s_wk[threadIdx.x >> 5] = best; s_wt[threadIdx.x >> 5] = who; }
+            __syncthreads();
+            uint64_t b = s_wk[0]; uint32_t bw = s_wt[0];
+            for (uint32_t w = 1; w < blockDim.x / 32; w++) if (s_wk[w] > b) { b = s_wk[w]; bw = s_wt[w]; }
+            if (threadIdx.x == bw && b != KEY_NONE) head++;
+            if (threadIdx.x == 0) buf[r] = b;
+            if (b != KEY_NONE) n_real++;
+            __syncthreads();
+        }
+        got = n_real;
+    } else {
+        got = block_topn_stream(buf, p.capb, p.limit, total, [&](uint64_t i) { return src[i]; });
+    }
     __shared__ uint32_t s_cnt;
     if (threadIdx.x == 0) s_cnt = 0;
     __syncthreads();
