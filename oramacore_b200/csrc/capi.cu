@@ -118,7 +118,7 @@ struct oc_ctx {
     DevBuf seg, df_dev, row_ok, tau, cand_key, cand_ft, cand_cnt, tile_cnt, tile_max, tile_min, min_hint;
     DevBuf out_blob, shard_send, shard_recv;
     bool gemm_pending = false; const float *gemm_inv_norm = nullptr;
-    DevBuf g_tau, g_cand, g_cnt, g_flag, r_qpad, r_qinv, r_map, r_doc, r_score, r_row, r_cnt, r_raw;
+    DevBuf g_tau, g_cand, g_cnt, g_flag, g_max, r_qpad, r_qinv, r_map, r_doc, r_score, r_row, r_cnt, r_raw;
 
     HostBuf h_in, h_out;
     OcComm comm;
@@ -159,7 +159,7 @@ extern "C" void oc_shutdown(oc_ctx *c) {
     DevBuf *bufs[] = {&c->in_blob, &c->q_pad, &c->q_inv, &c->eff_norm, &c->filter_dev, &c->scan_cand, &c->v_doc,
                       &c->v_score, &c->v_row, &c->v_cnt, &c->v_srow, &c->v_ft, &c->v_present, &c->v_raw, &c->seg, &c->df_dev,
                       &c->row_ok, &c->tau, &c->cand_key, &c->cand_ft, &c->cand_cnt, &c->tile_cnt, &c->tile_max,
-                      &c->tile_min, &c->min_hint, &c->out_blob, &c->shard_send, &c->shard_recv, &c->g_tau, &c->g_cand, &c->g_cnt,
+                      &c->tile_min, &c->min_hint, &c->out_blob, &c->shard_send, &c->shard_recv, &c->g_tau, &c->g_cand, &c->g_cnt, &c->g_max,
                       &c->g_flag, &c->r_qpad, &c->r_qinv, &c->r_map, &c->r_doc, &c->r_score, &c->r_row, &c->r_cnt, &c->r_raw};
     for (DevBuf *b : bufs) b->release();
     c->h_in.release(); c->h_out.release();
@@ -471,35 +471,52 @@ static int run_vector_stage(oc_ctx *c, oc_emb *e, const float *q_dev, uint32_t B
 
     // ---------------- K2: tcgen05 tf32 batched scan ----------------
     const uint32_t keep = limit <= 16 ? 32 : 64, cap = 128;   // cap == warp sort scratch; compress when > 96
-    const uint32_t cpg = std::max<uint32_t>(1, c->prop.multiProcessorCount / n_qgroups);
-    const uint32_t grid = cpg * n_qgroups;
+    // NG = 2: one CTA serves two query groups against each staged X tile (one copy of X per 256 queries)
+    const int NG = n_qgroups >= 2 ? 2 : 1;
+    const uint32_t n_super = NG == 1 ? n_qgroups : (n_qgroups + 1) / 2;
+    const uint32_t cpg = std::max<uint32_t>(1, c->prop.multiProcessorCount / n_super);
+    const uint32_t grid = cpg * n_super;
+    const uint32_t lists = NG == 1 ? cpg * 2 : cpg;
+    const uint32_t Bpad2 = n_super * NG * GEMM_M;   // query rows the kernel may address (TMA zero-fills beyond the tensor)
     CUtensorMap tm_q, tm_x;
     OCTRY(make_tmap_2d(&tm_q, c->q_pad.as<float>(), Bpad, e->stride, GEMM_M));
     OCTRY(make_tmap_2d(&tm_x, e->rows, e->n_rows, e->stride, GEMM_N));
-    OCTRY(c->g_tau.ensure(size_t(Bpad) * 4));
-    OCTRY(c->g_cand.ensure(size_t(Bpad) * cpg * 2 * cap * 8));
-    OCTRY(c->g_cnt.ensure(size_t(Bpad) * cpg * 2 * 4));
+    OCTRY(c->g_tau.ensure(size_t(Bpad2) * 4));
+    OCTRY(c->g_cand.ensure(size_t(Bpad2) * lists * cap * 8));
+    OCTRY(c->g_cnt.ensure(size_t(Bpad2) * lists * 4));
     OCTRY(c->g_flag.ensure(B));
-    CU(cudaMemsetAsync(c->g_tau.p, 0, size_t(Bpad) * 4, c->stream));
-    gemm_seed_tau_kernel<<<B, 256, 0, c->stream>>>(e->rows, inv_norm, e->stride, 1024, c->q_pad.as<float>(),
-                                                   c->q_inv.as<float>(), keep, c->g_tau.as<unsigned int>());
-    launched(c);
+    CU(cudaMemsetAsync(c->g_tau.p, 0, size_t(Bpad2) * 4, c->stream));
+    OCTRY(c->g_max.ensure(size_t(Bpad2) * lists * 4));
     GemmParams gp{};
     gp.n_rows = e->n_rows; gp.n_kblocks = e->stride / GEMM_KB; gp.inv_norm = inv_norm; gp.n_queries = B;
-    gp.n_qgroups = n_qgroups; gp.ctas_per_group = cpg; gp.keep = keep; gp.cap = cap;
+    gp.n_qgroups = n_qgroups; gp.ctas_per_group = cpg; gp.keep = keep; gp.cap = cap; gp.lists_per_query = lists;
     gp.tau = c->g_tau.as<unsigned int>(); gp.cand = c->g_cand.as<uint64_t>(); gp.cand_cnt = c->g_cnt.as<uint32_t>();
+    gp.gmax = c->g_max.as<float>();
     static bool gemm_cfg = false;
     if (!gemm_cfg) {
-        CU(cudaFuncSetAttribute(emb_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes()));
+        CU(cudaFuncSetAttribute(emb_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes(1)));
+        CU(cudaFuncSetAttribute(emb_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes(2)));
         gemm_cfg = true;
     }
-    emb_gemm_kernel<<<grid, GEMM_THREADS, gemm_smem_bytes(), c->stream>>>(tm_q, tm_x, gp);
-    launched(c, true);
-    CU(cudaGetLastError());
+    auto launch_gemm = [&]() -> int {
+        if (NG == 1) emb_gemm_kernel<1><<<grid, GEMM_THREADS, gemm_smem_bytes(1), c->stream>>>(tm_q, tm_x, gp);
+        else emb_gemm_kernel<2><<<grid, GEMM_THREADS, gemm_smem_bytes(2), c->stream>>>(tm_q, tm_x, gp);
+        launched(c, gp.max_mode == 0);   // the one-tile threshold pass is not counted as a sweep
+        CU(cudaGetLastError());
+        return OC_OK;
+    };
+    // threshold pass: one row tile per CTA, record per-list maxima, derive each query's tau
+    gp.max_mode = 1; gp.tile_limit = 1;
+    OCTRY(launch_gemm());
+    gemm_tau_from_max_kernel<<<B, 256, 0, c->stream>>>(c->g_max.as<float>(), lists, keep, c->g_tau.as<unsigned int>());
+    launched(c);
+    // the sweep
+    gp.max_mode = 0; gp.tile_limit = 0;
+    OCTRY(launch_gemm());
     c->timing.scan_bytes += e->n_rows * (uint64_t(e->stride) * 4 + 4);
     CU(cudaEventRecord(c->ev[EV_SCAN1], c->stream));
     GemmMergeParams mp{};
-    mp.cand = gp.cand; mp.cand_cnt = gp.cand_cnt; mp.ctas_per_group = cpg * 2; mp.cap = cap; mp.keep = keep; mp.limit = limit;
+    mp.cand = gp.cand; mp.cand_cnt = gp.cand_cnt; mp.ctas_per_group = lists; mp.cap = cap; mp.keep = keep; mp.limit = limit;
     mp.rows = e->rows; mp.stride = e->stride; mp.inv_norm = inv_norm; mp.queries = c->q_pad.as<float>();
     mp.inv_qnorm = c->q_inv.as<float>(); mp.row_doc_ids = e->row_doc; mp.rescale_e5 = e->e5; mp.similarity = similarity;
     mp.out_doc = out.doc; mp.out_score = out.score; mp.out_row = out.row; mp.out_count = out.cnt; mp.out_raw = out.raw;

@@ -56,12 +56,17 @@ struct GemmParams {
     uint32_t keep;             // K'
     uint32_t cap;              // 2 K'
     unsigned int *tau;         // [n_qgroups*128] ordered-uint running thresholds (init 0)
-    uint64_t *cand;            // [n_qgroups*128][ctas_per_group*2][cap]  (two column halves per CTA)
-    uint32_t *cand_cnt;        // [n_qgroups*128][ctas_per_group*2]
+    uint32_t lists_per_query;  // candidate lists per query (NG=1: 2 per row partition, NG=2: 1)
+    int max_mode;              // 1 => threshold pass: record each list's best tf32 score, push nothing
+    uint32_t tile_limit;       // max row tiles per CTA (0 = all); the threshold pass looks at one
+    float *gmax;               // [n_qgroups*128][lists_per_query] best score per list (max_mode)
+    uint64_t *cand;            // [n_qgroups*128][lists_per_query][cap]
+    uint32_t *cand_cnt;        // [n_qgroups*128][lists_per_query]
 };
 
-__host__ __device__ inline size_t gemm_smem_bytes() {
-    return 1024 /*align slack*/ + size_t(GEMM_STAGES) * GEMM_STAGE_BYTES + 2 * GEMM_N * 4 /*inv norms*/ +
+__host__ __device__ inline size_t gemm_smem_bytes(int ng) {
+    const size_t ring = ng == 1 ? size_t(4) * (GEMM_A_BYTES + GEMM_B_BYTES) : size_t(3) * (2 * GEMM_A_BYTES + GEMM_B_BYTES);
+    return 1024 /*align slack*/ + ring + 2 * GEMM_N * 4 /*inv norms*/ +
            GEMM_EPI_WARPS * 128 * 8 /*warp sort scratch*/ + 256 /*barriers, tmem ptr*/;
 }
 
@@ -121,34 +126,48 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 constexpr uint64_t TMA_EVICT_FIRST = 0x12F0000000000000ull;
 constexpr uint64_t TMA_EVICT_LAST = 0x14F0000000000000ull;
 
+// NG = query groups (of 128) handled by ONE CTA against each streamed row tile:
+//   NG=1: accumulator double-buffered across tiles (2 x 256 TMEM columns), 4 smem stages of 48 KB;
+//         several CTAs (one per group) walk the same rows.
+//   NG=2: both groups consume the SAME staged X tile (one copy of X per CTA instead of one per
+//         group: L2->SM traffic per 256 rows x 256 queries drops from 96 KB to 64 KB per K-block),
+//         one accumulator per group (2 x 256 columns), 3 stages of 64 KB; every CTA is a row partition.
+template <int NG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 emb_gemm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_x, const GemmParams p) {
     // SWIZZLE_128B tiles need 1024-byte alignment; every pointer below is derived from the
     // __shared__ array itself so loads/stores stay in the shared address space (LDS/STS).
     extern __shared__ __align__(1024) uint8_t smem_gemm[];
+    constexpr uint32_t STAGES = NG == 1 ? 4 : 3;
+    constexpr uint32_t STAGE_BYTES = NG * GEMM_A_BYTES + GEMM_B_BYTES;
     uint8_t *ring = smem_gemm;
-    float *inr_s = reinterpret_cast<float *>(smem_gemm + GEMM_STAGES * GEMM_STAGE_BYTES);   // [2][256]
-    uint64_t *scratch = reinterpret_cast<uint64_t *>(inr_s + 2 * GEMM_N);                  // [8 warps][128]
+    float *inr_s = reinterpret_cast<float *>(smem_gemm + STAGES * STAGE_BYTES);   // [2][256]
+    uint64_t *scratch = reinterpret_cast<uint64_t *>(inr_s + 2 * GEMM_N);          // [8 warps][128]
     uint64_t *bars = scratch + GEMM_EPI_WARPS * 128;
-    uint64_t *full = bars, *empty = bars + GEMM_STAGES;
-    uint64_t *tfull = bars + 2 * GEMM_STAGES, *tempty = tfull + 2;
+    uint64_t *full = bars, *empty = bars + STAGES;
+    uint64_t *tfull = bars + 2 * STAGES, *tempty = tfull + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t g = blockIdx.x % p.n_qgroups;       // query group
-    const uint32_t c = blockIdx.x / p.n_qgroups;       // row partition
+    // NG=1: blockIdx -> (query group g, row partition c); NG=2: every CTA is a row partition, groups 2*sg, 2*sg+1
+    const uint32_t n_super = NG == 1 ? p.n_qgroups : (p.n_qgroups + 1) / 2;
+    const uint32_t g0 = (blockIdx.x % n_super) * NG;   // first query group of this CTA
+    const uint32_t c = blockIdx.x / n_super;           // row partition
     const uint64_t n_tiles = (p.n_rows + GEMM_N - 1) / GEMM_N;
-    const uint64_t my_tiles = (n_tiles > c) ? (n_tiles - c + p.ctas_per_group - 1) / p.ctas_per_group : 0;
+    uint64_t my_tiles = (n_tiles > c) ? (n_tiles - c + p.ctas_per_group - 1) / p.ctas_per_group : 0;
+    if (p.tile_limit && my_tiles > p.tile_limit) my_tiles = p.tile_limit;
     const uint32_t nkb = p.n_kblocks;
+    // threads that release an accumulator slot: NG=1 all 8 epilogue warps, NG=2 the 4 warps of that group
+    constexpr uint32_t TEMPTY_COUNT = NG == 1 ? GEMM_EPI_WARPS * 32 : GEMM_EPI_WARPS * 16;
 
     if (threadIdx.x == 0) {
-        for (uint32_t s = 0; s < GEMM_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (uint32_t a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], GEMM_EPI_WARPS * 32); }
+        for (uint32_t s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (uint32_t a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], TEMPTY_COUNT); }
         fence_mbar_init();
         tma_prefetch_desc(&tm_q);
         tma_prefetch_desc(&tm_x);
     }
-    if (warp == 1) {   // TMEM: all 512 columns (2 accumulator stages x 256 fp32 columns)
+    if (warp == 1) {   // TMEM: all 512 columns (2 accumulators x 256 fp32 columns)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -165,11 +184,14 @@ emb_gemm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             for (uint64_t it = 0; it < my_tiles; it++) {
                 const uint64_t row0 = (c + it * p.ctas_per_group) * GEMM_N;
                 for (uint32_t kb = 0; kb < nkb; kb++, n++) {
-                    const uint32_t s = uint32_t(n % GEMM_STAGES), ph = uint32_t((n / GEMM_STAGES) & 1);
+                    const uint32_t s = uint32_t(n % STAGES), ph = uint32_t((n / STAGES) & 1);
                     mbar_wait(&empty[s], ph ^ 1);
-                    uint8_t *a_dst = ring + s * GEMM_STAGE_BYTES, *b_dst = a_dst + GEMM_A_BYTES;
-                    mbar_expect_tx(&full[s], GEMM_STAGE_BYTES);
-                    tma_load_2d(a_dst, &tm_q, &full[s], int32_t(kb * GEMM_KB), int32_t(g * GEMM_M), TMA_EVICT_LAST);
+                    uint8_t *a_dst = ring + s * STAGE_BYTES, *b_dst = a_dst + NG * GEMM_A_BYTES;
+                    mbar_expect_tx(&full[s], STAGE_BYTES);
+#pragma unroll
+                    for (int gi = 0; gi < NG; gi++)   // rows past the padded query matrix are zero-filled by TMA
+                        tma_load_2d(a_dst + gi * GEMM_A_BYTES, &tm_q, &full[s], int32_t(kb * GEMM_KB),
+                                    int32_t((g0 + gi) * GEMM_M), TMA_EVICT_LAST);
                     tma_load_2d(b_dst, &tm_x, &full[s], int32_t(kb * GEMM_KB), int32_t(row0), TMA_EVICT_FIRST);
                 }
             }
@@ -180,42 +202,55 @@ emb_gemm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             const uint32_t idesc = umma_idesc_tf32(GEMM_M, GEMM_N);
             uint64_t n = 0;
             for (uint64_t it = 0; it < my_tiles; it++) {
-                const uint32_t acc = uint32_t(it & 1), aph = uint32_t((it >> 1) & 1);
-                mbar_wait(&tempty[acc], aph ^ 1);          // epilogue drained this accumulator
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * GEMM_N;
+                // accumulator slot and barrier phase: NG=1 alternates slots per tile; NG=2 uses slot = group every tile
+                const uint32_t slot1 = uint32_t(it & 1), ph1 = uint32_t((it >> 1) & 1), ph2 = uint32_t(it & 1);
+                if (NG == 1) { mbar_wait(&tempty[slot1], ph1 ^ 1); tc_fence_after(); }
                 for (uint32_t kb = 0; kb < nkb; kb++, n++) {
-                    const uint32_t s = uint32_t(n % GEMM_STAGES), ph = uint32_t((n / GEMM_STAGES) & 1);
+                    const uint32_t s = uint32_t(n % STAGES), ph = uint32_t((n / STAGES) & 1);
                     mbar_wait(&full[s], ph);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(ring + s * GEMM_STAGE_BYTES);
-                    const uint64_t adesc = umma_desc_sw128(a_addr), bdesc = umma_desc_sw128(a_addr + GEMM_A_BYTES);
+                    const uint32_t a_addr = smem_u32(ring + s * STAGE_BYTES);
+                    const uint64_t bdesc = umma_desc_sw128(a_addr + NG * GEMM_A_BYTES);
 #pragma unroll
-                    for (uint32_t k = 0; k < 4; k++)      // UMMA_K = 8 tf32 = 32 B: advance start address by 32 B
-                        tc_mma_tf32(d_tmem, adesc + k * 2, bdesc + k * 2, idesc, (kb | k) != 0);
+                    for (int gi = 0; gi < NG; gi++) {
+                        if (NG == 2 && kb == 0) { mbar_wait(&tempty[gi], ph2 ^ 1); tc_fence_after(); }   // epilogue drained D_gi
+                        const uint32_t d_tmem = tmem_base + (NG == 1 ? slot1 : uint32_t(gi)) * GEMM_N;
+                        const uint64_t adesc = umma_desc_sw128(a_addr + gi * GEMM_A_BYTES);
+#pragma unroll
+                        for (uint32_t k = 0; k < 4; k++)      // UMMA_K = 8 tf32 = 32 B: advance start address by 32 B
+                            tc_mma_tf32(d_tmem, adesc + k * 2, bdesc + k * 2, idesc, (kb | k) != 0);
+                        if (NG == 2 && kb + 1 == nkb) tc_commit(&tfull[gi]);   // group gi's accumulator complete
+                    }
                     tc_commit(&empty[s]);                  // frees the smem stage when these MMAs retire
                 }
-                tc_commit(&tfull[acc]);                    // accumulator complete -> epilogue
+                if (NG == 1) tc_commit(&tfull[slot1]);     // accumulator complete -> epilogue
             }
         }
     } else {
-        // ===================== epilogue: thread = (TMEM lane = one query, one half of the tile's rows) ====
+        // ===================== epilogue: thread = TMEM lane = one query =====================
+        // NG=1: the two warps of a lane quadrant split the tile's 256 columns (rows) in halves;
+        // NG=2: they take one query group each and all 256 columns.
         const uint32_t ew = warp - 2;                      // 0..7
         const uint32_t quad = warp & 3;                    // TMEM lane quadrant this warp may access
-        const uint32_t half = ew >> 2;                     // columns [128*half, 128*half+128)
+        const uint32_t sel = ew >> 2;                      // NG=1: column half, NG=2: group within the CTA
         const uint32_t m = quad * 32 + lane;
-        const uint32_t q = g * GEMM_M + m;
+        const uint32_t grp = g0 + (NG == 2 ? sel : 0u);
+        const uint32_t q = grp * GEMM_M + m;
         const bool live = q < p.n_queries;
         const uint32_t et = ew * 32 + lane;                // 0..255 among epilogue threads
-        const uint32_t lists = p.ctas_per_group * 2;
-        uint64_t *__restrict__ mybuf = p.cand + (size_t(q) * lists + c * 2 + half) * p.cap;
+        const uint32_t lists = p.lists_per_query;
+        const uint32_t my_list = NG == 1 ? c * 2 + sel : c;
+        uint64_t *__restrict__ mybuf = p.cand + (size_t(q) * lists + my_list) * p.cap;
         uint64_t *wscr = scratch + ew * 128;
         uint32_t cnt = 0;
         float tau = live ? -INFINITY : INFINITY;
+        float best = -INFINITY;                            // max_mode: best tf32 score seen by this list
+        const uint32_t ncols = NG == 1 ? 128u : 256u, col0 = NG == 1 ? sel * 128u : 0u;
         for (uint64_t it = 0; it < my_tiles; it++) {
-            const uint32_t acc = uint32_t(it & 1), aph = uint32_t((it >> 1) & 1);
+            const uint32_t slot = NG == 1 ? uint32_t(it & 1) : sel;
+            const uint32_t ph = NG == 1 ? uint32_t((it >> 1) & 1) : uint32_t(it & 1);
             const uint64_t row0 = (c + it * p.ctas_per_group) * GEMM_N;
-            float *inr = inr_s + acc * GEMM_N;
+            float *inr = inr_s + uint32_t(it & 1) * GEMM_N;
             {
                 const uint64_t r = row0 + et;
                 inr[et] = r < p.n_rows ? __ldg(p.inv_norm + r) : __int_as_float(0x7fc00000);
@@ -225,12 +260,11 @@ emb_gemm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 if (tg) tau = fmaxf(tau, f32_unordered(tg));
             }
             named_bar_sync(1, GEMM_EPI_WARPS * 32);
-            mbar_wait(&tfull[acc], aph);
+            mbar_wait(&tfull[slot], ph);
             tc_fence_after();
-            const uint32_t col0 = half * 128;
-            const uint32_t taddr = tmem_base + ((quad * 32u) << 16) + acc * GEMM_N + col0;
+            const uint32_t taddr = tmem_base + ((quad * 32u) << 16) + slot * GEMM_N + col0;
             const float4 *inr4 = reinterpret_cast<const float4 *>(inr + col0);
-            for (uint32_t ch = 0; ch < 4; ch++) {
+            for (uint32_t ch = 0; ch < ncols / 32; ch++) {
                 uint32_t d[32];
                 tmem_ld32(taddr + ch * 32, d);
                 tmem_ld_wait();
@@ -244,6 +278,11 @@ emb_gemm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                     v[4 * j4 + 2] = __uint_as_float(d[4 * j4 + 2]) * w.z;
                     v[4 * j4 + 3] = __uint_as_float(d[4 * j4 + 3]) * w.w;
                 }
+                if (p.max_mode) {
+#pragma unroll
+                    for (uint32_t j = 0; j < 32; j++) best = fmaxf(best, v[j]);   // NaN (dead rows) ignored
+                    continue;
+                }
 #pragma unroll
                 for (uint32_t j = 0; j < 32; j++) mask |= (v[j] > tau ? 1u : 0u) << j;
                 if (mask) {   // rare once the threshold has warmed up
@@ -256,8 +295,8 @@ emb_gemm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 while (need) {
                     const uint32_t l = __ffs(need) - 1;
                     need &= need - 1;
-                    const uint32_t lq = g * GEMM_M + quad * 32 + l;
-                    uint64_t *lbuf = p.cand + (size_t(lq) * lists + c * 2 + half) * p.cap;
+                    const uint32_t lq = grp * GEMM_M + quad * 32 + l;
+                    uint64_t *lbuf = p.cand + (size_t(lq) * lists + my_list) * p.cap;
                     const uint32_t lcnt = __shfl_sync(0xffffffffu, cnt, l);
                     __syncwarp();
                     for (uint32_t i = lane; i < 128; i += 32) wscr[i] = i < lcnt ? lbuf[i] : KEY_NONE;
@@ -273,9 +312,10 @@ emb_gemm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 }
             }
             tc_fence_before();
-            mbar_arrive(&tempty[acc]);
+            mbar_arrive(&tempty[slot]);
         }
-        p.cand_cnt[size_t(q) * lists + c * 2 + half] = live ? cnt : 0;
+        if (p.max_mode) p.gmax[size_t(q) * lists + my_list] = live ? best : -INFINITY;
+        else if (grp < p.n_qgroups) p.cand_cnt[size_t(q) * lists + my_list] = live ? cnt : 0;
     }
     __syncthreads();
     if (warp == 1) {
@@ -388,41 +428,21 @@ __global__ void __launch_bounds__(256) emb_gemm_merge_kernel(const GemmMergePara
     if (tid == 0) { p.out_count[q] = s_cnt; p.out_unproven[q] = proven ? 0 : 1; }
 }
 
-// Seeds the per-query thresholds before the sweep: exact fp32 scores of the first `n_sample`
-// rows, split into `keep` groups; the minimum of the group maxima is a valid lower bound of
-// the sample's keep-th best score, hence of the global one (minus the tf32 error bound, since
-// the sweep compares tf32 scores).  Without it every CTA starts at -inf and floods its buffers.
-__global__ void __launch_bounds__(256) gemm_seed_tau_kernel(const float *rows, const float *inv_norm, uint32_t stride,
-                                                            uint32_t n_sample, const float *queries, const float *inv_qnorm,
-                                                            uint32_t keep, unsigned int *tau) {
-    __shared__ float gmax[64];
-    const uint32_t q = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t per = n_sample / keep;                 // rows per group
-    const float4 *qp = reinterpret_cast<const float4 *>(queries + size_t(q) * stride);
-    for (uint32_t gidx = warp; gidx < keep; gidx += 8) {
-        float mx = -INFINITY;
-        for (uint32_t r = gidx * per; r < (gidx + 1) * per; r++) {
-            const float4 *rp = reinterpret_cast<const float4 *>(rows + size_t(r) * stride);
-            float acc = 0.f;
-            for (uint32_t j = 0; j < stride / 128; j++) {
-                const float4 x = __ldg(rp + lane + 32 * j), y = __ldg(qp + lane + 32 * j);
-                acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc); acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
-            }
-            const float v = warp_sum(acc) * inv_norm[r];   // cos * |q| ; NaN rows are ignored by fmaxf
-            mx = fmaxf(mx, v);
-        }
-        if (lane == 0) gmax[gidx] = mx;
+// Threshold pass, step 2: every list of the threshold pass reported the best tf32 score of a
+// disjoint group of rows; the keep-th largest of those group maxima is attained by `keep`
+// distinct rows, hence a valid lower bound of the query's global keep-th best tf32 score —
+// in the same arithmetic the sweep compares with (no error margin needed).
+__global__ void __launch_bounds__(256) gemm_tau_from_max_kernel(const float *gmax, uint32_t lists, uint32_t keep,
+                                                                unsigned int *tau) {
+    __shared__ uint64_t keys[512];
+    const uint32_t q = blockIdx.x, tid = threadIdx.x;
+    const uint32_t n = min(lists, 512u), np2 = max(64u, next_pow2(n));
+    for (uint32_t i = tid; i < np2; i += blockDim.x) {
+        const float v = i < n ? gmax[size_t(q) * lists + i] : -INFINITY;
+        keys[i] = (v == v && v > -INFINITY) ? make_key(v, i) : KEY_NONE;
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float mn = INFINITY;
-        for (uint32_t i = 0; i < keep; i++) mn = fminf(mn, gmax[i]);
-        const float iqn = inv_qnorm[q];
-        if (iqn > 0.f && mn > -INFINITY && mn < INFINITY) {
-            const float seed = mn - GEMM_EPS_TF32 / iqn;   // tf32 score of those rows is >= exact - eps*|q|
-            tau[q] = f32_ordered(seed);
-        }
-    }
+    group_bitonic_desc(keys, np2, tid, blockDim.x, 0);
+    if (tid == 0 && n >= keep && keys[keep - 1] != KEY_NONE) tau[q] = f32_ordered(key_score(keys[keep - 1]));
 }
 
 // copies the exact-path results of re-run queries into their slots of the batch outputs
