@@ -400,33 +400,43 @@ __global__ void __launch_bounds__(BM25_THREADS) bm25_tile_kernel(const Bm25Param
     for (uint32_t base = 0; base < rows_here; base += BM25_CHUNK) {
         const uint32_t l0 = base + tid * 4;                   // 4 consecutive rows per thread: one LDS.128
         bool pushed = false;
-        if (l0 < rows_here) {
+        {
+            // branch-free bookkeeping: absent rows hold 0.0 (never touched; rows past n_rows too), so
+            // fmax/fmin with them are no-ops (folds start at 0.0) and only the rare candidate path branches
             const float4 s4 = *reinterpret_cast<const float4 *>(score + l0);
-            uint4 m4 = make_uint4(0u, 0u, 0u, 0u);
-            if (THRESH) m4 = *reinterpret_cast<const uint4 *>(mask + l0);
-            const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
-            const uint32_t mv[4] = {m4.x, m4.y, m4.z, m4.w};
+            float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+            if (THRESH) {
+                const uint4 m4 = *reinterpret_cast<const uint4 *>(mask + l0);
+                const uint32_t mv[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+                for (int u = 0; u < 4; u++)   // bm25.rs:416-428: keep popcount(mask) >= required
+                    sv[u] = (mv[u] != 0u && uint32_t(__popc(mv[u])) >= qd.required) ? sv[u] : 0.f;
+            }
+            uint32_t cand = 0;
+            float pv[4];
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                const uint32_t l = l0 + u;
                 const float s = sv[u];
-                bool present;
-                if (THRESH) present = mv[u] != 0u && uint32_t(__popc(mv[u])) >= qd.required;  // bm25.rs:416-428
-                else present = s != 0.f;
-                if (!present || l >= rows_here) continue;
-                matched++;
+                const bool present = THRESH ? (s != 0.f || false) : (s != 0.f);
+                matched += present ? 1u : 0u;
                 lmax = fmaxf(lmax, s);
                 lmin = fminf(lmin, s);
                 float proxy = __fsub_rn(s, mh);
-                if (OMC) proxy = __fmul_rn(proxy, aux[l]);
-                if (proxy >= tau_f) {                          // NaN fails; ties re-checked on the full key
-                    const unsigned long long key = make_key(proxy, row0 + l);
-                    if (key > tau) {
-                        const uint32_t slot = atomicAdd(&s_cnt, 1u);
-                        tbuf[slot] = key;   // slot < cap guaranteed by the compress rule below
-                        pushed = true;
+                if (OMC) proxy = __fmul_rn(proxy, aux[l0 + u]);
+                pv[u] = proxy;
+                cand |= (present && proxy >= tau_f) ? (1u << u) : 0u;   // NaN fails; ties re-checked on the key
+            }
+            if (cand) {
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if ((cand >> u) & 1u) {
+                        const unsigned long long key = make_key(pv[u], row0 + l0 + u);
+                        if (key > tau) {
+                            const uint32_t slot = atomicAdd(&s_cnt, 1u);
+                            tbuf[slot] = key;   // slot < cap guaranteed by the compress rule below
+                            pushed = true;
+                        }
                     }
-                }
             }
         }
         if (!__syncthreads_or(pushed)) continue;               // nothing pushed in this chunk: no overflow risk

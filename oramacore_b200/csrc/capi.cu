@@ -516,7 +516,7 @@ static int run_vector_stage(oc_ctx *c, oc_emb *e, const float *q_dev, uint32_t B
     c->timing.scan_bytes += e->n_rows * (uint64_t(e->stride) * 4 + 4);
     CU(cudaEventRecord(c->ev[EV_SCAN1], c->stream));
     GemmMergeParams mp{};
-    mp.cand = gp.cand; mp.cand_cnt = gp.cand_cnt; mp.ctas_per_group = lists; mp.cap = cap; mp.keep = keep; mp.limit = limit;
+    mp.cand = gp.cand; mp.cand_cnt = gp.cand_cnt; mp.tau = gp.tau; mp.ctas_per_group = lists; mp.cap = cap; mp.keep = keep; mp.limit = limit;
     mp.rows = e->rows; mp.stride = e->stride; mp.inv_norm = inv_norm; mp.queries = c->q_pad.as<float>();
     mp.inv_qnorm = c->q_inv.as<float>(); mp.row_doc_ids = e->row_doc; mp.rescale_e5 = e->e5; mp.similarity = similarity;
     mp.out_doc = out.doc; mp.out_score = out.score; mp.out_row = out.row; mp.out_count = out.cnt; mp.out_raw = out.raw;

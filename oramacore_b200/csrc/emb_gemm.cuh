@@ -329,6 +329,7 @@ emb_gemm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 // ---------------------------------------------------------------------------------------
 struct GemmMergeParams {
     const uint64_t *cand; const uint32_t *cand_cnt;
+    const unsigned int *tau;     // final per-query thresholds (ordered uint, 0 = never set)
     uint32_t ctas_per_group, cap, keep, limit;
     const float *rows; uint32_t stride; const float *inv_norm;
     const float *queries;        // [B][stride] padded
@@ -376,7 +377,12 @@ __global__ void __launch_bounds__(256) emb_gemm_merge_kernel(const GemmMergePara
         });
     }
     const float iqn = p.inv_qnorm[q];
-    const float a_keep = got == p.keep ? key_score(buf[p.keep - 1]) * iqn : -INFINITY;   // approx cosine of the K'-th
+    // bound on the tf32 score (cos*|q| units) of every row OUTSIDE the selected candidates:
+    // rows never pushed were <= the query's threshold at that time <= its final value; rows
+    // dropped by a compress or by the top-K' selection above are <= the K'-th selected score.
+    const unsigned int tq = p.tau[q];
+    float bound_v = tq ? f32_unordered(tq) : -INFINITY;
+    if (got == p.keep) bound_v = fmaxf(bound_v, key_score(buf[p.keep - 1]));
     // exact fp32 re-score, one warp per candidate, K1's lane layout and FMA order
     for (uint32_t i = tid; i < 64; i += blockDim.x) exact[i] = KEY_NONE;
     if (tid == 0) s_cnt = 0;
@@ -399,11 +405,12 @@ __global__ void __launch_bounds__(256) emb_gemm_merge_kernel(const GemmMergePara
     if (warp == 0) warp_bitonic_desc(exact, 64, lane);
     __syncthreads();
     const uint32_t n_top = min(got, p.limit);
-    // proof: limit-th exact cosine >= a_K' + eps  (or every live row is already a candidate)
-    bool proven = got < p.keep;
+    // proof: every outside row has exact cos <= bound_v*iqn + eps; the answer is exact when the
+    // limit-th exact cosine clears that (or when nothing was ever excluded)
+    bool proven = bound_v == -INFINITY;
     if (!proven && n_top == p.limit) {
         const float c_lim = 1.0f + key_score(exact[p.limit - 1]);   // cos = 1 - distance
-        proven = c_lim >= a_keep + GEMM_EPS_TF32;
+        proven = c_lim >= bound_v * iqn + GEMM_EPS_TF32;
     }
     for (uint32_t i = tid; i < p.limit; i += blockDim.x) {
         uint64_t doc = 0; float score = 0.f, raw = 0.f; uint32_t row = 0xffffffffu;
