@@ -113,6 +113,7 @@ struct Bm25Params {
     const TermDesc *terms;
     const TokenDesc *tokens;
     const QueryDesc *queries;
+    const uint32_t *term_token;   // [n_term_desc] token index of each expanded term
     const uint32_t *seg;          // [n_term_desc][n_tiles+1]
     uint32_t n_queries, n_tiles;
     uint64_t n_rows;
@@ -260,102 +261,116 @@ __global__ void __launch_bounds__(BM25_THREADS) bm25_tile_kernel(const Bm25Param
     __syncthreads();
 
     // ------------------------------------------------ accumulate, token by token, term by term.
-    // Software pipelined: the next term's sub-range bounds and its first batch of postings are
-    // requested before the barrier that closes the current term, so their latency hides behind it.
+    // Warp 0 builds a per-CTA table of the query's term sub-ranges for this tile (up to
+    // TERM_PASS terms per pass); every thread then walks the table with broadcast LDS.  Terms
+    // with no posting in the tile cost nothing (no barrier); the first batch of the next
+    // non-empty term is requested before the barrier that closes the current one.
     {
-        uint32_t t = qd.token_begin, e = 0;
-        TokenDesc tk{};
-        bool have = false;
-        for (; t < qd.token_end; t++) {
-            tk = p.tokens[t];
-            if (tk.term_begin < tk.term_end) { e = tk.term_begin; have = true; break; }
-        }
-        TermDesc td{};
-        uint32_t lo = 0, hi = 0;
-        uint2 rec[4];
-        auto fetch = [&](const TermDesc &d, uint32_t base, uint32_t end, uint2 (&r)[4]) {
-            const uint2 *pp = reinterpret_cast<const uint2 *>(d.ptr);
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const uint32_t pi = base + tid + u * BM25_THREADS;
-                r[u] = pi < end ? __ldg(pp + pi) : make_uint2(0xffffffffu, 0u);
+        constexpr uint32_t TERM_PASS = 96;
+        __shared__ const uint2 *t_ptr[TERM_PASS];
+        __shared__ uint32_t t_n[TERM_PASS], t_bit[TERM_PASS], t_flag[TERM_PASS];   // flag bit0: single, bit1: last term of its token
+        __shared__ float t_w[TERM_PASS], t_idf[TERM_PASS];
+        __shared__ uint32_t t_tok_begin[TERM_PASS];                                 // first term (table index space: global e) of the token
+        const uint32_t e_begin = qd.token_begin < qd.token_end ? p.tokens[qd.token_begin].term_begin : 0;
+        const uint32_t e_end = qd.token_begin < qd.token_end ? p.tokens[qd.token_end - 1].term_end : 0;
+        for (uint32_t pass0 = e_begin; pass0 < e_end; pass0 += TERM_PASS) {
+            const uint32_t nt = min(TERM_PASS, e_end - pass0);
+            __syncthreads();   // previous pass fully consumed
+            for (uint32_t j = tid; j < nt; j += BM25_THREADS) {
+                const uint32_t e = pass0 + j;
+                const TermDesc td = p.terms[e];
+                const TokenDesc tk = p.tokens[p.term_token[e]];
+                const uint32_t *sg = p.seg + size_t(e) * (p.n_tiles + 1);
+                const uint32_t lo = sg[tile], hi = sg[tile + 1];
+                t_ptr[j] = reinterpret_cast<const uint2 *>(td.ptr) + lo;
+                t_n[j] = hi - lo;
+                t_w[j] = td.weight; t_idf[j] = tk.idf; t_bit[j] = tk.bit;
+                const bool single = !MULTI || (tk.term_end - tk.term_begin == 1);
+                t_flag[j] = (single ? 1u : 0u) | ((e + 1 == tk.term_end) ? 2u : 0u);
+                t_tok_begin[j] = tk.term_begin;
             }
-        };
-        if (have) {
-            td = p.terms[e];
-            const uint32_t *sg = p.seg + size_t(e) * (p.n_tiles + 1);
-            lo = sg[tile]; hi = sg[tile + 1];
-            fetch(td, lo, hi, rec);
-        }
-        while (have) {
-            // successor term (block-uniform control flow)
-            uint32_t nt = t, ne = e + 1;
-            TokenDesc ntk = tk;
-            bool nhave = true;
-            if (ne >= tk.term_end) {
-                nhave = false;
-                for (nt = t + 1; nt < qd.token_end; nt++) {
-                    ntk = p.tokens[nt];
-                    if (ntk.term_begin < ntk.term_end) { ne = ntk.term_begin; nhave = true; break; }
-                }
-            }
-            TermDesc nd{};
-            uint32_t nlo = 0, nhi = 0;
-            if (nhave) {
-                nd = p.terms[ne];
-                const uint32_t *nsg = p.seg + size_t(ne) * (p.n_tiles + 1);
-                nlo = nsg[tile]; nhi = nsg[tile + 1];
-            }
-            const bool single = !MULTI || (tk.term_end - tk.term_begin == 1);
-            for (uint32_t base = lo; base < hi; base += BM25_THREADS * 4) {
-                if (base != lo) fetch(td, base, hi, rec);
+            __syncthreads();
+            uint2 rec[4];
+            auto fetch = [&](uint32_t j, uint32_t base, uint2 (&r)[4]) {
+                const uint2 *pp = t_ptr[j];
+                const uint32_t n = t_n[j];
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
-                    if (rec[u].x == 0xffffffffu) continue;
-                    const uint32_t l = rec[u].x - row0;
-                    if (use_ok && !((okb[l >> 5] >> (l & 31)) & 1u)) continue;
-                    const float ntf = __fmul_rn(td.weight, __uint_as_float(rec[u].y));   // w * tf'
-                    if (single) {
-                        // S = 0.0 + 1.0*ntf; skip unless is_normal (bm25.rs:387,501)
-                        if (f32_is_normal(ntf)) {
-                            const float c = bm25_sat(ntf, p.k, kp1, tk.idf);
-                            if (c == c) {
-                                score[l] = __fadd_rn(score[l], c);
-                                if (THRESH) mask[l] |= tk.bit;
-                            }
-                        }
-                    } else {
-                        aux[l] = __fadd_rn(aux[l], ntf);  // S += weight(1.0) * ntf, push order
-                    }
+                    const uint32_t pi = base + tid + u * BM25_THREADS;
+                    r[u] = pi < n ? __ldg(pp + pi) : make_uint2(0xffffffffu, 0u);
                 }
-            }
-            uint2 nrec[4];
-            if (nhave) fetch(nd, nlo, nhi, nrec);
-            __syncthreads();  // next term / token may touch the same rows
-            if (MULTI && !single && e + 1 == tk.term_end) {
-                // finalize_term: drain S over the rows this token touched (second walk, L2-hot)
-                for (uint32_t fe = tk.term_begin; fe < tk.term_end; fe++) {
-                    const TermDesc fd = p.terms[fe];
-                    const uint32_t *sg = p.seg + size_t(fe) * (p.n_tiles + 1);
-                    const uint32_t flo = sg[tile], fhi = sg[tile + 1];
-                    for (uint32_t pi = flo + tid; pi < fhi; pi += BM25_THREADS) {
-                        const uint32_t l = fd.ptr[pi].row - row0;
-                        const float S = __uint_as_float(atomicExch(reinterpret_cast<unsigned int *>(&aux[l]), 0u));
-                        if (f32_is_normal(S)) {
-                            const float c = bm25_sat(S, p.k, kp1, tk.idf);
-                            if (c == c) {
-                                score[l] = __fadd_rn(score[l], c);
-                                if (THRESH) mask[l] |= tk.bit;
-                            }
-                        }
-                    }
-                    __syncthreads();
-                }
-            }
-            t = nt; e = ne; tk = ntk; td = nd; lo = nlo; hi = nhi; have = nhave;
+            };
+            // first non-empty term of the pass (multi-term tokens keep their empty terms: finalize needs the walk)
+            auto next_nonempty = [&](uint32_t j) { while (j < nt && t_n[j] == 0 && (t_flag[j] & 1u)) j++; return j; };
+            uint32_t j = next_nonempty(0);
+            if (j < nt && (tid & ~31u) < t_n[j]) fetch(j, 0, rec);
+            while (j < nt) {
+                const uint32_t n = t_n[j], flag = t_flag[j];
+                const bool single = flag & 1u;
+                const float w = t_w[j], idf = t_idf[j];
+                const uint32_t bit = t_bit[j];
+                for (uint32_t base = 0; base < n; base += BM25_THREADS * 4) {
+                    if (base + (tid & ~31u) >= n) break;             // this warp has no posting in the batch
+                    if (base != 0) fetch(j, base, rec);
 #pragma unroll
-            for (int u = 0; u < 4; u++) rec[u] = nrec[u];
+                    for (int u = 0; u < 4; u++) {
+                        if (rec[u].x == 0xffffffffu) continue;
+                        const uint32_t l = rec[u].x - row0;
+                        if (use_ok && !((okb[l >> 5] >> (l & 31)) & 1u)) continue;
+                        const float ntf = __fmul_rn(w, __uint_as_float(rec[u].y));   // w * tf'
+                        if (single) {
+                            // S = 0.0 + 1.0*ntf; skip unless is_normal (bm25.rs:387,501)
+                            if (f32_is_normal(ntf)) {
+                                const float c = bm25_sat(ntf, p.k, kp1, idf);
+                                if (c == c) {
+                                    score[l] = __fadd_rn(score[l], c);
+                                    if (THRESH) mask[l] |= bit;
+                                }
+                            }
+                        } else {
+                            aux[l] = __fadd_rn(aux[l], ntf);  // S += weight(1.0) * ntf, push order
+                        }
+                    }
+                }
+                const uint32_t jn = next_nonempty(j + 1);
+                uint2 nrec[4];
+                const bool pre = jn < nt && (tid & ~31u) < t_n[jn];
+                if (pre) fetch(jn, 0, nrec);
+                __syncthreads();  // next term / token may touch the same rows
+                if (MULTI && !single && (flag & 2u)) {
+                    // finalize_term: drain S over the rows this token touched (second walk, L2-hot)
+                    const uint32_t tb = t_tok_begin[j];
+                    for (uint32_t fe = tb; fe <= pass0 + j; fe++) {
+                        // terms of this token that fell into an earlier pass are re-read from the descriptors
+                        const uint2 *fp; uint32_t fn;
+                        if (fe >= pass0) { fp = t_ptr[fe - pass0]; fn = t_n[fe - pass0]; }
+                        else {
+                            const TermDesc fd = p.terms[fe];
+                            const uint32_t *sg = p.seg + size_t(fe) * (p.n_tiles + 1);
+                            fp = reinterpret_cast<const uint2 *>(fd.ptr) + sg[tile]; fn = sg[tile + 1] - sg[tile];
+                        }
+                        for (uint32_t pi = tid; pi < fn; pi += BM25_THREADS) {
+                            const uint32_t l = fp[pi].x - row0;
+                            const float S = __uint_as_float(atomicExch(reinterpret_cast<unsigned int *>(&aux[l]), 0u));
+                            if (f32_is_normal(S)) {
+                                const float c = bm25_sat(S, p.k, kp1, idf);
+                                if (c == c) {
+                                    score[l] = __fadd_rn(score[l], c);
+                                    if (THRESH) mask[l] |= bit;
+                                }
+                            }
+                        }
+                        __syncthreads();
+                    }
+                }
+                j = jn;
+                if (pre) {
+#pragma unroll
+                    for (int u = 0; u < 4; u++) rec[u] = nrec[u];
+                }
+            }
         }
+        __syncthreads();
     }
 
     // ------------------------------------------------ OMC multipliers for this tile

@@ -828,6 +828,7 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
     const bool tombs = has_ft && str->n_deleted > 0;
     const uint32_t n_tiles = has_ft ? (uint32_t)((str->n_rows + BM25_TILE - 1) / BM25_TILE) : 0;
     std::vector<TermDesc> terms;
+    std::vector<uint32_t> term_token;
     std::vector<TokenDesc> tokens;
     std::vector<QueryDesc> queries;
     std::vector<uint8_t> tok_need_df;
@@ -869,6 +870,7 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
                     df_known = f.global_df.empty() ? td.len : f.global_df[ti];
                     postings_walked += td.len;
                     terms.push_back(td);
+                    term_token.push_back((uint32_t)tokens.size());
                 }
                 tk.term_end = (uint32_t)terms.size();
                 const uint32_t nt = tk.term_end - tk.term_begin;
@@ -911,6 +913,7 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
     const size_t o_flt = filter ? pk.add(p->filter_bits, fwords * 8) : 0;
     const size_t o_terms = has_ft ? pk.add(terms.data(), terms.size() * sizeof(TermDesc)) : 0;
     const size_t o_tokens = has_ft ? pk.add(tokens.data(), tokens.size() * sizeof(TokenDesc)) : 0;
+    const size_t o_ttok = has_ft ? pk.add(term_token.data(), term_token.size() * 4) : 0;
     const size_t o_queries = has_ft ? pk.add(queries.data(), queries.size() * sizeof(QueryDesc)) : 0;
     const size_t o_omcd = n_omc ? pk.add(p->omc_doc_ids, size_t(n_omc) * 8) : 0;
     const size_t o_omcm = n_omc ? pk.add(p->omc_mult, size_t(n_omc) * 4) : 0;
@@ -1024,6 +1027,7 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
         bp.terms = reinterpret_cast<const TermDesc *>(din + o_terms);
         bp.tokens = reinterpret_cast<const TokenDesc *>(din + o_tokens);
         bp.queries = reinterpret_cast<const QueryDesc *>(din + o_queries);
+        bp.term_token = reinterpret_cast<const uint32_t *>(din + o_ttok);
         bp.seg = c->seg.as<uint32_t>();
         bp.n_queries = B; bp.n_tiles = n_tiles; bp.n_rows = str->n_rows;
         bp.k = p->bm25_k; bp.b = p->bm25_b;
