@@ -28,8 +28,8 @@
 
 namespace oc {
 
-constexpr uint32_t BM25_TILE = 16384;          // rows per tile
-constexpr uint32_t BM25_THREADS = 512;
+constexpr uint32_t BM25_TILE = 8192;           // rows per tile (32 KB of fp32 accumulators: 4 CTAs per SM)
+constexpr uint32_t BM25_THREADS = 256;
 constexpr uint32_t BM25_CHUNK = BM25_THREADS * 4;
 
 struct PostingRaw {    // 8 bytes, as handed over by the host (string_field.rs:162: field_length is u16)
@@ -309,6 +309,11 @@ __global__ void __launch_bounds__(BM25_THREADS) bm25_tile_kernel(const Bm25Param
                 const bool single = flag & 1u;
                 const float w = t_w[j], idf = t_idf[j];
                 const uint32_t bit = t_bit[j];
+                // request the next non-empty term's first batch now: its latency hides behind this term's work
+                const uint32_t jn = next_nonempty(j + 1);
+                uint2 nrec[4];
+                const bool pre = jn < nt && (tid & ~31u) < t_n[jn];
+                if (pre) fetch(jn, 0, nrec);
                 for (uint32_t base = 0; base < n; base += BM25_THREADS * 4) {
                     if (base + (tid & ~31u) >= n) break;             // this warp has no posting in the batch
                     if (base != 0) fetch(j, base, rec);
@@ -332,10 +337,6 @@ __global__ void __launch_bounds__(BM25_THREADS) bm25_tile_kernel(const Bm25Param
                         }
                     }
                 }
-                const uint32_t jn = next_nonempty(j + 1);
-                uint2 nrec[4];
-                const bool pre = jn < nt && (tid & ~31u) < t_n[jn];
-                if (pre) fetch(jn, 0, nrec);
                 __syncthreads();  // next term / token may touch the same rows
                 if (MULTI && !single && (flag & 2u)) {
                     // finalize_term: drain S over the rows this token touched (second walk, L2-hot)
@@ -410,62 +411,80 @@ __global__ void __launch_bounds__(BM25_THREADS) bm25_tile_kernel(const Bm25Param
     uint32_t matched = 0;
     float lmax = 0.f, lmin = 0.f;
     const uint64_t rows_here = min(uint64_t(BM25_TILE), p.n_rows - row0);
-    const float tau_f0 = tau ? key_score(tau) : -INFINITY;   // cheap float pre-filter for the rank key compare
-    float tau_f = tau_f0;
-    for (uint32_t base = 0; base < rows_here; base += BM25_CHUNK) {
-        const uint32_t l0 = base + tid * 4;                   // 4 consecutive rows per thread: one LDS.128
-        bool pushed = false;
-        {
-            // branch-free bookkeeping: absent rows hold 0.0 (never touched; rows past n_rows too), so
-            // fmax/fmin with them are no-ops (folds start at 0.0) and only the rare candidate path branches
-            const float4 s4 = *reinterpret_cast<const float4 *>(score + l0);
-            float sv[4] = {s4.x, s4.y, s4.z, s4.w};
-            if (THRESH) {
-                const uint4 m4 = *reinterpret_cast<const uint4 *>(mask + l0);
-                const uint32_t mv[4] = {m4.x, m4.y, m4.z, m4.w};
+    float tau_f = tau ? key_score(tau) : -INFINITY;   // cheap float pre-filter for the rank key compare
+    __shared__ uint32_t s_ovf;
+    // One pass over the tile.  chunked=false: no barriers, pushes are overflow-checked (the common
+    // case once the query's threshold has warmed up: a handful of pushes per tile).  If the buffer
+    // overflowed (cold threshold: the first tiles of a query) the pass is redone chunk by chunk with
+    // a barrier + compress between chunks.
+    auto scan_pass = [&](const bool chunked) {
+        matched = 0; lmax = 0.f; lmin = 0.f;
+        for (uint32_t base = 0; base < rows_here; base += BM25_CHUNK) {
+            const uint32_t l0 = base + tid * 4;                   // 4 consecutive rows per thread: one LDS.128
+            bool pushed = false;
+            {
+                // branch-free bookkeeping: absent rows hold 0.0 (never touched; rows past n_rows too), so
+                // fmax/fmin with them are no-ops (folds start at 0.0) and only the rare candidate path branches
+                const float4 s4 = *reinterpret_cast<const float4 *>(score + l0);
+                float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+                if (THRESH) {
+                    const uint4 m4 = *reinterpret_cast<const uint4 *>(mask + l0);
+                    const uint32_t mv[4] = {m4.x, m4.y, m4.z, m4.w};
 #pragma unroll
-                for (int u = 0; u < 4; u++)   // bm25.rs:416-428: keep popcount(mask) >= required
-                    sv[u] = (mv[u] != 0u && uint32_t(__popc(mv[u])) >= qd.required) ? sv[u] : 0.f;
-            }
-            uint32_t cand = 0;
-            float pv[4];
+                    for (int u = 0; u < 4; u++)   // bm25.rs:416-428: keep popcount(mask) >= required
+                        sv[u] = (mv[u] != 0u && uint32_t(__popc(mv[u])) >= qd.required) ? sv[u] : 0.f;
+                }
+                uint32_t cand = 0;
+                float pv[4];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const float s = sv[u];
-                const bool present = THRESH ? (s != 0.f || false) : (s != 0.f);
-                matched += present ? 1u : 0u;
-                lmax = fmaxf(lmax, s);
-                lmin = fminf(lmin, s);
-                float proxy = __fsub_rn(s, mh);
-                if (OMC) proxy = __fmul_rn(proxy, aux[l0 + u]);
-                pv[u] = proxy;
-                cand |= (present && proxy >= tau_f) ? (1u << u) : 0u;   // NaN fails; ties re-checked on the key
-            }
-            if (cand) {
+                for (int u = 0; u < 4; u++) {
+                    const float s = sv[u];
+                    const bool present = s != 0.f;
+                    matched += present ? 1u : 0u;
+                    lmax = fmaxf(lmax, s);
+                    lmin = fminf(lmin, s);
+                    float proxy = __fsub_rn(s, mh);
+                    if (OMC) proxy = __fmul_rn(proxy, aux[l0 + u]);
+                    pv[u] = proxy;
+                    cand |= (present && proxy >= tau_f) ? (1u << u) : 0u;   // NaN fails; ties re-checked on the key
+                }
+                if (cand) {
 #pragma unroll
-                for (int u = 0; u < 4; u++)
-                    if ((cand >> u) & 1u) {
-                        const unsigned long long key = make_key(pv[u], row0 + l0 + u);
-                        if (key > tau) {
-                            const uint32_t slot = atomicAdd(&s_cnt, 1u);
-                            tbuf[slot] = key;   // slot < cap guaranteed by the compress rule below
-                            pushed = true;
+                    for (int u = 0; u < 4; u++)
+                        if ((cand >> u) & 1u) {
+                            const unsigned long long key = make_key(pv[u], row0 + l0 + u);
+                            if (key > tau) {
+                                const uint32_t slot = atomicAdd(&s_cnt, 1u);
+                                if (slot < p.cap) tbuf[slot] = key;   // chunked: guaranteed by the compress rule
+                                else s_ovf = 1u;
+                                pushed = true;
+                            }
                         }
-                    }
+                }
+            }
+            if (!chunked) continue;
+            if (!__syncthreads_or(pushed)) continue;               // nothing pushed in this chunk: no overflow risk
+            const uint32_t c = s_cnt;   // snapshot, then barrier, so the branch is block-uniform
+            __syncthreads();
+            if (c + BM25_CHUNK > p.cap && base + BM25_CHUNK < rows_here) {
+                // compress: keep the best n_keep (ft travels by re-lookup: key -> row -> score[])
+                block_keep_top(tbuf, c, p.cap, p.n_keep, tid);
+                const uint32_t kept = min(c, p.n_keep);
+                if (tid == 0) s_cnt = kept;
+                if (kept == p.n_keep) { tau = max(tau, (unsigned long long)tbuf[p.n_keep - 1]); tau_f = key_score(tau); }
+                __syncthreads();
             }
         }
-        if (!__syncthreads_or(pushed)) continue;               // nothing pushed in this chunk: no overflow risk
-        const uint32_t c = s_cnt;   // snapshot, then barrier, so the branch is block-uniform
+    };
+    if (tid == 0) s_ovf = 0u;
+    __syncthreads();
+    scan_pass(false);
+    __syncthreads();
+    if (s_ovf) {
         __syncthreads();
-        if (c + BM25_CHUNK > p.cap && base + BM25_CHUNK < rows_here) {
-            // compress: keep the best n_keep
-            // ft travels by re-lookup (score[] still holds it): key -> row -> score
-            block_keep_top(tbuf, c, p.cap, p.n_keep, tid);
-            const uint32_t kept = min(c, p.n_keep);
-            if (tid == 0) s_cnt = kept;
-            if (kept == p.n_keep) { tau = max(tau, (unsigned long long)tbuf[p.n_keep - 1]); tau_f = key_score(tau); }
-            __syncthreads();
-        }
+        if (tid == 0) { s_cnt = 0u; s_ovf = 0u; }
+        __syncthreads();
+        scan_pass(true);
     }
     __syncthreads();
     // ---- block reductions of count / extrema
