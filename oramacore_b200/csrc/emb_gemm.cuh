@@ -354,9 +354,11 @@ __global__ void __launch_bounds__(256) emb_gemm_merge_kernel(const GemmMergePara
     __shared__ uint32_t s_off[512];
     __shared__ uint32_t s_valid;
     uint32_t got;
-    if (tid == 0) {
+    for (uint32_t l = tid; l < p.ctas_per_group && l < 512; l += blockDim.x) s_off[l] = min(cnts[l], p.cap);   // parallel loads
+    __syncthreads();
+    if (tid == 0) {   // exclusive scan in shared memory (<= 512 entries)
         uint32_t acc = 0;
-        for (uint32_t l = 0; l < p.ctas_per_group && l < 512; l++) { s_off[l] = acc; acc += min(cnts[l], p.cap); }
+        for (uint32_t l = 0; l < p.ctas_per_group && l < 512; l++) { const uint32_t c = s_off[l]; s_off[l] = acc; acc += c; }
         s_valid = p.ctas_per_group <= 512 ? acc : 0xffffffffu;
     }
     __syncthreads();

@@ -159,7 +159,45 @@ __global__ void __launch_bounds__(256) fuse_topk_kernel(const FuseParams p) {
         }
         return f == f ? make_key(f, idx) : KEY_NONE;
     };
-    const uint32_t got = block_topn_stream(buf, p.capb, p.n_keep, total, load);
+    // Most tiles emit no candidate once the query's threshold has warmed up: compact the valid
+    // slots first (per-thread counts + block exclusive scan) and sort only those; fall back to
+    // the streaming top-n when they do not fit the key buffer.
+    __shared__ uint32_t s_scan[256];
+    __shared__ uint32_t s_total_valid;
+    uint32_t got;
+    {
+        uint32_t mine = 0;
+        if (has_ft)
+            for (uint32_t t = tid; t < p.n_tiles; t += blockDim.x) mine += min(p.cand_cnt[size_t(q) * p.n_tiles + t], p.n_keep);
+        s_scan[tid] = mine;
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t acc = 0;
+            for (uint32_t i = 0; i < blockDim.x; i++) { const uint32_t c = s_scan[i]; s_scan[i] = acc; acc += c; }
+            s_total_valid = acc;
+        }
+        __syncthreads();
+        const uint32_t n_valid_ft = s_total_valid, n_all = n_valid_ft + vc;
+        if (n_all <= p.capb) {
+            uint32_t pos = s_scan[tid];
+            if (has_ft)
+                for (uint32_t t = tid; t < p.n_tiles; t += blockDim.x) {
+                    const uint32_t c = min(p.cand_cnt[size_t(q) * p.n_tiles + t], p.n_keep);
+                    for (uint32_t k = 0; k < c; k++) buf[pos++] = load(uint64_t(t) * p.n_keep + k);
+                }
+            for (uint32_t j = tid; j < vc; j += blockDim.x) buf[n_valid_ft + j] = load(n_ft_slots + j);
+            const uint32_t np2 = max(32u, next_pow2(n_all));
+            for (uint32_t i = n_all + tid; i < np2; i += blockDim.x) buf[i] = KEY_NONE;
+            group_bitonic_desc(buf, np2, tid, blockDim.x, 0);
+            uint32_t real = min(n_all, p.n_keep);
+            __shared__ uint32_t s_real2;
+            if (tid == 0) { while (real > 0 && buf[real - 1] == KEY_NONE) real--; s_real2 = real; }
+            __syncthreads();
+            got = s_real2;
+        } else {
+            got = block_topn_stream(buf, p.capb, p.n_keep, total, load);
+        }
+    }
 
     // ---- skip(offset).take(limit)
     const uint32_t n_out = got > p.offset ? min(p.limit, got - p.offset) : 0;
