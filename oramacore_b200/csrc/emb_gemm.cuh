@@ -340,7 +340,7 @@ struct GemmMergeParams {
     uint8_t *out_unproven;       // [B] 1 => host must re-run this query through the exact sweep
 };
 
-__global__ void __launch_bounds__(256) emb_gemm_merge_kernel(const GemmMergeParams p) {
+__global__ void __launch_bounds__(1024) emb_gemm_merge_kernel(const GemmMergeParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint64_t *buf = reinterpret_cast<uint64_t *>(smem);          // [2048]
     uint64_t *exact = buf + 2048;                                 // [64]
@@ -390,14 +390,21 @@ __global__ void __launch_bounds__(256) emb_gemm_merge_kernel(const GemmMergePara
     if (tid == 0) s_cnt = 0;
     __syncthreads();
     const float4 *qp = reinterpret_cast<const float4 *>(p.queries + size_t(q) * p.stride);
-    for (uint32_t i = warp; i < got; i += 8) {
+    for (uint32_t i = warp; i < got; i += blockDim.x / 32) {   // one warp per candidate (32 warps)
         const uint32_t row = key_idx(buf[i]);
         const float4 *rp = reinterpret_cast<const float4 *>(p.rows + size_t(row) * p.stride);
+        // all row loads are issued before the first use (the rows were streamed evict-first: DRAM latency)
+        float4 xr[8];
+        const uint32_t nch = p.stride / 128;   // <= 8
+#pragma unroll
+        for (uint32_t j = 0; j < 8; j++) if (j < nch) xr[j] = __ldg(rp + lane + 32 * j);
         float acc = 0.f;
-        for (uint32_t j = 0; j < p.stride / 128; j++) {
-            const float4 x = rp[lane + 32 * j], y = qp[lane + 32 * j];
-            acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc); acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
-        }
+#pragma unroll
+        for (uint32_t j = 0; j < 8; j++)
+            if (j < nch) {
+                const float4 x = xr[j], y = qp[lane + 32 * j];
+                acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc); acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
+            }
         const float dot = warp_sum(acc);
         const float cosv = dot * p.inv_norm[row] * iqn;
         const float kf = -(1.0f - cosv);

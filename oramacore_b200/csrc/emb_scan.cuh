@@ -207,8 +207,9 @@ __global__ void emb_prep_queries_kernel(const float *q_in, uint32_t dim, uint32_
     const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x & 31;
     if (q >= nq) return;
     float s = 0.f;
+#pragma unroll 8
     for (uint32_t j = lane; j < stride; j += 32) {
-        const float v = j < dim ? q_in[size_t(q) * dim + j] : 0.f;
+        const float v = j < dim ? __ldg(q_in + size_t(q) * dim + j) : 0.f;
         q_out[size_t(q) * stride + j] = v;
         s = fmaf(v, v, s);
     }

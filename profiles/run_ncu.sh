@@ -1,19 +1,19 @@
 #!/bin/bash
 # Profiling recipe (B200_PROFILING.md), run on the GPU box under gpurun, 1 GPU.
-# Outputs land in gpurun_out/; summaries are copied to profiles/ by hand and committed.
+# Outputs land in gpurun_out/; summaries are copied to profiles/ (profiles/summarize.py) and committed.
 set -x
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 # (1) launch lists: every kernel with its device time (cold-cache, serialised: compare SHARES)
+ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_h1.csv \
+    python bench.py --workload h1 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_h1_stdout.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_v1.csv \
     python bench.py --workload v1 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_v1_stdout.log 2>&1
-ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_h1.csv \
-    python bench.py --workload h1 --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_h1_stdout.log 2>&1
-# (2) full captures of the top kernels
-ncu --set full --clock-control none --import-source on -k regex:emb_scan_kernel -s 3 -c 2 -f -o gpurun_out/prof_scan_v1 \
-    python bench.py --workload v1 --steps 2 --warmup 1 --no-cpu-baseline > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:bm25_tile_kernel -s 1 -c 1 -f -o gpurun_out/prof_bm25_h1 \
-    python bench.py --workload h1 --steps 2 --warmup 1 --no-cpu-baseline > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:emb_scan_kernel -s 70 -c 1 -f -o gpurun_out/prof_scan_h1 \
-    python bench.py --workload h1 --steps 2 --warmup 1 --no-cpu-baseline > /dev/null 2>&1
+# (2) full captures of the top kernels (same command as the bench)
+ncu --set full --clock-control none --import-source on -k regex:emb_gemm_kernel -s 5 -c 1 -f -o gpurun_out/prof_gemm_h1 \
+    python bench.py --workload h1 --steps 3 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:bm25_tile_kernel -s 2 -c 1 -f -o gpurun_out/prof_bm25_h1 \
+    python bench.py --workload h1 --steps 3 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:emb_scan_kernel -s 3 -c 1 -f -o gpurun_out/prof_scan_v1 \
+    python bench.py --workload v1 --steps 3 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
 ls -la gpurun_out/

@@ -21,6 +21,8 @@ def _both_paths(ctx, emb, qv, limit, sim, fb=None, nb=0):
 
 
 @pytest.mark.parametrize("n,dim,model,B", [(20000, 768, "BGEBase", 32), (70001, 384, "BGESmall", 130),
+                                            (40000, 384, "BGESmall", 600),   # 5 query groups: odd super-group tail
+
                                             (9000, 1024, "BGELarge", 8), (50000, 768, "MultilingualE5Base", 256)])
 def test_gemm_path_matches_oracle(gpu_ctx, orc, n, dim, model, B):
     rows = synth.make_vectors(n, dim, seed=n)
