@@ -84,11 +84,37 @@ __global__ void __launch_bounds__(256) shard_pack_kernel(const ShardPackParams p
     uint32_t got = 0;
     if (has_ft) {
         const uint64_t total = uint64_t(p.n_tiles) * p.n_keep;
-        got = block_topn_stream(buf, p.capb, p.n_keep, total, [&](uint64_t i) -> uint64_t {
-            const uint32_t t = uint32_t(i / p.n_keep), k = uint32_t(i % p.n_keep);
-            const size_t s = size_t(q) * p.n_tiles + t;
-            return k < p.cand_cnt[s] ? p.cand_key[s * p.n_keep + k] : KEY_NONE;
-        });
+        // compact the (mostly empty) per-tile candidate lists, sort only the valid keys
+        __shared__ uint32_t s_scan[256];
+        __shared__ uint32_t s_nvalid;
+        uint32_t mine = 0;
+        for (uint32_t t = tid; t < p.n_tiles; t += blockDim.x) mine += min(p.cand_cnt[size_t(q) * p.n_tiles + t], p.n_keep);
+        s_scan[tid] = mine;
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t acc = 0;
+            for (uint32_t i = 0; i < blockDim.x; i++) { const uint32_t c = s_scan[i]; s_scan[i] = acc; acc += c; }
+            s_nvalid = acc;
+        }
+        __syncthreads();
+        if (s_nvalid <= p.capb) {
+            uint32_t pos = s_scan[tid];
+            for (uint32_t t = tid; t < p.n_tiles; t += blockDim.x) {
+                const size_t s2 = size_t(q) * p.n_tiles + t;
+                const uint32_t c = min(p.cand_cnt[s2], p.n_keep);
+                for (uint32_t k = 0; k < c; k++) buf[pos++] = p.cand_key[s2 * p.n_keep + k];
+            }
+            const uint32_t nv = s_nvalid, np2 = max(32u, next_pow2(nv));
+            for (uint32_t i = nv + tid; i < np2; i += blockDim.x) buf[i] = KEY_NONE;
+            group_bitonic_desc(buf, np2, tid, blockDim.x, 0);
+            got = min(nv, p.n_keep);
+        } else {
+            got = block_topn_stream(buf, p.capb, p.n_keep, total, [&](uint64_t i) -> uint64_t {
+                const uint32_t t = uint32_t(i / p.n_keep), k = uint32_t(i % p.n_keep);
+                const size_t s = size_t(q) * p.n_tiles + t;
+                return k < p.cand_cnt[s] ? p.cand_key[s * p.n_keep + k] : KEY_NONE;
+            });
+        }
         for (uint32_t i = tid; i < p.n_keep; i += blockDim.x) {
             ShardFt e{0, 0.f, 0xffffffffu};
             if (i < got) {
@@ -326,7 +352,8 @@ static int run_sharded_merge(oc_ctx *c, const oc_search_params *p, const oc::Fus
     ShardFuseParams sp{};
     sp.recv = c->shard_recv.as<uint8_t>(); sp.world = W; sp.n_queries = B; sp.mode = p->mode;
     sp.n_keep = fp.n_keep; sp.limit = fp.limit; sp.offset = fp.offset; sp.v_stride = fp.v_stride;
-    sp.capb = std::max<uint32_t>(2048, next_pow2(2 * std::max(fp.n_keep, fp.v_stride)));
+    sp.capb = std::min<uint32_t>(2048, std::max<uint32_t>(64, next_pow2(std::max<uint32_t>(W * fp.n_keep + fp.v_stride, W * fp.v_stride))));
+    sp.capb = std::max<uint32_t>(sp.capb, next_pow2(2 * std::max(fp.n_keep, fp.v_stride)));
     sp.omc_doc = fp.omc_doc; sp.omc_mult = fp.omc_mult; sp.n_omc = fp.n_omc;
     sp.out_doc = fp.out_doc; sp.out_score = fp.out_score; sp.out_n = fp.out_n; sp.out_count = fp.out_count; sp.out_min = fp.out_min;
     const size_t fsmem = size_t(sp.capb) * 8 + size_t(fp.v_stride) * 36 + 64;
