@@ -112,7 +112,15 @@ int oc_str_set_rows(oc_str *s, uint64_t n_rows, const uint64_t *row_doc_ids, uin
 int oc_str_load_field(oc_str *s, uint32_t field, float avg_field_len, uint32_t n_terms,
                       const uint64_t *term_offsets, const uint32_t *post_row, const uint16_t *post_tf,
                       const uint16_t *post_len, const uint32_t *global_df);
-/* StringFieldStorage::delete (string_field.rs:180-182): tombstones rows until the next load. */
+/* StringFieldStorage::insert(DocumentId, IndexedValue{field_length:u16, terms}) (string_field.rs:155-177),
+ * with terms already resolved to the field's term ids by the host dictionary: buffered on the host,
+ * visible to searches after oc_str_commit. Re-inserting a document replaces its postings in that field. */
+int oc_str_insert(oc_str *s, uint32_t field, uint64_t doc_id, uint16_t field_len, uint32_t n_terms,
+                  const uint32_t *term_ids, const uint16_t *tfs);
+/* == compact(version) (string_field.rs:186-191): merges pending inserts / deletes into the committed
+ * device-resident layout (rows = ascending doc ids, avg_field_len and document_count refreshed). */
+int oc_str_commit(oc_str *s);
+/* StringFieldStorage::delete (string_field.rs:180-182): tombstones rows until the next commit / load. */
 int oc_str_delete(oc_str *s, const uint64_t *doc_ids, uint64_t n);
 
 typedef struct {

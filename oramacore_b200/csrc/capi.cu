@@ -643,11 +643,15 @@ struct StrField {
     Posting *post = nullptr;             // device: (row, tf') derived for b_cached
     float b_cached = -1.f;
     uint64_t n_post = 0;
+    std::vector<PostingRaw> host_post;   // host copy of the committed postings (term-major), kept for oc_str_commit
+    struct Pending { uint64_t doc; uint32_t term; uint16_t tf, len; };
+    std::vector<Pending> pending;        // StringFieldStorage::insert since the last commit
 };
 struct oc_str {
     oc_ctx *ctx;
     std::vector<StrField> fields;
     uint64_t n_rows = 0, document_count = 0;
+    bool explicit_doc_count = false;     // set_rows gave a (global) N: commit must not overwrite it
     std::vector<uint64_t> row_doc_host;  // empty => identity
     uint64_t *row_doc = nullptr;         // device or NULL
     uint32_t *alive = nullptr;           // device bitmap (allocated on first delete)
@@ -681,6 +685,7 @@ extern "C" int oc_str_set_rows(oc_str *s, uint64_t n_rows, const uint64_t *row_d
     cudaFree(s->row_doc); s->row_doc = nullptr; s->row_doc_host.clear();
     cudaFree(s->alive); s->alive = nullptr; s->alive_host.clear(); s->n_deleted = 0;
     s->n_rows = n_rows; s->document_count = document_count;
+    s->explicit_doc_count = document_count != n_rows;
     if (row_doc_ids && n_rows) {
         for (uint64_t i = 1; i < n_rows; i++)
             if (row_doc_ids[i] <= row_doc_ids[i - 1]) return fail(OC_ERR_INVALID, "row_doc_ids must be strictly ascending");
@@ -707,6 +712,8 @@ extern "C" int oc_str_load_field(oc_str *s, uint32_t field, float avg_field_len,
         if (term_offsets[t + 1] - term_offsets[t] > 0xffffffffull) return fail(OC_ERR_UNSUPPORTED, "posting list too long");
     }
     f.avg_len = avg_field_len; f.n_terms = n_terms; f.n_post = np;
+    f.host_post.resize(np);
+    for (uint64_t i = 0; i < np; i++) { f.host_post[i].row = post_row[i]; f.host_post[i].tf = post_tf[i]; f.host_post[i].len = post_len[i]; }
     f.term_offsets.assign(term_offsets, term_offsets + n_terms + 1);
     f.global_df.clear();
     if (global_df) f.global_df.assign(global_df, global_df + n_terms);
@@ -751,6 +758,102 @@ extern "C" int oc_str_delete(oc_str *s, const uint64_t *doc_ids, uint64_t n) {
         if (s->alive_host[r >> 5] & (1u << (r & 31))) { s->alive_host[r >> 5] &= ~(1u << (r & 31)); s->n_deleted++; }
     }
     CU(cudaMemcpy(s->alive, s->alive_host.data(), words * 4, cudaMemcpyHostToDevice));
+    return OC_OK;
+}
+
+// StringFieldStorage::insert(DocumentId, IndexedValue{field_length, terms}) (string_field.rs:155-177):
+// buffered on the host; visible to searches after oc_str_commit (== compact, :186-191).
+extern "C" int oc_str_insert(oc_str *s, uint32_t field, uint64_t doc_id, uint16_t field_len, uint32_t n_terms,
+                             const uint32_t *term_ids, const uint16_t *tfs) {
+    if (!s || field >= s->fields.size() || (n_terms && (!term_ids || !tfs))) return fail(OC_ERR_INVALID, "bad arguments");
+    std::lock_guard<std::mutex> g(s->ctx->mu);
+    StrField &f = s->fields[field];
+    for (uint32_t i = 0; i < n_terms; i++) f.pending.push_back({doc_id, term_ids[i], tfs[i], field_len});
+    return OC_OK;
+}
+
+static int str_upload_field(oc_str *s, StrField &f);
+
+// Merges pending inserts and deletes into the committed, device-resident layout: rows are
+// re-derived as the ascending doc ids, postings re-sorted term-major / row-ascending,
+// avg_field_len and document_count refreshed (unless a global count was given), tombstones dropped.
+extern "C" int oc_str_commit(oc_str *s) {
+    if (!s) return fail(OC_ERR_INVALID, "str is NULL");
+    oc_ctx *c = s->ctx;
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    // surviving old rows -> doc ids
+    std::vector<uint64_t> docs;
+    std::vector<uint8_t> old_alive(s->n_rows, 1);
+    for (uint64_t r = 0; r < s->n_rows; r++) {
+        const bool alive = s->alive_host.empty() || (s->alive_host[r >> 5] >> (r & 31)) & 1u;
+        old_alive[r] = alive;
+        if (alive) docs.push_back(s->row_doc_host.empty() ? r : s->row_doc_host[r]);
+    }
+    for (auto &f : s->fields) for (auto &pn : f.pending) docs.push_back(pn.doc);
+    std::sort(docs.begin(), docs.end());
+    docs.erase(std::unique(docs.begin(), docs.end()), docs.end());
+    if (docs.size() > 0xfffffff0ull) return fail(OC_ERR_UNSUPPORTED, "more than 2^32 rows per store");
+    auto row_of = [&](uint64_t d) { return (uint32_t)(std::lower_bound(docs.begin(), docs.end(), d) - docs.begin()); };
+    std::vector<uint32_t> remap(s->n_rows, 0xffffffffu);
+    for (uint64_t r = 0; r < s->n_rows; r++) if (old_alive[r]) remap[r] = row_of(s->row_doc_host.empty() ? r : s->row_doc_host[r]);
+    struct Rec { uint32_t term, row; uint16_t tf, len; };
+    for (auto &f : s->fields) {
+        std::vector<Rec> recs;
+        recs.reserve(f.host_post.size() + f.pending.size());
+        // a re-inserted document replaces its old postings in this field
+        std::vector<uint8_t> replaced(docs.size(), 0);
+        for (auto &pn : f.pending) replaced[row_of(pn.doc)] = 1;
+        for (uint32_t t = 0; t < f.n_terms; t++)
+            for (uint64_t i = f.term_offsets[t]; i < f.term_offsets[t + 1]; i++) {
+                const uint32_t nr = remap[f.host_post[i].row];
+                if (nr != 0xffffffffu && !replaced[nr]) recs.push_back({t, nr, f.host_post[i].tf, f.host_post[i].len});
+            }
+        uint32_t max_term = f.n_terms;
+        for (auto &pn : f.pending) { recs.push_back({pn.term, row_of(pn.doc), pn.tf, pn.len}); max_term = std::max(max_term, pn.term + 1); }
+        std::sort(recs.begin(), recs.end(), [](const Rec &a, const Rec &b) { return a.term != b.term ? a.term < b.term : a.row < b.row; });
+        f.n_terms = max_term;
+        f.term_offsets.assign(size_t(max_term) + 1, 0);
+        f.host_post.resize(recs.size());
+        std::vector<uint16_t> len_of_row(docs.size(), 0);
+        for (size_t i = 0; i < recs.size(); i++) {
+            if (i && recs[i].term == recs[i - 1].term && recs[i].row == recs[i - 1].row) return fail(OC_ERR_INVALID, "duplicate (term, doc) posting");
+            f.term_offsets[recs[i].term + 1]++;
+            f.host_post[i].row = recs[i].row; f.host_post[i].tf = recs[i].tf; f.host_post[i].len = recs[i].len;
+            len_of_row[recs[i].row] = recs[i].len;
+        }
+        for (uint32_t t = 0; t < max_term; t++) f.term_offsets[t + 1] += f.term_offsets[t];
+        double sum = 0; uint64_t cnt = 0;
+        for (uint16_t l : len_of_row) if (l) { sum += l; cnt++; }
+        if (cnt) f.avg_len = (float)(sum / (double)cnt);   // info().avg_field_length
+        f.pending.clear();
+        f.global_df.clear();
+        f.n_post = recs.size();
+    }
+    // rows
+    const bool identity = !docs.empty() && docs.front() == 0 && docs.back() == docs.size() - 1;
+    cudaFree(s->row_doc); s->row_doc = nullptr; s->row_doc_host.clear();
+    cudaFree(s->alive); s->alive = nullptr; s->alive_host.clear(); s->n_deleted = 0;
+    if (!s->explicit_doc_count) s->document_count = docs.size();
+    s->n_rows = docs.size();
+    if (!identity && !docs.empty()) {
+        s->row_doc_host = docs;
+        CU(cudaMalloc(&s->row_doc, docs.size() * 8));
+        CU(cudaMemcpy(s->row_doc, docs.data(), docs.size() * 8, cudaMemcpyHostToDevice));
+    }
+    for (auto &f : s->fields) OCTRY(str_upload_field(s, f));
+    return OC_OK;
+}
+
+static int str_upload_field(oc_str *s, StrField &f) {
+    oc_ctx *c = s->ctx;
+    cudaFree(f.post); f.post = nullptr; cudaFree(f.raw); f.raw = nullptr; f.b_cached = -1.f;
+    const uint64_t np = f.host_post.size();
+    if (!np) return OC_OK;
+    CU(cudaMalloc(&f.post, (np + 4) * sizeof(Posting)));
+    CU(cudaMalloc(&f.raw, (np + 4) * sizeof(PostingRaw)));
+    CU(cudaMemcpyAsync(f.raw, f.host_post.data(), np * sizeof(PostingRaw), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
     return OC_OK;
 }
 

@@ -171,10 +171,30 @@ class StringFieldStorage:
                                           _p(np.ascontiguousarray(f.post_tf)), _p(np.ascontiguousarray(f.post_len)),
                                           _p(gdf)))
 
+    @classmethod
+    def empty(cls, ctx: Context, n_fields: int = 1) -> "StringFieldStorage":
+        """StringFieldStorage::new (string_field.rs:72-82): no committed postings yet."""
+        self = cls.__new__(cls)
+        self.ctx, self.data = ctx, None
+        self._h = C.c_void_p()
+        check(lib().oc_str_create(ctx._h, n_fields, C.byref(self._h)))
+        return self
+
     def close(self):
         if self._h:
             lib().oc_str_destroy(self._h)
             self._h = C.c_void_p()
+
+    def insert(self, doc_id: int, field: int, field_length: int, terms: Dict[int, int]):
+        """insert(DocumentId, IndexedValue{field_length, terms}) (string_field.rs:155-177) with terms
+        resolved to term ids; visible after commit()."""
+        t = np.asarray(list(terms.keys()), np.uint32)
+        f = np.asarray([min(v, 65535) for v in terms.values()], np.uint16)
+        check(lib().oc_str_insert(self._h, field, int(doc_id), min(int(field_length), 65535), t.shape[0], _p(t), _p(f)))
+
+    def commit(self):
+        """compact(version) (string_field.rs:186-191)."""
+        check(lib().oc_str_commit(self._h))
 
     def delete(self, doc_id: int):
         d = np.asarray([doc_id], np.uint64)

@@ -352,3 +352,60 @@ def test_scale_properties(gpu_ctx, orc):
     hits = ob.search(gpu_ctx, None, strs, "fulltext", texts=texts, limit=10)
     _check(hits, _oracle_batch(orc, data, None, 0, texts=texts, limit=10), exact_scores=True)
     strs.close()
+
+
+def test_incremental_insert_commit_delete(gpu_ctx, orc):
+    # StringFieldStorage::insert / delete / compact (string_field.rs:155-191) through oc_str_insert/_commit
+    rng = np.random.default_rng(3)
+    vocab = [f"w{i}" for i in range(300)]
+    docs = {}
+    for d in range(0, 4000, 2):                      # sparse, even doc ids
+        n = int(rng.integers(3, 40))
+        docs[d] = " ".join(rng.choice(vocab, size=n, p=None))
+    from oramacore_b200.hostindex import HostStringIndex, tokenize
+    tid = {t: i for i, t in enumerate(sorted(vocab))}
+
+    def feed(strs, items):
+        for d, text in items:
+            toks = tokenize(text)
+            counts = {}
+            for t in toks:
+                counts[tid[t]] = counts.get(tid[t], 0) + 1
+            strs.insert(d, 0, len(toks), counts)
+
+    strs = ob.StringFieldStorage.empty(gpu_ctx, 1)
+    items = sorted(docs.items())
+    feed(strs, items[:1500])
+    strs.commit()
+    feed(strs, items[1500:])                         # second batch + a replacement + deletes
+    docs[10] = "w1 w1 w1 w2"
+    feed(strs, [(10, docs[10])])
+    strs.commit()
+    for gone in (20, 30):
+        strs.delete(gone)
+        docs.pop(gone)
+    strs.commit()
+
+    h = HostStringIndex(["text"])
+    for d, text in sorted(docs.items()):
+        h.insert(d, {"text": text})
+    h.commit()
+    # the incremental store numbers terms by the fixed vocabulary; rebuild the oracle's view with the same ids
+    assert h.terms[0] == sorted(set(t for text in docs.values() for t in tokenize(text)))
+    remap = {i: tid[t] for i, t in enumerate(h.terms[0])}
+    texts = []
+    for _ in range(10):
+        ids = rng.choice(len(h.terms[0]), size=3, replace=False)
+        texts.append(([int(i) for i in ids], [remap[int(i)] for i in ids]))
+    ix = orc.StrIndex(h.data)
+    sb = orc.SearchBatch(ix, None)
+    for o_ids, _ in texts:
+        sb.add(0, limit=10, text=TextQuery.single_terms(o_ids))
+    od, os_, on, oc = sb.run(2)
+    hits = ob.search(gpu_ctx, None, strs, "fulltext", texts=[TextQuery.single_terms(g) for _, g in texts], limit=10)
+    for i, hh in enumerate(hits):
+        assert hh.count == int(oc[i])
+        assert np.array_equal(hh.scores, os_[i, :on[i]]), (hh.scores, os_[i, :on[i]])
+        assert_topk_equal(hh.doc_ids, hh.scores, od[i, :on[i]], os_[i, :on[i]])
+    assert strs.info()["total_documents"] == len(docs)
+    strs.close()
