@@ -46,7 +46,7 @@ struct TermDesc {      // one expanded index term of one token of one query
     uint32_t len;          // postings in the list (rows unique, ascending)
     float weight;          // field boost x exact-match factor
     float avg_len;         // the field's avg_field_length
-    uint32_t pad;
+    uint32_t flags;        // bit0: postings are batch-precomputed (row, c) records, see bm25_precompute_kernel
 };
 
 struct TokenDesc {
@@ -104,6 +104,13 @@ __global__ void bm25_derive_postings_kernel(const PostingRaw *raw, uint64_t n, f
 __device__ __forceinline__ float bm25_sat(float S, float k, float kp1, float idf) {
     return __fdiv_rn(__fmul_rn(__fmul_rn(idf, kp1), S), __fadd_rn(k, S));
 }
+struct PreDesc {        // one (term, weight) pair shared by several queries of the batch
+    const Posting *src;
+    Posting *dst;
+    uint32_t len;
+    float weight, idf;
+    uint32_t pad;
+};
 __device__ __forceinline__ bool f32_is_normal(float x) {
     const uint32_t e = (__float_as_uint(x) >> 23) & 0xffu;
     return e != 0u && e != 0xffu;
@@ -148,6 +155,27 @@ __host__ __device__ inline size_t bm25_smem_bytes(bool multi, bool threshold, bo
     b += size_t(BM25_TILE) / 8;                       // row_ok bits
     b += size_t(cap) * 8;                             // top buffer keys (ft is re-read from score[])
     return b + 64;
+}
+
+// Zipf query terms repeat across the queries of a batch: the per-posting contribution
+// c = idf*(k+1)*S/(k+S), S = w*tf' of a single-term token depends only on (term, weight), so it is
+// computed ONCE per batch into (row, c) records (same rounded ops => bit-identical scores); the
+// tile kernel then only adds.  items[i] = (pre index, chunk of PRE_CHUNK postings).
+constexpr uint32_t PRE_CHUNK = 4096;
+__global__ void __launch_bounds__(256) bm25_precompute_kernel(const PreDesc *pre, const uint2 *items, float k) {
+    const uint2 it = items[blockIdx.x];
+    const PreDesc d = pre[it.x];
+    const float kp1 = __fadd_rn(k, 1.0f);
+    const uint32_t lo = it.y * PRE_CHUNK, hi = min(d.len, lo + PRE_CHUNK);
+    const uint2 *src = reinterpret_cast<const uint2 *>(d.src);
+    uint2 *dst = reinterpret_cast<uint2 *>(d.dst);
+    for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        const uint2 r = __ldg(src + i);
+        const float ntf = __fmul_rn(d.weight, __uint_as_float(r.y));
+        float c = __int_as_float(0x7fc00000);                  // NaN => skipped (bm25.rs:387,391)
+        if (f32_is_normal(ntf)) c = bm25_sat(ntf, k, kp1, d.idf);
+        dst[i] = make_uint2(r.x, __float_as_uint(c));
+    }
 }
 
 // ---- df pre-pass (only when a filter / tombstones / multi-term tokens make df != list length):
@@ -286,7 +314,7 @@ __global__ void __launch_bounds__(BM25_THREADS) bm25_tile_kernel(const Bm25Param
                 t_n[j] = hi - lo;
                 t_w[j] = td.weight; t_idf[j] = tk.idf; t_bit[j] = tk.bit;
                 const bool single = !MULTI || (tk.term_end - tk.term_begin == 1);
-                t_flag[j] = (single ? 1u : 0u) | ((e + 1 == tk.term_end) ? 2u : 0u);
+                t_flag[j] = (single ? 1u : 0u) | ((e + 1 == tk.term_end) ? 2u : 0u) | ((td.flags & 1u) ? 4u : 0u);
                 t_tok_begin[j] = tk.term_begin;
             }
             __syncthreads();
@@ -322,6 +350,14 @@ __global__ void __launch_bounds__(BM25_THREADS) bm25_tile_kernel(const Bm25Param
                         if (rec[u].x == 0xffffffffu) continue;
                         const uint32_t l = rec[u].x - row0;
                         if (use_ok && !((okb[l >> 5] >> (l & 31)) & 1u)) continue;
+                        if (flag & 4u) {   // contribution precomputed once per batch for this (term, weight): NaN = skip
+                            const float c = __uint_as_float(rec[u].y);
+                            if (c == c) {
+                                score[l] = __fadd_rn(score[l], c);
+                                if (THRESH) mask[l] |= bit;
+                            }
+                            continue;
+                        }
                         const float ntf = __fmul_rn(w, __uint_as_float(rec[u].y));   // w * tf'
                         if (single) {
                             // S = 0.0 + 1.0*ntf; skip unless is_normal (bm25.rs:387,501)

@@ -118,7 +118,7 @@ struct oc_ctx {
     DevBuf seg, df_dev, row_ok, tau, cand_key, cand_ft, cand_cnt, tile_cnt, tile_max, tile_min, min_hint;
     DevBuf out_blob, shard_send, shard_recv;
     bool gemm_pending = false; const float *gemm_inv_norm = nullptr;
-    DevBuf g_tau, g_cand, g_cnt, g_flag, g_max, r_qpad, r_qinv, r_map, r_doc, r_score, r_row, r_cnt, r_raw;
+    DevBuf pre_post, g_tau, g_cand, g_cnt, g_flag, g_max, r_qpad, r_qinv, r_map, r_doc, r_score, r_row, r_cnt, r_raw;
 
     HostBuf h_in, h_out;
     OcComm comm;
@@ -159,7 +159,7 @@ extern "C" void oc_shutdown(oc_ctx *c) {
     DevBuf *bufs[] = {&c->in_blob, &c->q_pad, &c->q_inv, &c->eff_norm, &c->filter_dev, &c->scan_cand, &c->v_doc,
                       &c->v_score, &c->v_row, &c->v_cnt, &c->v_srow, &c->v_ft, &c->v_present, &c->v_raw, &c->seg, &c->df_dev,
                       &c->row_ok, &c->tau, &c->cand_key, &c->cand_ft, &c->cand_cnt, &c->tile_cnt, &c->tile_max,
-                      &c->tile_min, &c->min_hint, &c->out_blob, &c->shard_send, &c->shard_recv, &c->g_tau, &c->g_cand, &c->g_cnt, &c->g_max,
+                      &c->tile_min, &c->min_hint, &c->out_blob, &c->shard_send, &c->shard_recv, &c->pre_post, &c->g_tau, &c->g_cand, &c->g_cnt, &c->g_max,
                       &c->g_flag, &c->r_qpad, &c->r_qinv, &c->r_map, &c->r_doc, &c->r_score, &c->r_row, &c->r_cnt, &c->r_raw};
     for (DevBuf *b : bufs) b->release();
     c->h_in.release(); c->h_out.release();
@@ -932,9 +932,12 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
     const uint32_t n_tiles = has_ft ? (uint32_t)((str->n_rows + BM25_TILE - 1) / BM25_TILE) : 0;
     std::vector<TermDesc> terms;
     std::vector<uint32_t> term_token;
+    std::vector<uint64_t> term_key;     // (field << 32 | term id) of each expanded term
     std::vector<TokenDesc> tokens;
     std::vector<QueryDesc> queries;
     std::vector<uint8_t> tok_need_df;
+    std::vector<PreDesc> pre_descs;
+    std::vector<uint2> pre_items;
     bool any_multi = false, need_df = false;
     uint64_t postings_walked = 0;
     const bool thr = p->threshold >= 0.0f;
@@ -972,6 +975,7 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
                     td.avg_len = f.avg_len;
                     df_known = f.global_df.empty() ? td.len : f.global_df[ti];
                     postings_walked += td.len;
+                    term_key.push_back((uint64_t(fi) << 32) | ti);
                     terms.push_back(td);
                     term_token.push_back((uint32_t)tokens.size());
                 }
@@ -987,6 +991,46 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
             }
             qd.token_end = (uint32_t)tokens.size();
             queries[q] = qd;
+        }
+        // ---- batch-level sharing of per-posting contributions (single-term tokens with a host-known idf)
+        {
+            struct U { uint32_t first_e; uint32_t uses; };
+            std::unordered_map<std::string, uint32_t> index;   // key: (field, term, weight bits, idf bits)
+            std::vector<U> uniq;
+            std::vector<uint32_t> e_to_u(terms.size(), 0xffffffffu);
+            uint64_t walked = 0, distinct = 0;
+            for (size_t t = 0; t < tokens.size(); t++) {
+                const TokenDesc &tk = tokens[t];
+                if (tk.term_end - tk.term_begin != 1 || tok_need_df[t]) continue;
+                const uint32_t e = tk.term_begin;
+                if (terms[e].len < 64) continue;
+                char key[24];
+                memcpy(key, &term_key[e], 8); memcpy(key + 8, &terms[e].weight, 4); memcpy(key + 12, &tk.idf, 4);
+                auto ins = index.emplace(std::string(key, 16), (uint32_t)uniq.size());
+                if (ins.second) { uniq.push_back({e, 0}); distinct += terms[e].len; }
+                uniq[ins.first->second].uses++;
+                e_to_u[e] = ins.first->second;
+                walked += terms[e].len;
+            }
+            const char *share_env = getenv("OC_BM25_SHARE");   // "off" / "force": A/B testing of the sharing pass
+            const bool share_off = share_env && !strcmp(share_env, "off"), share_force = share_env && !strcmp(share_env, "force");
+            if (distinct && !share_off && (share_force || walked >= distinct + distinct / 2) && distinct * 8 <= (size_t(6) << 30)) {
+                OCTRY(c->pre_post.ensure(distinct * 8 + 64));
+                uint64_t off = 0;
+                std::vector<uint64_t> u_off(uniq.size());
+                for (size_t u = 0; u < uniq.size(); u++) {
+                    u_off[u] = off;
+                    const TermDesc &td = terms[uniq[u].first_e];
+                    PreDesc pd{};
+                    pd.src = td.ptr; pd.dst = c->pre_post.as<Posting>() + off; pd.len = td.len; pd.weight = td.weight;
+                    pd.idf = tokens[term_token[uniq[u].first_e]].idf;
+                    pre_descs.push_back(pd);
+                    for (uint32_t ch = 0; ch * PRE_CHUNK < td.len; ch++) pre_items.push_back(make_uint2((uint32_t)u, ch));
+                    off += td.len;
+                }
+                for (size_t e = 0; e < terms.size(); e++)
+                    if (e_to_u[e] != 0xffffffffu) { terms[e].ptr = c->pre_post.as<Posting>() + u_off[e_to_u[e]]; terms[e].flags |= 1u; }
+            }
         }
         if (need_df && p->sharded && c->comm.world > 1) return fail(OC_ERR_UNSUPPORTED, "sharded search with filters/multi-term tokens needs a df all-reduce (not built)");
     }
@@ -1017,6 +1061,8 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
     const size_t o_terms = has_ft ? pk.add(terms.data(), terms.size() * sizeof(TermDesc)) : 0;
     const size_t o_tokens = has_ft ? pk.add(tokens.data(), tokens.size() * sizeof(TokenDesc)) : 0;
     const size_t o_ttok = has_ft ? pk.add(term_token.data(), term_token.size() * 4) : 0;
+    const size_t o_pre = pre_descs.empty() ? 0 : pk.add(pre_descs.data(), pre_descs.size() * sizeof(PreDesc));
+    const size_t o_pitems = pre_items.empty() ? 0 : pk.add(pre_items.data(), pre_items.size() * sizeof(uint2));
     const size_t o_queries = has_ft ? pk.add(queries.data(), queries.size() * sizeof(QueryDesc)) : 0;
     const size_t o_omcd = n_omc ? pk.add(p->omc_doc_ids, size_t(n_omc) * 8) : 0;
     const size_t o_omcm = n_omc ? pk.add(p->omc_mult, size_t(n_omc) * 4) : 0;
@@ -1065,6 +1111,12 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
     auto device_tail = [&]() -> int {
     if (has_ft) {
         CU(cudaEventRecord(c->ev[EV_BM0], c->stream));
+        if (!pre_items.empty()) {
+            bm25_precompute_kernel<<<(unsigned)pre_items.size(), 256, 0, c->stream>>>(
+                reinterpret_cast<const PreDesc *>(din + o_pre), reinterpret_cast<const uint2 *>(din + o_pitems), p->bm25_k);
+            launched(c);
+            CU(cudaGetLastError());
+        }
         const uint64_t ok_words = uint64_t(n_tiles) * (BM25_TILE / 32);
         const uint32_t *row_ok = nullptr;
         if (filter || tombs) {

@@ -409,3 +409,21 @@ def test_incremental_insert_commit_delete(gpu_ctx, orc):
         assert_topk_equal(hh.doc_ids, hh.scores, od[i, :on[i]], os_[i, :on[i]])
     assert strs.info()["total_documents"] == len(docs)
     strs.close()
+
+
+def test_bm25_shared_term_precompute_is_bit_identical(gpu_ctx, orc):
+    # the batch-level sharing of per-posting contributions must not change a single bit
+    data = synth.make_text_corpus(60000, 2000, seed=17)
+    texts = synth.make_text_queries(2000, 64, seed=18)
+    strs = ob.StringFieldStorage(gpu_ctx, data)
+    out = {}
+    for mode in ("off", "force"):
+        os.environ["OC_BM25_SHARE"] = mode
+        try:
+            out[mode] = ob.search(gpu_ctx, None, strs, "fulltext", texts=texts, limit=10, threshold=0.5)
+        finally:
+            os.environ.pop("OC_BM25_SHARE", None)
+    for a, b in zip(out["off"], out["force"]):
+        assert a.count == b.count and np.array_equal(a.doc_ids, b.doc_ids) and np.array_equal(a.scores, b.scores)
+    _check(out["force"], _oracle_batch(orc, data, None, 0, texts=texts, limit=10, threshold=0.5), exact_scores=True)
+    strs.close()
