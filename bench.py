@@ -216,7 +216,10 @@ def main():
     qv = wl.get("qv")
     # the step's inputs as they sit in host memory: resolved term ids (packed CSR) + query vectors
     packed = ob.TextQueryBatch(texts) if texts is not None else None
-    qv_host = None if qv is None else np.ascontiguousarray(qv, np.float32)
+    qv_host = None
+    if qv is not None:          # the step's query vectors sit in pinned host memory (DMA'd by oc_search)
+        qv_host = ob.pinned_empty(qv.shape, np.float32)
+        qv_host[...] = qv
 
     def step():
         return tsc.execute_batch_arrays(params, packed, qv_host)

@@ -167,6 +167,12 @@ typedef struct {
 int oc_search(oc_ctx *ctx, oc_emb *emb, oc_str *str, const oc_search_params *p,
               uint64_t *out_doc_ids, float *out_scores, uint32_t *out_n, uint64_t *out_count);
 
+/* ---- pinned host buffers (optional) ----------------------------------------------------------
+ * Query vectors handed to oc_search from memory obtained here (or otherwise page-locked) are
+ * DMA'd straight from the caller's buffer; pageable buffers are staged through a pinned blob. */
+int oc_pinned_alloc(size_t bytes, void **out);
+void oc_pinned_free(void *p);
+
 /* ---- measurement ------------------------------------------------------------------------
  * CUDA-event timings (ms, on the ctx stream) of the last oc_search / oc_emb_search on this
  * ctx, and launch counts. */

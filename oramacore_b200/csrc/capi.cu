@@ -88,19 +88,26 @@ struct HostBuf {  // pinned staging
 // lays several host arrays out in one pinned blob -> one H2D copy (sources are copied once,
 // straight into the pinned staging buffer)
 struct Packer {
-    struct Seg { const void *src; size_t off, bytes; };
+    struct Seg { const void *src; size_t off, bytes; bool direct; };
     std::vector<Seg> segs;
     size_t total = 0;
-    size_t add(const void *src, size_t bytes) {
+    // direct = the source already lives in pinned host memory (oc_pinned_alloc / cudaHostRegister):
+    // it is DMA'd straight from the caller's buffer instead of being staged
+    size_t add(const void *src, size_t bytes, bool direct = false) {
         const size_t off = (total + 255) & ~size_t(255);
-        segs.push_back({src, off, bytes});
+        segs.push_back({src, off, bytes, direct});
         total = off + bytes;
         return off;
     }
     void fill(void *dst) const {
-        for (const Seg &g : segs) if (g.bytes && g.src) memcpy(static_cast<uint8_t *>(dst) + g.off, g.src, g.bytes);
+        for (const Seg &g : segs) if (g.bytes && g.src && !g.direct) memcpy(static_cast<uint8_t *>(dst) + g.off, g.src, g.bytes);
     }
 };
+static bool is_pinned_host(const void *p) {
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
 
 enum { EV_START, EV_H2D, EV_DEV, EV_D2H, EV_SCAN0, EV_SCAN1, EV_BM0, EV_BM1, EV_FUSE0, EV_FUSE1, EV_COMM0, EV_COMM1, EV_N };
 
@@ -175,6 +182,13 @@ extern "C" int oc_device_info(oc_ctx *c, int *sm_count, size_t *hbm_bytes, char 
     if (name && name_cap) { strncpy(name, c->prop.name, name_cap - 1); name[name_cap - 1] = 0; }
     return OC_OK;
 }
+
+extern "C" int oc_pinned_alloc(size_t bytes, void **out) {
+    if (!out) return fail(OC_ERR_INVALID, "out is NULL");
+    CU(cudaMallocHost(out, bytes ? bytes : 1));
+    return OC_OK;
+}
+extern "C" void oc_pinned_free(void *p) { if (p) cudaFreeHost(p); }
 
 extern "C" int oc_last_timing(oc_ctx *c, oc_timing *out) {
     if (!c || !out) return fail(OC_ERR_INVALID, "NULL argument");
@@ -995,7 +1009,11 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
         // ---- batch-level sharing of per-posting contributions (single-term tokens with a host-known idf)
         {
             struct U { uint32_t first_e; uint32_t uses; };
-            std::unordered_map<std::string, uint32_t> index;   // key: (field, term, weight bits, idf bits)
+            struct K128 { uint64_t a, b; };            // (field, term) | (weight bits, idf bits)
+            size_t cap_t = 64;
+            while (cap_t < tokens.size() * 2) cap_t <<= 1;
+            std::vector<K128> tab_k(cap_t);
+            std::vector<uint32_t> tab_v(cap_t, 0xffffffffu);   // open addressing, linear probing
             std::vector<U> uniq;
             std::vector<uint32_t> e_to_u(terms.size(), 0xffffffffu);
             uint64_t walked = 0, distinct = 0;
@@ -1004,17 +1022,23 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
                 if (tk.term_end - tk.term_begin != 1 || tok_need_df[t]) continue;
                 const uint32_t e = tk.term_begin;
                 if (terms[e].len < 64) continue;
-                char key[24];
-                memcpy(key, &term_key[e], 8); memcpy(key + 8, &terms[e].weight, 4); memcpy(key + 12, &tk.idf, 4);
-                auto ins = index.emplace(std::string(key, 16), (uint32_t)uniq.size());
-                if (ins.second) { uniq.push_back({e, 0}); distinct += terms[e].len; }
-                uniq[ins.first->second].uses++;
-                e_to_u[e] = ins.first->second;
+                uint32_t wb, ib;
+                memcpy(&wb, &terms[e].weight, 4); memcpy(&ib, &tk.idf, 4);
+                const K128 key{term_key[e], (uint64_t(wb) << 32) | ib};
+                uint64_t h = (key.a * 0x9E3779B97F4A7C15ull) ^ (key.b * 0xC2B2AE3D27D4EB4Full);
+                size_t slot = (h ^ (h >> 29)) & (cap_t - 1);
+                while (tab_v[slot] != 0xffffffffu && !(tab_k[slot].a == key.a && tab_k[slot].b == key.b)) slot = (slot + 1) & (cap_t - 1);
+                if (tab_v[slot] == 0xffffffffu) {
+                    tab_k[slot] = key; tab_v[slot] = (uint32_t)uniq.size();
+                    uniq.push_back({e, 0}); distinct += terms[e].len;
+                }
+                uniq[tab_v[slot]].uses++;
+                e_to_u[e] = tab_v[slot];
                 walked += terms[e].len;
             }
             const char *share_env = getenv("OC_BM25_SHARE");   // "off" / "force": A/B testing of the sharing pass
             const bool share_off = share_env && !strcmp(share_env, "off"), share_force = share_env && !strcmp(share_env, "force");
-            if (distinct && !share_off && (share_force || walked >= distinct + distinct / 2) && distinct * 8 <= (size_t(6) << 30)) {
+            if (distinct && !share_off && (share_force || (walked >= 2 * distinct && walked >= (64u << 20))) && distinct * 8 <= (size_t(6) << 30)) {
                 OCTRY(c->pre_post.ensure(distinct * 8 + 64));
                 uint64_t off = 0;
                 std::vector<uint64_t> u_off(uniq.size());
@@ -1055,7 +1079,7 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
 
     // ------------------------------------------------------------ H2D: one packed blob
     Packer pk;
-    const size_t o_qv = has_v ? pk.add(p->q_vecs, size_t(B) * emb->dim * 4) : 0;
+    const size_t o_qv = has_v ? pk.add(p->q_vecs, size_t(B) * emb->dim * 4, is_pinned_host(p->q_vecs)) : 0;
     const size_t fwords = filter ? (p->filter_nbits + 63) / 64 : 0;
     const size_t o_flt = filter ? pk.add(p->filter_bits, fwords * 8) : 0;
     const size_t o_terms = has_ft ? pk.add(terms.data(), terms.size() * sizeof(TermDesc)) : 0;
@@ -1072,7 +1096,20 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
     OCTRY(c->in_blob.ensure(pk.total + 256));
     pk.fill(c->h_in.p);
     CU(cudaEventRecord(c->ev[EV_START], c->stream));
-    if (pk.total) CU(cudaMemcpyAsync(c->in_blob.p, c->h_in.p, pk.total, cudaMemcpyHostToDevice, c->stream));
+    {   // staged segments go in one copy per contiguous run; pinned caller buffers are DMA'd directly
+        size_t run0 = 0;
+        for (size_t i = 0; i <= pk.segs.size(); i++) {
+            const bool brk = i == pk.segs.size() || pk.segs[i].direct;
+            if (brk) {
+                const size_t end = i == pk.segs.size() ? pk.total : pk.segs[i].off;
+                if (end > run0) CU(cudaMemcpyAsync(c->in_blob.as<uint8_t>() + run0, c->h_in.as<uint8_t>() + run0, end - run0, cudaMemcpyHostToDevice, c->stream));
+                if (i < pk.segs.size()) {
+                    CU(cudaMemcpyAsync(c->in_blob.as<uint8_t>() + pk.segs[i].off, pk.segs[i].src, pk.segs[i].bytes, cudaMemcpyHostToDevice, c->stream));
+                    run0 = pk.segs[i].off + pk.segs[i].bytes;
+                }
+            }
+        }
+    }
     CU(cudaEventRecord(c->ev[EV_H2D], c->stream));
     c->timing.h2d_bytes = pk.total;
     uint8_t *din = c->in_blob.as<uint8_t>();

@@ -82,6 +82,16 @@ class Context:
         check(lib().oc_comm_init(self._h, world_size, rank, buf))
 
 
+def pinned_empty(shape, dtype=np.float32) -> np.ndarray:
+    """numpy array backed by page-locked host memory (oc_pinned_alloc): inputs placed here are DMA'd
+    directly by oc_search. The memory is intentionally never freed before interpreter exit."""
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = C.c_void_p()
+    check(lib().oc_pinned_alloc(n, C.byref(p)))
+    buf = (C.c_uint8 * max(n, 1)).from_address(p.value)
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+
 @dataclass
 class VectorSearchParams:
     """committed_field/vector.rs:10-15"""

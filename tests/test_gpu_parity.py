@@ -427,3 +427,37 @@ def test_bm25_shared_term_precompute_is_bit_identical(gpu_ctx, orc):
         assert a.count == b.count and np.array_equal(a.doc_ids, b.doc_ids) and np.array_equal(a.scores, b.scores)
     _check(out["force"], _oracle_batch(orc, data, None, 0, texts=texts, limit=10, threshold=0.5), exact_scores=True)
     strs.close()
+
+
+def test_concurrent_callers_share_one_ctx(gpu_ctx, orc):
+    # many searches run concurrently in the reference (tokio workers, read/mod.rs:621); handles are
+    # Send+Sync here: calls on one ctx serialise internally and must not corrupt each other
+    import threading
+    n, dim = 20000, 384
+    rows = synth.make_vectors(n, dim, seed=51)
+    data = synth.make_text_corpus(n, 1500, seed=52)
+    emb = ob.EmbeddingFieldStorage(gpu_ctx, "BGESmall")
+    emb.insert_batch(np.arange(n, dtype=np.uint64), rows)
+    strs = ob.StringFieldStorage(gpu_ctx, data)
+    qv, _ = synth.make_vector_queries(rows, 12, seed=53)
+    qv_p = ob.pinned_empty(qv.shape)                       # pinned inputs take the direct-DMA path
+    qv_p[...] = qv
+    texts = synth.make_text_queries(1500, 12, seed=54)
+    ref = _oracle_batch(orc, data, orc.EmbStore(rows), 2, texts=texts, qv=qv, limit=10, similarity=0.0)
+    errs = []
+
+    def worker(k):
+        try:
+            for _ in range(5):
+                hits = ob.search(gpu_ctx, emb, strs, "hybrid", texts=texts, q_vecs=qv_p if k % 2 else qv, limit=10, similarity=0.0)
+                _check(hits, ref)
+        except Exception as e:  # noqa
+            errs.append(e)
+
+    th = [threading.Thread(target=worker, args=(k,)) for k in range(4)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs, errs
+    emb.close(); strs.close()
