@@ -535,7 +535,7 @@ static int run_vector_stage(oc_ctx *c, oc_emb *e, const float *q_dev, uint32_t B
     mp.inv_qnorm = c->q_inv.as<float>(); mp.row_doc_ids = e->row_doc; mp.rescale_e5 = e->e5; mp.similarity = similarity;
     mp.out_doc = out.doc; mp.out_score = out.score; mp.out_row = out.row; mp.out_count = out.cnt; mp.out_raw = out.raw;
     mp.out_unproven = c->g_flag.as<uint8_t>();
-    emb_gemm_merge_kernel<<<B, 1024, (2048 + 64) * 8, c->stream>>>(mp);
+    emb_gemm_merge_kernel<<<B, 512, (2048 + 64) * 8, c->stream>>>(mp);
     launched(c);
     CU(cudaGetLastError());
     // the proof flags travel back with the results; oc_*search re-runs flagged queries (fix_unproven)

@@ -340,7 +340,7 @@ struct GemmMergeParams {
     uint8_t *out_unproven;       // [B] 1 => host must re-run this query through the exact sweep
 };
 
-__global__ void __launch_bounds__(1024) emb_gemm_merge_kernel(const GemmMergeParams p) {
+__global__ void __launch_bounds__(512, 2) emb_gemm_merge_kernel(const GemmMergeParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint64_t *buf = reinterpret_cast<uint64_t *>(smem);          // [2048]
     uint64_t *exact = buf + 2048;                                 // [64]
