@@ -5,9 +5,9 @@ from .types import (FieldPostings, StringIndexData, TextQuery, SearchHits, MODE_
                     MODE_HYBRID, BM25_B, BM25_K)
 from ._lib import OcError, build, lib, SO_PATH
 from .engine import (Context, EmbeddingFieldStorage, StringFieldStorage, TextQueryBatch, TokenScoreContext, TokenScoreParams,
-                     VectorSearchParams, pinned_empty, search)
+                     VectorSearchParams, from_bf16, pinned_empty, search, to_bf16)
 
 __all__ = ["FieldPostings", "StringIndexData", "TextQuery", "SearchHits", "MODE_FULLTEXT", "MODE_VECTOR",
            "MODE_HYBRID", "BM25_B", "BM25_K", "OcError", "build", "lib", "SO_PATH", "Context",
            "EmbeddingFieldStorage", "StringFieldStorage", "TextQueryBatch", "TokenScoreContext", "TokenScoreParams",
-           "VectorSearchParams", "pinned_empty", "search"]
+           "VectorSearchParams", "from_bf16", "pinned_empty", "search", "to_bf16"]

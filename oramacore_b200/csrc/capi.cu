@@ -125,7 +125,7 @@ struct oc_ctx {
     DevBuf seg, df_dev, row_ok, tau, cand_key, cand_ft, cand_cnt, tile_cnt, tile_max, tile_min, min_hint;
     DevBuf out_blob, shard_send, shard_recv;
     bool gemm_pending = false; const float *gemm_inv_norm = nullptr;
-    DevBuf pre_post, g_tau, g_cand, g_cnt, g_flag, g_max, r_qpad, r_qinv, r_map, r_doc, r_score, r_row, r_cnt, r_raw;
+    DevBuf q_bf16, pre_post, g_tau, g_cand, g_cnt, g_flag, g_max, r_qpad, r_qinv, r_map, r_doc, r_score, r_row, r_cnt, r_raw;
 
     HostBuf h_in, h_out;
     OcComm comm;
@@ -166,7 +166,7 @@ extern "C" void oc_shutdown(oc_ctx *c) {
     DevBuf *bufs[] = {&c->in_blob, &c->q_pad, &c->q_inv, &c->eff_norm, &c->filter_dev, &c->scan_cand, &c->v_doc,
                       &c->v_score, &c->v_row, &c->v_cnt, &c->v_srow, &c->v_ft, &c->v_present, &c->v_raw, &c->seg, &c->df_dev,
                       &c->row_ok, &c->tau, &c->cand_key, &c->cand_ft, &c->cand_cnt, &c->tile_cnt, &c->tile_max,
-                      &c->tile_min, &c->min_hint, &c->out_blob, &c->shard_send, &c->shard_recv, &c->pre_post, &c->g_tau, &c->g_cand, &c->g_cnt, &c->g_max,
+                      &c->tile_min, &c->min_hint, &c->out_blob, &c->shard_send, &c->shard_recv, &c->q_bf16, &c->pre_post, &c->g_tau, &c->g_cand, &c->g_cnt, &c->g_max,
                       &c->g_flag, &c->r_qpad, &c->r_qinv, &c->r_map, &c->r_doc, &c->r_score, &c->r_row, &c->r_cnt, &c->r_raw};
     for (DevBuf *b : bufs) b->release();
     c->h_in.release(); c->h_out.release();
@@ -217,7 +217,8 @@ struct oc_emb {
     oc_ctx *ctx;
     uint32_t dim, stride;
     int dtype, e5;
-    float *rows = nullptr;       // [cap][stride]
+    void *rows = nullptr;        // [cap][stride] fp32 or bf16
+    uint32_t esz = 4;            // element bytes
     float *inv_norm = nullptr;   // [cap] (NaN = tombstone)
     uint64_t *row_doc = nullptr; // [cap]
     uint64_t n_rows = 0, cap = 0, n_live = 0;
@@ -227,9 +228,10 @@ struct oc_emb {
 extern "C" int oc_emb_create(oc_ctx *c, uint32_t dim, int dtype, int rescale_e5, oc_emb **out) {
     if (!c || !out) return fail(OC_ERR_INVALID, "NULL argument");
     if (dim == 0 || dim > 1024) return fail(OC_ERR_UNSUPPORTED, "dim %u unsupported (1..1024)", dim);
-    if (dtype != OC_DTYPE_F32) return fail(OC_ERR_UNSUPPORTED, "dtype %d not built yet (f32 only)", dtype);
+    if (dtype != OC_DTYPE_F32 && dtype != OC_DTYPE_BF16) return fail(OC_ERR_UNSUPPORTED, "dtype %d unknown", dtype);
     oc_emb *e = new oc_emb();
     e->ctx = c; e->dim = dim; e->dtype = dtype; e->e5 = rescale_e5 ? 1 : 0;
+    e->esz = dtype == OC_DTYPE_BF16 ? 2 : 4;
     e->stride = ((dim + 127) / 128) * 128;
     if (e->stride / 128 == 5 || e->stride / 128 == 7) e->stride += 128;  // instantiated widths: 1,2,3,4,6,8
     *out = e;
@@ -249,12 +251,12 @@ static int emb_grow(oc_emb *e, uint64_t want_rows) {
     oc_ctx *c = e->ctx;
     uint64_t ncap = std::max<uint64_t>(want_rows, e->cap + e->cap / 2);
     ncap = (ncap + 63) / 64 * 64;
-    float *nr = nullptr, *nn = nullptr; uint64_t *nd = nullptr;
-    CU(cudaMalloc(&nr, ncap * e->stride * sizeof(float)));
+    void *nr = nullptr; float *nn = nullptr; uint64_t *nd = nullptr;
+    CU(cudaMalloc(&nr, ncap * e->stride * e->esz));
     CU(cudaMalloc(&nn, (ncap + 64) * sizeof(float)));
     CU(cudaMalloc(&nd, ncap * sizeof(uint64_t)));
     if (e->n_rows) {
-        CU(cudaMemcpyAsync(nr, e->rows, e->n_rows * e->stride * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+        CU(cudaMemcpyAsync(nr, e->rows, e->n_rows * e->stride * e->esz, cudaMemcpyDeviceToDevice, c->stream));
         CU(cudaMemcpyAsync(nn, e->inv_norm, e->n_rows * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
         CU(cudaMemcpyAsync(nd, e->row_doc, e->n_rows * sizeof(uint64_t), cudaMemcpyDeviceToDevice, c->stream));
     }
@@ -279,14 +281,15 @@ extern "C" int oc_emb_insert(oc_emb *e, const uint64_t *doc_ids, const void *row
     CU(cudaSetDevice(c->device));
     if (e->n_rows + n > 0xfffffff0ull) return fail(OC_ERR_UNSUPPORTED, "more than 2^32 rows per store");
     OCTRY(emb_grow(e, e->n_rows + n));
-    float *dst = e->rows + e->n_rows * e->stride;
-    if (e->stride != e->dim) CU(cudaMemsetAsync(dst, 0, n * e->stride * sizeof(float), c->stream));
-    CU(cudaMemcpy2DAsync(dst, e->stride * sizeof(float), rows, e->dim * sizeof(float), e->dim * sizeof(float), n,
+    uint8_t *dst = static_cast<uint8_t *>(e->rows) + e->n_rows * e->stride * e->esz;
+    if (e->stride != e->dim) CU(cudaMemsetAsync(dst, 0, n * e->stride * e->esz, c->stream));
+    CU(cudaMemcpy2DAsync(dst, size_t(e->stride) * e->esz, rows, size_t(e->dim) * e->esz, size_t(e->dim) * e->esz, n,
                          cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(e->row_doc + e->n_rows, doc_ids, n * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
     const uint64_t warps_per_block = 8;
     const uint64_t blocks = (n + warps_per_block - 1) / warps_per_block;
-    emb_inv_norm_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(e->rows, e->stride, e->n_rows, e->n_rows + n, e->inv_norm);
+    if (e->esz == 2) emb_inv_norm_kernel<bf16_t><<<(unsigned)blocks, 256, 0, c->stream>>>(e->rows, e->stride, e->n_rows, e->n_rows + n, e->inv_norm);
+    else emb_inv_norm_kernel<float><<<(unsigned)blocks, 256, 0, c->stream>>>(e->rows, e->stride, e->n_rows, e->n_rows + n, e->inv_norm);
     launched(c);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(c->stream));
@@ -325,34 +328,38 @@ extern "C" int oc_emb_delete(oc_emb *e, const uint64_t *doc_ids, uint64_t n) {
 extern "C" int oc_emb_info(oc_emb *e, oc_emb_info_t *out) {
     if (!e || !out) return fail(OC_ERR_INVALID, "NULL argument");
     out->num_embeddings = e->n_live; out->num_rows = e->n_rows; out->dimensions = e->dim; out->dtype = e->dtype;
-    out->device_bytes = e->cap * (uint64_t(e->stride) * 4 + 4 + 8);
+    out->device_bytes = e->cap * (uint64_t(e->stride) * e->esz + 4 + 8);
     return OC_OK;
 }
 
 // ---- scan launch plumbing
-template <int NCH, int QB>
+template <int NCH, int QB, typename T>
 static int launch_scan_t(oc_ctx *c, const ScanParams &sp, uint32_t grid, size_t smem) {
     static size_t configured = 0;  // per instantiation
     if (smem > configured) {
-        CU(cudaFuncSetAttribute(emb_scan_kernel<NCH, QB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(emb_scan_kernel<NCH, QB, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    emb_scan_kernel<NCH, QB><<<grid, SCAN_THREADS, smem, c->stream>>>(sp);
+    emb_scan_kernel<NCH, QB, T><<<grid, SCAN_THREADS, smem, c->stream>>>(sp);
     launched(c, true);
     CU(cudaGetLastError());
     return OC_OK;
 }
-template <int QB>
+template <int QB, typename T>
 static int launch_scan_q(oc_ctx *c, const ScanParams &sp, uint32_t grid, size_t smem) {
     switch (sp.stride / 128) {
-        case 1: return launch_scan_t<1, QB>(c, sp, grid, smem);
-        case 2: return launch_scan_t<2, QB>(c, sp, grid, smem);
-        case 3: return launch_scan_t<3, QB>(c, sp, grid, smem);
-        case 4: return launch_scan_t<4, QB>(c, sp, grid, smem);
-        case 6: return launch_scan_t<6, QB>(c, sp, grid, smem);
-        case 8: return launch_scan_t<8, QB>(c, sp, grid, smem);
+        case 1: return launch_scan_t<1, QB, T>(c, sp, grid, smem);
+        case 2: return launch_scan_t<2, QB, T>(c, sp, grid, smem);
+        case 3: return launch_scan_t<3, QB, T>(c, sp, grid, smem);
+        case 4: return launch_scan_t<4, QB, T>(c, sp, grid, smem);
+        case 6: return launch_scan_t<6, QB, T>(c, sp, grid, smem);
+        case 8: return launch_scan_t<8, QB, T>(c, sp, grid, smem);
     }
     return fail(OC_ERR_UNSUPPORTED, "stride %u not instantiated", sp.stride);
+}
+template <int QB>
+static int launch_scan_d(oc_ctx *c, const ScanParams &sp, uint32_t grid, size_t smem, uint32_t esz) {
+    return esz == 2 ? launch_scan_q<QB, bf16_t>(c, sp, grid, smem) : launch_scan_q<QB, float>(c, sp, grid, smem);
 }
 
 struct ScanPlan {
@@ -361,7 +368,7 @@ struct ScanPlan {
 static ScanPlan plan_scan(const oc_ctx *c, const oc_emb *e, uint32_t n_keep) {
     ScanPlan pl;
     uint32_t qb = 4;
-    const uint32_t row_bytes = e->stride * 4;
+    const uint32_t row_bytes = e->stride * e->esz;
     uint32_t R = (32768 / row_bytes) / 8 * 8;
     if (R < 8) R = 8;
     pl.rows_per_stage = R;
@@ -396,11 +403,11 @@ static int run_exact_sweeps(oc_ctx *c, oc_emb *e, const float *inv_norm, const f
         sp.n_keep = limit; sp.wcap = pl.wcap; sp.rows_per_stage = pl.rows_per_stage; sp.n_stages = pl.n_stages;
         sp.n_ctas_total = pl.grid;
         sp.cand = c->scan_cand.as<uint64_t>() + size_t(q0) * pl.grid * limit;
-        const size_t smem = scan_smem_bytes(e->stride, pl.rows_per_stage, pl.n_stages, pl.wcap, qb);
-        if (qb == 4) OCTRY((launch_scan_q<4>(c, sp, pl.grid, smem)));
-        else if (qb == 2) OCTRY((launch_scan_q<2>(c, sp, pl.grid, smem)));
-        else OCTRY((launch_scan_q<1>(c, sp, pl.grid, smem)));
-        c->timing.scan_bytes += e->n_rows * (uint64_t(e->stride) * 4 + 4);
+        const size_t smem = scan_smem_bytes(e->stride, pl.rows_per_stage, pl.n_stages, pl.wcap, qb, e->esz);
+        if (qb == 4) OCTRY((launch_scan_d<4>(c, sp, pl.grid, smem, e->esz)));
+        else if (qb == 2) OCTRY((launch_scan_d<2>(c, sp, pl.grid, smem, e->esz)));
+        else OCTRY((launch_scan_d<1>(c, sp, pl.grid, smem, e->esz)));
+        c->timing.scan_bytes += e->n_rows * (uint64_t(e->stride) * e->esz + 4);
         q0 += qb;
     }
     CU(cudaEventRecord(c->ev[EV_SCAN1], c->stream));
@@ -424,7 +431,7 @@ static int run_exact_sweeps(oc_ctx *c, oc_emb *e, const float *inv_norm, const f
 typedef CUresult (*EncodeTiled_t)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static int make_tmap_2d(CUtensorMap *m, const float *base, uint64_t n_rows, uint32_t stride, uint32_t box_rows) {
+static int make_tmap_2d(CUtensorMap *m, const void *base, uint64_t n_rows, uint32_t stride, uint32_t box_rows, bool bf16) {
     static EncodeTiled_t fn = nullptr;
     if (!fn) {
         void *f = nullptr;
@@ -434,10 +441,10 @@ static int make_tmap_2d(CUtensorMap *m, const float *base, uint64_t n_rows, uint
         fn = (EncodeTiled_t)f;
     }
     cuuint64_t dims[2] = {stride, n_rows};
-    cuuint64_t strides[1] = {cuuint64_t(stride) * 4};
-    cuuint32_t box[2] = {GEMM_KB, box_rows};
+    cuuint64_t strides[1] = {cuuint64_t(stride) * (bf16 ? 2 : 4)};
+    cuuint32_t box[2] = {bf16 ? 2 * GEMM_KB : GEMM_KB, box_rows};   // 128 bytes of K either way
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
+    CUresult r = fn(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(OC_ERR_CUDA, "cuTensorMapEncodeTiled failed: %d", (int)r);
@@ -493,8 +500,17 @@ static int run_vector_stage(oc_ctx *c, oc_emb *e, const float *q_dev, uint32_t B
     const uint32_t lists = NG == 1 ? cpg * 2 : cpg;
     const uint32_t Bpad2 = n_super * NG * GEMM_M;   // query rows the kernel may address (TMA zero-fills beyond the tensor)
     CUtensorMap tm_q, tm_x;
-    OCTRY(make_tmap_2d(&tm_q, c->q_pad.as<float>(), Bpad, e->stride, GEMM_M));
-    OCTRY(make_tmap_2d(&tm_x, e->rows, e->n_rows, e->stride, GEMM_N));
+    const bool bf16 = e->esz == 2;
+    const void *q_operand = c->q_pad.p;
+    if (bf16) {   // the sweep's query operand in the store's dtype (the exact re-score keeps the fp32 query)
+        OCTRY(c->q_bf16.ensure(size_t(Bpad) * e->stride * 2));
+        const size_t nq_el = size_t(Bpad) * e->stride;
+        f32_to_bf16_kernel<<<(unsigned)((nq_el + 255) / 256), 256, 0, c->stream>>>(c->q_pad.as<float>(), c->q_bf16.as<uint16_t>(), nq_el);
+        launched(c);
+        q_operand = c->q_bf16.p;
+    }
+    OCTRY(make_tmap_2d(&tm_q, q_operand, Bpad, e->stride, GEMM_M, bf16));
+    OCTRY(make_tmap_2d(&tm_x, e->rows, e->n_rows, e->stride, GEMM_N, bf16));
     OCTRY(c->g_tau.ensure(size_t(Bpad2) * 4));
     OCTRY(c->g_cand.ensure(size_t(Bpad2) * lists * cap * 8));
     OCTRY(c->g_cnt.ensure(size_t(Bpad2) * lists * 4));
@@ -502,19 +518,23 @@ static int run_vector_stage(oc_ctx *c, oc_emb *e, const float *q_dev, uint32_t B
     CU(cudaMemsetAsync(c->g_tau.p, 0, size_t(Bpad2) * 4, c->stream));
     OCTRY(c->g_max.ensure(size_t(Bpad2) * lists * 4));
     GemmParams gp{};
-    gp.n_rows = e->n_rows; gp.n_kblocks = e->stride / GEMM_KB; gp.inv_norm = inv_norm; gp.n_queries = B;
+    gp.n_rows = e->n_rows; gp.n_kblocks = e->stride / (bf16 ? 2 * GEMM_KB : GEMM_KB); gp.inv_norm = inv_norm; gp.n_queries = B;
     gp.n_qgroups = n_qgroups; gp.ctas_per_group = cpg; gp.keep = keep; gp.cap = cap; gp.lists_per_query = lists;
     gp.tau = c->g_tau.as<unsigned int>(); gp.cand = c->g_cand.as<uint64_t>(); gp.cand_cnt = c->g_cnt.as<uint32_t>();
     gp.gmax = c->g_max.as<float>();
     static bool gemm_cfg = false;
     if (!gemm_cfg) {
-        CU(cudaFuncSetAttribute(emb_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes(1)));
-        CU(cudaFuncSetAttribute(emb_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes(2)));
+        CU(cudaFuncSetAttribute(emb_gemm_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes(1)));
+        CU(cudaFuncSetAttribute(emb_gemm_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes(2)));
+        CU(cudaFuncSetAttribute(emb_gemm_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes(1)));
+        CU(cudaFuncSetAttribute(emb_gemm_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes(2)));
         gemm_cfg = true;
     }
     auto launch_gemm = [&]() -> int {
-        if (NG == 1) emb_gemm_kernel<1><<<grid, GEMM_THREADS, gemm_smem_bytes(1), c->stream>>>(tm_q, tm_x, gp);
-        else emb_gemm_kernel<2><<<grid, GEMM_THREADS, gemm_smem_bytes(2), c->stream>>>(tm_q, tm_x, gp);
+        if (NG == 1 && !bf16) emb_gemm_kernel<1, false><<<grid, GEMM_THREADS, gemm_smem_bytes(1), c->stream>>>(tm_q, tm_x, gp);
+        else if (NG == 1) emb_gemm_kernel<1, true><<<grid, GEMM_THREADS, gemm_smem_bytes(1), c->stream>>>(tm_q, tm_x, gp);
+        else if (!bf16) emb_gemm_kernel<2, false><<<grid, GEMM_THREADS, gemm_smem_bytes(2), c->stream>>>(tm_q, tm_x, gp);
+        else emb_gemm_kernel<2, true><<<grid, GEMM_THREADS, gemm_smem_bytes(2), c->stream>>>(tm_q, tm_x, gp);
         launched(c, gp.max_mode == 0);   // the one-tile threshold pass is not counted as a sweep
         CU(cudaGetLastError());
         return OC_OK;
@@ -527,11 +547,11 @@ static int run_vector_stage(oc_ctx *c, oc_emb *e, const float *q_dev, uint32_t B
     // the sweep
     gp.max_mode = 0; gp.tile_limit = 0;
     OCTRY(launch_gemm());
-    c->timing.scan_bytes += e->n_rows * (uint64_t(e->stride) * 4 + 4);
+    c->timing.scan_bytes += e->n_rows * (uint64_t(e->stride) * e->esz + 4);
     CU(cudaEventRecord(c->ev[EV_SCAN1], c->stream));
     GemmMergeParams mp{};
     mp.cand = gp.cand; mp.cand_cnt = gp.cand_cnt; mp.tau = gp.tau; mp.ctas_per_group = lists; mp.cap = cap; mp.keep = keep; mp.limit = limit;
-    mp.rows = e->rows; mp.stride = e->stride; mp.inv_norm = inv_norm; mp.queries = c->q_pad.as<float>();
+    mp.rows = e->rows; mp.rows_bf16 = bf16 ? 1 : 0; mp.stride = e->stride; mp.inv_norm = inv_norm; mp.queries = c->q_pad.as<float>();
     mp.inv_qnorm = c->q_inv.as<float>(); mp.row_doc_ids = e->row_doc; mp.rescale_e5 = e->e5; mp.similarity = similarity;
     mp.out_doc = out.doc; mp.out_score = out.score; mp.out_row = out.row; mp.out_count = out.cnt; mp.out_raw = out.raw;
     mp.out_unproven = c->g_flag.as<uint8_t>();

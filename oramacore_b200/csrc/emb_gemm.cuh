@@ -38,7 +38,7 @@ constexpr uint32_t GEMM_EPI_WARPS = 8;  // two warps per TMEM lane quadrant, eac
 constexpr int GEMM_THREADS = 64 + GEMM_EPI_WARPS * 32;   // warp0: TMA producer, warp1: MMA issuer, warps 2-9: epilogue
 constexpr uint32_t GEMM_M = 128;       // queries per CTA
 constexpr uint32_t GEMM_N = 256;       // rows per tile
-constexpr uint32_t GEMM_KB = 32;       // floats per K-block (128 B swizzle row)
+constexpr uint32_t GEMM_KB = 32;       // fp32 elements per K-block (one 128 B swizzle row); bf16 rows: 64
 constexpr uint32_t GEMM_STAGES = 4;
 constexpr uint32_t GEMM_A_BYTES = GEMM_M * 128;   // 16 KB
 constexpr uint32_t GEMM_B_BYTES = GEMM_N * 128;   // 32 KB
@@ -98,6 +98,16 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uin
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// same for bf16 operands (kind::f16, UMMA_K = 16 elements = 32 B)
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
 // start>>4 [0,14) | LBO>>4 [16,30) = 1 | SBO>>4 [32,46) = 1024/16 | version [46,48) = 1 | layout [61,64) = 2
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
@@ -108,6 +118,10 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 // instruction descriptor: D=f32 (1<<4), A=B=tf32 (2<<7, 2<<10), K-major both, N>>3 at [17,23), M>>4 at [24,29)
 __host__ __device__ constexpr uint32_t umma_idesc_tf32(uint32_t m, uint32_t n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+// D=f32, A=B=bf16 (format 1)
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t m, uint32_t n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
@@ -132,7 +146,7 @@ constexpr uint64_t TMA_EVICT_LAST = 0x14F0000000000000ull;
 //   NG=2: both groups consume the SAME staged X tile (one copy of X per CTA instead of one per
 //         group: L2->SM traffic per 256 rows x 256 queries drops from 96 KB to 64 KB per K-block),
 //         one accumulator per group (2 x 256 columns), 3 stages of 64 KB; every CTA is a row partition.
-template <int NG>
+template <int NG, bool BF16>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 emb_gemm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_x, const GemmParams p) {
     // SWIZZLE_128B tiles need 1024-byte alignment; every pointer below is derived from the
@@ -190,16 +204,16 @@ emb_gemm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                     mbar_expect_tx(&full[s], STAGE_BYTES);
 #pragma unroll
                     for (int gi = 0; gi < NG; gi++)   // rows past the padded query matrix are zero-filled by TMA
-                        tma_load_2d(a_dst + gi * GEMM_A_BYTES, &tm_q, &full[s], int32_t(kb * GEMM_KB),
+                        tma_load_2d(a_dst + gi * GEMM_A_BYTES, &tm_q, &full[s], int32_t(kb * (BF16 ? 2 * GEMM_KB : GEMM_KB)),
                                     int32_t((g0 + gi) * GEMM_M), TMA_EVICT_LAST);
-                    tma_load_2d(b_dst, &tm_x, &full[s], int32_t(kb * GEMM_KB), int32_t(row0), TMA_EVICT_FIRST);
+                    tma_load_2d(b_dst, &tm_x, &full[s], int32_t(kb * (BF16 ? 2 * GEMM_KB : GEMM_KB)), int32_t(row0), TMA_EVICT_FIRST);
                 }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (one thread) =====================
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc_tf32(GEMM_M, GEMM_N);
+            const uint32_t idesc = BF16 ? umma_idesc_bf16(GEMM_M, GEMM_N) : umma_idesc_tf32(GEMM_M, GEMM_N);
             uint64_t n = 0;
             for (uint64_t it = 0; it < my_tiles; it++) {
                 // accumulator slot and barrier phase: NG=1 alternates slots per tile; NG=2 uses slot = group every tile
@@ -217,8 +231,10 @@ emb_gemm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                         const uint32_t d_tmem = tmem_base + (NG == 1 ? slot1 : uint32_t(gi)) * GEMM_N;
                         const uint64_t adesc = umma_desc_sw128(a_addr + gi * GEMM_A_BYTES);
 #pragma unroll
-                        for (uint32_t k = 0; k < 4; k++)      // UMMA_K = 8 tf32 = 32 B: advance start address by 32 B
-                            tc_mma_tf32(d_tmem, adesc + k * 2, bdesc + k * 2, idesc, (kb | k) != 0);
+                        for (uint32_t k = 0; k < 4; k++) {    // UMMA_K = 8 tf32 / 16 bf16 = 32 B: advance start address by 32 B
+                            if (BF16) tc_mma_bf16(d_tmem, adesc + k * 2, bdesc + k * 2, idesc, (kb | k) != 0);
+                            else tc_mma_tf32(d_tmem, adesc + k * 2, bdesc + k * 2, idesc, (kb | k) != 0);
+                        }
                         if (NG == 2 && kb + 1 == nkb) tc_commit(&tfull[gi]);   // group gi's accumulator complete
                     }
                     tc_commit(&empty[s]);                  // frees the smem stage when these MMAs retire
@@ -331,8 +347,8 @@ struct GemmMergeParams {
     const uint64_t *cand; const uint32_t *cand_cnt;
     const unsigned int *tau;     // final per-query thresholds (ordered uint, 0 = never set)
     uint32_t ctas_per_group, cap, keep, limit;
-    const float *rows; uint32_t stride; const float *inv_norm;
-    const float *queries;        // [B][stride] padded
+    const void *rows; int rows_bf16; uint32_t stride; const float *inv_norm;
+    const float *queries;        // [B][stride] padded fp32 (exact re-score always uses the fp32 query)
     const float *inv_qnorm;      // [B]
     const uint64_t *row_doc_ids;
     int rescale_e5; float similarity;
@@ -392,12 +408,13 @@ __global__ void __launch_bounds__(512, 2) emb_gemm_merge_kernel(const GemmMergeP
     const float4 *qp = reinterpret_cast<const float4 *>(p.queries + size_t(q) * p.stride);
     for (uint32_t i = warp; i < got; i += blockDim.x / 32) {   // one warp per candidate (32 warps)
         const uint32_t row = key_idx(buf[i]);
-        const float4 *rp = reinterpret_cast<const float4 *>(p.rows + size_t(row) * p.stride);
+        const void *rp = static_cast<const uint8_t *>(p.rows) + size_t(row) * p.stride * (p.rows_bf16 ? 2 : 4);
         // all row loads are issued before the first use (the rows were streamed evict-first: DRAM latency)
         float4 xr[8];
         const uint32_t nch = p.stride / 128;   // <= 8
 #pragma unroll
-        for (uint32_t j = 0; j < 8; j++) if (j < nch) xr[j] = __ldg(rp + lane + 32 * j);
+        for (uint32_t j = 0; j < 8; j++)
+            if (j < nch) xr[j] = p.rows_bf16 ? RowLoad<bf16_t>::ld(rp, lane + 32 * j) : RowLoad<float>::ld(rp, lane + 32 * j);
         float acc = 0.f;
 #pragma unroll
         for (uint32_t j = 0; j < 8; j++)
@@ -459,6 +476,15 @@ __global__ void __launch_bounds__(256) gemm_tau_from_max_kernel(const float *gma
     }
     group_bitonic_desc(keys, np2, tid, blockDim.x, 0);
     if (tid == 0 && n >= keep && keys[keep - 1] != KEY_NONE) tau[q] = f32_ordered(key_score(keys[keep - 1]));
+}
+
+// fp32 -> bf16 (round to nearest even) of the padded queries: the B operand of the bf16 sweep
+__global__ void f32_to_bf16_kernel(const float *in, uint16_t *out, size_t n) {
+    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t u = __float_as_uint(in[i]);
+    const uint32_t r = ((u & 0x7fffffffu) > 0x7f800000u) ? (u | 0x00400000u) : (u + 0x7fffu + ((u >> 16) & 1u));
+    out[i] = uint16_t(r >> 16);
 }
 
 // copies the exact-path results of re-run queries into their slots of the batch outputs

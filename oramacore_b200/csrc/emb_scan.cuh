@@ -25,7 +25,7 @@ constexpr int SCAN_CONSUMER_WARPS = 8;
 constexpr int SCAN_THREADS = (SCAN_CONSUMER_WARPS + 1) * 32;  // + producer warp
 
 struct ScanParams {
-    const float *rows;        // [n_rows][stride]
+    const void *rows;         // [n_rows][stride] fp32 or bf16 (OC_DTYPE_*)
     const float *inv_norm;    // [n_rows] (NaN => skip row)
     uint64_t n_rows;
     uint32_t stride;          // floats, multiple of 128
@@ -40,21 +40,41 @@ struct ScanParams {
 };
 
 __host__ __device__ inline size_t scan_smem_bytes(uint32_t stride, uint32_t rows_per_stage,
-                                                  uint32_t n_stages, uint32_t wcap, uint32_t qb) {
-    size_t b = size_t(n_stages) * rows_per_stage * stride * 4;      // row ring
+                                                  uint32_t n_stages, uint32_t wcap, uint32_t qb, uint32_t esz = 4) {
+    size_t b = size_t(n_stages) * rows_per_stage * stride * esz;    // row ring
     b += size_t(n_stages) * rows_per_stage * 4;                     // inverse-norm ring
     b += size_t(n_stages) * 2 * 8;                                  // full/empty mbarriers
     b += size_t(SCAN_CONSUMER_WARPS) * qb * wcap * 8;               // warp top-k buffers
     return b + 128;
 }
 
-template <int NCH, int QB>
+// 4 consecutive elements of a row as fp32: fp32 rows -> one LDS/LDG.128; bf16 rows -> one 8-byte load,
+// widened exactly (bf16 -> fp32 is a 16-bit shift).
+template <typename T> struct RowLoad;
+template <> struct RowLoad<float> {
+    static constexpr uint32_t ESZ = 4;
+    __device__ static __forceinline__ float4 ld(const void *row, uint32_t chunk) {
+        return reinterpret_cast<const float4 *>(row)[chunk];
+    }
+};
+struct bf16_t { uint16_t v; };
+template <> struct RowLoad<bf16_t> {
+    static constexpr uint32_t ESZ = 2;
+    __device__ static __forceinline__ float4 ld(const void *row, uint32_t chunk) {
+        const uint2 r = reinterpret_cast<const uint2 *>(row)[chunk];
+        return make_float4(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u),
+                           __uint_as_float(r.y << 16), __uint_as_float(r.y & 0xffff0000u));
+    }
+};
+
+template <int NCH, int QB, typename T>
 __global__ void __launch_bounds__(SCAN_THREADS, 1) emb_scan_kernel(const ScanParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t stride = p.stride;
     const uint32_t R = p.rows_per_stage, S = p.n_stages;
-    float *ring = reinterpret_cast<float *>(smem);
-    float *nring = ring + size_t(S) * R * stride;
+    constexpr uint32_t ESZ = RowLoad<T>::ESZ;
+    uint8_t *ring = smem;
+    float *nring = reinterpret_cast<float *>(ring + size_t(S) * R * stride * ESZ);
     uint64_t *full = reinterpret_cast<uint64_t *>(nring + size_t(S) * R);
     uint64_t *empty = full + S;
     uint64_t *wbuf = empty + S;  // [QB][8 warps][wcap]
@@ -84,10 +104,11 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) emb_scan_kernel(const ScanPar
                 const uint64_t tile = blockIdx.x + it * gridDim.x;
                 const uint64_t row0 = tile * R;
                 const uint32_t nr = uint32_t(min(uint64_t(R), p.n_rows - row0));
-                const uint32_t bytes_rows = nr * stride * 4;
+                const uint32_t bytes_rows = nr * stride * ESZ;
                 const uint32_t bytes_norm = ((nr * 4 + 15) / 16) * 16;  // n_rows padded alloc
                 mbar_expect_tx(&full[s], bytes_rows + bytes_norm);
-                bulk_g2s_hint(ring + size_t(s) * R * stride, p.rows + row0 * stride, bytes_rows, &full[s], pol);
+                bulk_g2s_hint(ring + size_t(s) * R * stride * ESZ, static_cast<const uint8_t *>(p.rows) + row0 * stride * ESZ,
+                              bytes_rows, &full[s], pol);
                 bulk_g2s(nring + size_t(s) * R, p.inv_norm + row0, bytes_norm, &full[s]);
             }
         }
@@ -123,16 +144,16 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) emb_scan_kernel(const ScanPar
         const uint64_t row0 = tile * R;
         const uint32_t nr = uint32_t(min(uint64_t(R), p.n_rows - row0));
         mbar_wait(&full[s], ph);
-        const float *st = ring + size_t(s) * R * stride;
+        const uint8_t *st = ring + size_t(s) * R * stride * ESZ;
         const float *sn = nring + size_t(s) * R;
         for (uint32_t r = warp; r < nr; r += SCAN_CONSUMER_WARPS) {
-            const float4 *rp = reinterpret_cast<const float4 *>(st + size_t(r) * stride);
+            const void *rp = st + size_t(r) * stride * ESZ;
             float acc[QB];
 #pragma unroll
             for (int q = 0; q < QB; q++) acc[q] = 0.f;
 #pragma unroll
             for (int j = 0; j < NCH; j++) {
-                const float4 x = rp[lane + 32 * j];
+                const float4 x = RowLoad<T>::ld(rp, lane + 32 * j);
 #pragma unroll
                 for (int q = 0; q < QB; q++) {
                     acc[q] = fmaf(x.x, qv[q][j].x, acc[q]);
@@ -186,15 +207,16 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) emb_scan_kernel(const ScanPar
 // ---------------------------------------------------------------------------------------
 // Row preparation: inverse L2 norms of newly inserted rows (one warp per row).
 // ---------------------------------------------------------------------------------------
-__global__ void emb_inv_norm_kernel(const float *rows, uint32_t stride, uint64_t row_begin, uint64_t row_end,
+template <typename T>
+__global__ void emb_inv_norm_kernel(const void *rows, uint32_t stride, uint64_t row_begin, uint64_t row_end,
                                     float *inv_norm) {
     const uint64_t r = row_begin + (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) / 32;
     const uint32_t lane = threadIdx.x & 31;
     if (r >= row_end) return;
-    const float4 *rp = reinterpret_cast<const float4 *>(rows + r * stride);
+    const void *rp = static_cast<const uint8_t *>(rows) + r * stride * RowLoad<T>::ESZ;
     float s = 0.f;
     for (uint32_t j = lane; j < stride / 4; j += 32) {
-        const float4 x = rp[j];
+        const float4 x = RowLoad<T>::ld(rp, j);
         s = fmaf(x.x, x.x, s); s = fmaf(x.y, x.y, s); s = fmaf(x.z, x.z, s); s = fmaf(x.w, x.w, s);
     }
     s = warp_sum(s);

@@ -82,6 +82,18 @@ class Context:
         check(lib().oc_comm_init(self._h, world_size, rank, buf))
 
 
+def to_bf16(x: np.ndarray) -> np.ndarray:
+    """fp32 -> bf16 bit patterns (uint16), round to nearest even."""
+    u = np.ascontiguousarray(x, np.float32).view(np.uint32)
+    r = u + np.uint32(0x7fff) + ((u >> np.uint32(16)) & np.uint32(1))
+    return (r >> np.uint32(16)).astype(np.uint16)
+
+
+def from_bf16(b: np.ndarray) -> np.ndarray:
+    """bf16 bit patterns -> the fp32 values they denote (exact)."""
+    return (b.astype(np.uint32) << np.uint32(16)).view(np.float32)
+
+
 def pinned_empty(shape, dtype=np.float32) -> np.ndarray:
     """numpy array backed by page-locked host memory (oc_pinned_alloc): inputs placed here are DMA'd
     directly by oc_search. The memory is intentionally never freed before interpreter exit."""
@@ -105,12 +117,16 @@ class VectorSearchParams:
 class EmbeddingFieldStorage:
     """embedding_field.rs:29-34 — cosine metric, device resident."""
 
-    def __init__(self, ctx: Context, model: str = "BGEBase", dim: Optional[int] = None):
+    def __init__(self, ctx: Context, model: str = "BGEBase", dim: Optional[int] = None, dtype: str = "f32"):
+        """dtype "f32" (what the reference stores, embedding_field.rs:232) or "bf16" (storage extension:
+        rows are kept as bf16, scores are exact fp32 arithmetic on those values)."""
         self.ctx = ctx
         self.model = model
         self.dim = int(dim if dim is not None else MODEL_DIMS[model])
+        self.dtype = dtype
         self._h = C.c_void_p()
-        check(lib().oc_emb_create(ctx._h, self.dim, 0, 1 if model in E5_MODELS else 0, C.byref(self._h)))
+        check(lib().oc_emb_create(ctx._h, self.dim, {"f32": 0, "bf16": 1}[dtype], 1 if model in E5_MODELS else 0,
+                                  C.byref(self._h)))
 
     def close(self):
         if self._h:
@@ -127,7 +143,10 @@ class EmbeddingFieldStorage:
 
     def insert_batch(self, doc_ids: np.ndarray, rows: np.ndarray):
         d = np.ascontiguousarray(doc_ids, np.uint64)
-        r = np.ascontiguousarray(rows, np.float32)
+        if self.dtype == "bf16":   # fp32 input is rounded to bf16 (RNE); uint16 input is taken as bf16 bits
+            r = np.ascontiguousarray(rows) if rows.dtype == np.uint16 else to_bf16(rows)
+        else:
+            r = np.ascontiguousarray(rows, np.float32)
         assert r.ndim == 2 and r.shape[1] == self.dim and r.shape[0] == d.shape[0]
         check(lib().oc_emb_insert(self._h, _p(d), _p(r), d.shape[0]))
 

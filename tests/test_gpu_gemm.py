@@ -84,3 +84,32 @@ def test_gemm_equals_exact_sweep_bitwise(gpu_ctx):
         os.environ.pop("OC_DISABLE_GEMM", None)
     assert np.array_equal(d1, d2) and np.array_equal(s1, s2) and np.array_equal(c1, c2)
     emb.close()
+
+
+@pytest.mark.parametrize("n,dim,model,B", [(30000, 1024, "BGELarge", 5), (30000, 1024, "BGELarge", 200),
+                                            (50000, 768, "BGEBase", 64), (20000, 384, "BGESmall", 130)])
+def test_bf16_store_parity(gpu_ctx, orc, n, dim, model, B):
+    """OC_DTYPE_BF16 store (BASELINE configs[4] shape, reduced): rows are bf16 values; every score is
+    exact fp32 arithmetic on those values, so the oracle runs on the bf16-rounded rows."""
+    rows = ob.from_bf16(ob.to_bf16(synth.make_vectors(n, dim, seed=n + dim)))
+    qv, planted = synth.make_vector_queries(rows, B, seed=n + 1)
+    emb = ob.EmbeddingFieldStorage(gpu_ctx, model, dtype="bf16")
+    emb.insert_batch(np.arange(n, dtype=np.uint64), rows)
+    assert emb.info()["device_bytes"] < n * dim * 2 * 1.7
+    st = orc.EmbStore(rows)
+    docs, scores, counts = emb.search_batch(qv, 10, -1.0)
+    t = gpu_ctx.last_timing()
+    assert t["scan_tensor_core"] == (1 if B >= 8 else 0)
+    assert np.all(docs[:, 0] == planted)
+    for i in list(range(0, B, max(1, B // 12))):
+        ed, es = orc.vector(st, qv[i], 10, -1.0)
+        order = np.argsort(-es, kind="stable")
+        assert_topk_equal(docs[i, :counts[i]], scores[i, :counts[i]], ed[order], es[order], atol=1e-5)
+    if B >= 8:   # tensor-core path == exact sweep, bit for bit
+        os.environ["OC_DISABLE_GEMM"] = "1"
+        try:
+            d2, s2, c2 = emb.search_batch(qv, 10, -1.0)
+        finally:
+            os.environ.pop("OC_DISABLE_GEMM", None)
+        assert np.array_equal(docs, d2) and np.array_equal(scores, s2)
+    emb.close()
