@@ -37,6 +37,8 @@ WORKLOADS = {
                desc="1M x 768-d fp32 embeddings, cosine top-10, batch=1 (BASELINE configs[1])"),
     "t1": dict(mode="fulltext", n_docs=10_000_000, dim=0, vocab=1_000_000, batch=256,
                desc="BM25 fulltext, 10M synthetic docs (Zipf), batch=256 (BASELINE configs[2])"),
+    "v2": dict(mode="vector", n_docs=10_000_000, dim=1024, vocab=0, batch=1024, dtype="bf16",
+               desc="10M x 1024-d bf16 embeddings, cosine top-10, batch=1024 (BASELINE configs[4])"),
 }
 
 
@@ -100,7 +102,13 @@ def make_workload(w, n_docs, batch, rank, world):
     from oramacore_b200 import synth
     lo, hi = (n_docs * rank) // world, (n_docs * (rank + 1)) // world
     out = dict(lo=lo, hi=hi)
-    if w["dim"]:
+    if w["dim"] and w.get("dtype") == "bf16":
+        # too large to hold in fp32 on the host: rows are generated chunk by chunk at load time (see main);
+        # queries are planted on rows of the first chunk
+        first = synth.make_vectors(min(n_docs, 1 << 18), w["dim"])
+        qv, planted = synth.make_vector_queries(first, batch)
+        out.update(rows=None, qv=qv, planted=planted, chunked=True)
+    elif w["dim"]:
         rows = synth.make_vectors(n_docs, w["dim"])          # deterministic: every rank draws the same stream
         qv, planted = synth.make_vector_queries(rows, batch)
         out.update(rows=rows[lo:hi], rows_all=rows if world == 1 else None, qv=qv, planted=planted)
@@ -197,11 +205,23 @@ def main():
     lo, hi = wl["lo"], wl["hi"]
     emb = strs = None
     if w["dim"]:
-        emb = ob.EmbeddingFieldStorage(ctx, dim=w["dim"], model="BGEBase" if w["dim"] == 768 else "BGELarge")
+        emb = ob.EmbeddingFieldStorage(ctx, dim=w["dim"], model="BGEBase" if w["dim"] == 768 else "BGELarge",
+                                       dtype=w.get("dtype", "f32"))
         emb.reserve(hi - lo)
         ids = np.arange(lo, hi, dtype=np.uint64)
-        for i in range(0, hi - lo, 1 << 18):
-            emb.insert_batch(ids[i:i + (1 << 18)], wl["rows"][i:i + (1 << 18)])
+        if wl.get("chunked"):
+            from oramacore_b200 import synth
+            CH = 1 << 18
+            for c0 in range(0, n_docs, CH):        # chunk c uses seed SEED+c (chunk 0 == the planted chunk)
+                c1 = min(n_docs, c0 + CH)
+                a, b = max(c0, lo), min(c1, hi)
+                if a >= b:
+                    continue
+                chunk = synth.make_vectors(c1 - c0, w["dim"], seed=synth.SEED_VECTORS + (c0 // CH) * (c0 > 0))
+                emb.insert_batch(np.arange(a, b, dtype=np.uint64), chunk[a - c0:b - c0])
+        else:
+            for i in range(0, hi - lo, 1 << 18):
+                emb.insert_batch(ids[i:i + (1 << 18)], wl["rows"][i:i + (1 << 18)])
     if w["vocab"]:
         if world == 1:
             strs = ob.StringFieldStorage(ctx, wl["data_all"])
@@ -276,7 +296,7 @@ def main():
         "metric": "hybrid_search_qps_at_recall10_ge_0.99_1Mx768" if args.workload == "h1" else f"{w['mode']}_search_qps",
         "value": value, "unit": "queries/s", "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
         "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
+        "dtype": "bf16 storage, f32 arithmetic" if w.get("dtype") == "bf16" else "f32", "data": "synthetic",
         "config": {"workload": w["desc"], "batch": B, "n_docs": n_docs, "dim": w["dim"], "vocab": w["vocab"],
                    "limit": 10, "similarity": 0.0, "parallelism": f"doc-shard x{world}",
                    "l2_flush": "inputs larger than L2 (matrix >> 126 MB)"},
@@ -293,9 +313,18 @@ def main():
         traffic = json.load(open(tpath)).get(args.workload)
     if w["dim"] and scan_ms >= bm_ms:
         ach = (scan_bytes / 1e9) / (scan_ms * 1e-3)
-        line["scan"] = {"kernel": "emb_gemm_kernel (tcgen05 kind::tf32 + exact fp32 re-score)" if tensor_core else "emb_scan_kernel (exact fp32 sweep)",
+        n_local = hi - lo
+        tflops = (2.0 * B * n_local * w["dim"] / 1e12) / (scan_ms / K * 1e-3) if tensor_core else None
+        kind = "kind::f16 (bf16 rows)" if w.get("dtype") == "bf16" else "kind::tf32 (fp32 rows)"
+        line["scan"] = {"kernel": f"emb_gemm_kernel (tcgen05 {kind} + exact fp32 re-score)" if tensor_core else "emb_scan_kernel (exact fp32 sweep)",
                         "unproven_queries_rerun_exact_per_step": unproven / K,
-                        "tf32_tflops": (2.0 * B * n_docs * w["dim"] * scan_launches / max(scan_launches, 1) / 1e12) / (scan_ms / K * 1e-3) if tensor_core else None}
+                        "tensor_tflops_per_gpu": tflops}
+        pk_json = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+        if tensor_core and w.get("dtype") == "bf16" and B >= 512:
+            tpeak = float(pk_json.get("bf16_tflops_sustained", 1400.0))
+            line["roofline_tensor"] = {"kernel": "emb_gemm_kernel", "bound": "tensor", "achieved": tflops, "peak": tpeak,
+                                       "unit": "TFLOP/s", "frac": tflops / tpeak,
+                                       "peak_source": "of measured (sustained)" if pk_json else "of fallback"}
         line["roofline"] = {"kernel": "emb_gemm_kernel" if tensor_core else "emb_scan_kernel", "bound": "hbm", "achieved": ach, "peak": peak,
                             "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "peak_source": f"of {peak_src}",
                             "launches_per_step": scan_launches / K,
@@ -308,7 +337,11 @@ def main():
                             "postings_per_s": postings / (bm_ms * 1e-3)}
 
     # ---- parity / recall of the timed configuration + CPU baseline (outside the timed region)
-    if not args.no_cpu_baseline:
+    if wl.get("chunked"):
+        hits_planted = sum(int(h.doc_ids[0]) == int(pj) for h, pj in zip(hits, wl["planted"])) if rank == 0 else 0
+        line["parity"] = {"planted_neighbour_is_rank1": hits_planted, "queries": B,
+                          "note": "corpus generated chunk-wise (41 GB in fp32): no host copy for the CPU oracle; parity of this path is covered by tests/test_gpu_gemm.py::test_bf16_store_parity"}
+    elif not args.no_cpu_baseline:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import oracle as orc
         orc.build()
