@@ -431,7 +431,9 @@ static int run_exact_sweeps(oc_ctx *c, oc_emb *e, const float *inv_norm, const f
 typedef CUresult (*EncodeTiled_t)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static int make_tmap_2d(CUtensorMap *m, const void *base, uint64_t n_rows, uint32_t stride, uint32_t box_rows, bool bf16) {
+// sw64: bf16 matrix, 32-element (64-byte) boxes in the SWIZZLE_64B layout (operand of the converting sweep)
+static int make_tmap_2d(CUtensorMap *m, const void *base, uint64_t n_rows, uint32_t stride, uint32_t box_rows, bool bf16,
+                        bool sw64 = false) {
     static EncodeTiled_t fn = nullptr;
     if (!fn) {
         void *f = nullptr;
@@ -442,10 +444,10 @@ static int make_tmap_2d(CUtensorMap *m, const void *base, uint64_t n_rows, uint3
     }
     cuuint64_t dims[2] = {stride, n_rows};
     cuuint64_t strides[1] = {cuuint64_t(stride) * (bf16 ? 2 : 4)};
-    cuuint32_t box[2] = {bf16 ? 2 * GEMM_KB : GEMM_KB, box_rows};   // 128 bytes of K either way
+    cuuint32_t box[2] = {(bf16 && !sw64) ? 2 * GEMM_KB : GEMM_KB, box_rows};   // 128 bytes of K (64 when sw64)
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(OC_ERR_CUDA, "cuTensorMapEncodeTiled failed: %d", (int)r);
     return OC_OK;
@@ -491,26 +493,36 @@ static int run_vector_stage(oc_ctx *c, oc_emb *e, const float *q_dev, uint32_t B
     if (!use_gemm) return run_exact_sweeps(c, e, inv_norm, c->q_pad.as<float>(), c->q_inv.as<float>(), B, limit, similarity, out);
 
     // ---------------- K2: tcgen05 tf32 batched scan ----------------
-    const uint32_t keep = limit <= 16 ? 32 : 64, cap = 128;   // cap == warp sort scratch; compress when > 96
+    const bool bf16 = e->esz == 2;
     // NG = 2: one CTA serves two query groups against each staged X tile (one copy of X per 256 queries)
     const int NG = n_qgroups >= 2 ? 2 : 1;
     const uint32_t n_super = NG == 1 ? n_qgroups : (n_qgroups + 1) / 2;
-    const uint32_t cpg = std::max<uint32_t>(1, c->prop.multiProcessorCount / n_super);
-    const uint32_t grid = cpg * n_super;
-    const uint32_t lists = NG == 1 ? cpg * 2 : cpg;
+    // CTA pairs (cta_group::2): two SMs share one 256-query x 512-row tile (25 % less L2->SM traffic)
+    const char *penv = getenv("OC_GEMM_PAIR");
+    const uint32_t n_pairs = c->prop.multiProcessorCount / 2;
+    const bool pair = NG == 2 && !(penv && penv[0] == '0') && n_pairs >= n_super;
+    const uint32_t cpg = pair ? std::max<uint32_t>(1, n_pairs / n_super)
+                              : std::max<uint32_t>(1, c->prop.multiProcessorCount / n_super);
+    const uint32_t grid = pair ? 2 * cpg * n_super : cpg * n_super;
+    const uint32_t lists = (NG == 1 || pair) ? cpg * 2 : cpg;
+    // fp32 store, pair path: convert the operands to bf16 inside the SM (kind::f16 at twice the tf32 rate)
+    const char *cenv = getenv("OC_GEMM_CVT");
+    const bool cvt = pair && !bf16 && !(cenv && cenv[0] == '0');
+    // K' candidates re-scored per query: the proof needs cos_limit - (K'-th approx) >= eps, so the wider
+    // eps of the bf16-rounded operands takes the deeper candidate list
+    const uint32_t keep = limit > 16 ? 64 : (cvt ? 48 : 32), cap = 128;   // cap == warp sort scratch; compress when > 96
     const uint32_t Bpad2 = n_super * NG * GEMM_M;   // query rows the kernel may address (TMA zero-fills beyond the tensor)
     CUtensorMap tm_q, tm_x;
-    const bool bf16 = e->esz == 2;
     const void *q_operand = c->q_pad.p;
-    if (bf16) {   // the sweep's query operand in the store's dtype (the exact re-score keeps the fp32 query)
+    if (bf16 || cvt) {   // the sweep's query operand in the store's dtype (the exact re-score keeps the fp32 query)
         OCTRY(c->q_bf16.ensure(size_t(Bpad) * e->stride * 2));
         const size_t nq_el = size_t(Bpad) * e->stride;
         f32_to_bf16_kernel<<<(unsigned)((nq_el + 255) / 256), 256, 0, c->stream>>>(c->q_pad.as<float>(), c->q_bf16.as<uint16_t>(), nq_el);
         launched(c);
         q_operand = c->q_bf16.p;
     }
-    OCTRY(make_tmap_2d(&tm_q, q_operand, Bpad, e->stride, GEMM_M, bf16));
-    OCTRY(make_tmap_2d(&tm_x, e->rows, e->n_rows, e->stride, GEMM_N, bf16));
+    OCTRY(make_tmap_2d(&tm_q, q_operand, Bpad, e->stride, GEMM_M, bf16 || cvt, cvt));
+    OCTRY(make_tmap_2d(&tm_x, e->rows, e->n_rows, e->stride, pair ? 128 : GEMM_N, bf16));
     OCTRY(c->g_tau.ensure(size_t(Bpad2) * 4));
     OCTRY(c->g_cand.ensure(size_t(Bpad2) * lists * cap * 8));
     OCTRY(c->g_cnt.ensure(size_t(Bpad2) * lists * 4));
@@ -518,7 +530,7 @@ static int run_vector_stage(oc_ctx *c, oc_emb *e, const float *q_dev, uint32_t B
     CU(cudaMemsetAsync(c->g_tau.p, 0, size_t(Bpad2) * 4, c->stream));
     OCTRY(c->g_max.ensure(size_t(Bpad2) * lists * 4));
     GemmParams gp{};
-    gp.n_rows = e->n_rows; gp.n_kblocks = e->stride / (bf16 ? 2 * GEMM_KB : GEMM_KB); gp.inv_norm = inv_norm; gp.n_queries = B;
+    gp.n_rows = e->n_rows; gp.n_kblocks = e->stride / (bf16 ? 2 * GEMM_KB : GEMM_KB); gp.inv_norm = inv_norm; gp.n_queries = B;   // cvt: 32-element K-blocks too
     gp.n_qgroups = n_qgroups; gp.ctas_per_group = cpg; gp.keep = keep; gp.cap = cap; gp.lists_per_query = lists;
     gp.tau = c->g_tau.as<unsigned int>(); gp.cand = c->g_cand.as<uint64_t>(); gp.cand_cnt = c->g_cnt.as<uint32_t>();
     gp.gmax = c->g_max.as<float>();
@@ -528,10 +540,16 @@ static int run_vector_stage(oc_ctx *c, oc_emb *e, const float *q_dev, uint32_t B
         CU(cudaFuncSetAttribute(emb_gemm_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes(2)));
         CU(cudaFuncSetAttribute(emb_gemm_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes(1)));
         CU(cudaFuncSetAttribute(emb_gemm_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes(2)));
+        CU(cudaFuncSetAttribute(emb_gemm_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_pair_smem_bytes()));
+        CU(cudaFuncSetAttribute(emb_gemm_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_pair_smem_bytes()));
+        CU(cudaFuncSetAttribute(emb_gemm_cvt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_cvt_smem_bytes()));
         gemm_cfg = true;
     }
     auto launch_gemm = [&]() -> int {
-        if (NG == 1 && !bf16) emb_gemm_kernel<1, false><<<grid, GEMM_THREADS, gemm_smem_bytes(1), c->stream>>>(tm_q, tm_x, gp);
+        if (cvt) emb_gemm_cvt_kernel<<<grid, CVT_THREADS, gemm_cvt_smem_bytes(), c->stream>>>(tm_q, tm_x, gp);
+        else if (pair && !bf16) emb_gemm_pair_kernel<false><<<grid, GEMM_THREADS, gemm_pair_smem_bytes(), c->stream>>>(tm_q, tm_x, gp);
+        else if (pair) emb_gemm_pair_kernel<true><<<grid, GEMM_THREADS, gemm_pair_smem_bytes(), c->stream>>>(tm_q, tm_x, gp);
+        else if (NG == 1 && !bf16) emb_gemm_kernel<1, false><<<grid, GEMM_THREADS, gemm_smem_bytes(1), c->stream>>>(tm_q, tm_x, gp);
         else if (NG == 1) emb_gemm_kernel<1, true><<<grid, GEMM_THREADS, gemm_smem_bytes(1), c->stream>>>(tm_q, tm_x, gp);
         else if (!bf16) emb_gemm_kernel<2, false><<<grid, GEMM_THREADS, gemm_smem_bytes(2), c->stream>>>(tm_q, tm_x, gp);
         else emb_gemm_kernel<2, true><<<grid, GEMM_THREADS, gemm_smem_bytes(2), c->stream>>>(tm_q, tm_x, gp);
@@ -555,7 +573,8 @@ static int run_vector_stage(oc_ctx *c, oc_emb *e, const float *q_dev, uint32_t B
     mp.inv_qnorm = c->q_inv.as<float>(); mp.row_doc_ids = e->row_doc; mp.rescale_e5 = e->e5; mp.similarity = similarity;
     mp.out_doc = out.doc; mp.out_score = out.score; mp.out_row = out.row; mp.out_count = out.cnt; mp.out_raw = out.raw;
     mp.out_unproven = c->g_flag.as<uint8_t>();
-    emb_gemm_merge_kernel<<<B, 512, (2048 + 64) * 8, c->stream>>>(mp);
+    mp.eps = cvt ? GEMM_EPS_BF16X2 : GEMM_EPS_TF32;
+    emb_gemm_merge_kernel<<<B, 512, (GEMM_MERGE_BUF + 64) * 8, c->stream>>>(mp);
     launched(c);
     CU(cudaGetLastError());
     // the proof flags travel back with the results; oc_*search re-runs flagged queries (fix_unproven)
@@ -1287,7 +1306,7 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
     fp.out_doc = reinterpret_cast<uint64_t *>(dout + o_doc); fp.out_score = reinterpret_cast<float *>(dout + o_sc);
     fp.out_n = reinterpret_cast<uint32_t *>(dout + o_n); fp.out_count = reinterpret_cast<unsigned long long *>(dout + o_cnt);
     fp.out_min = reinterpret_cast<float *>(dout + o_min);
-    fuse_smem = size_t(fp.capb) * 8 + size_t(vlimit) * 8 + 64;
+    fuse_smem = size_t(fp.capb) * 8 + size_t(std::max<uint32_t>(32, next_pow2(n_keep))) * 8 + size_t(vlimit) * 8 + 64;
     static size_t fuse_cfg = 0;
     if (fuse_smem > fuse_cfg) { CU(cudaFuncSetAttribute(fuse_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fuse_smem)); fuse_cfg = fuse_smem; }
 

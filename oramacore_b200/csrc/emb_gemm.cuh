@@ -44,6 +44,7 @@ constexpr uint32_t GEMM_A_BYTES = GEMM_M * 128;   // 16 KB
 constexpr uint32_t GEMM_B_BYTES = GEMM_N * 128;   // 32 KB
 constexpr uint32_t GEMM_STAGE_BYTES = GEMM_A_BYTES + GEMM_B_BYTES;
 constexpr uint32_t GEMM_MAX_KEEP = 64;            // K' upper bound (candidate buffer = 2 K')
+constexpr uint32_t GEMM_MERGE_BUF = 4096;         // keys the merge kernel sorts in shared memory
 constexpr float GEMM_EPS_TF32 = 2.1e-3f;          // rigorous |approx - exact| bound on the cosine
 
 struct GemmParams {
@@ -78,6 +79,13 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, u
         " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(dst)),
         "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(hint)
         : "memory");
+}
+// pulls a tile HBM -> L2 ahead of its TMA load (no shared memory, no barrier): the ring then only has to
+// cover L2 latency, not HBM latency
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap *map, int32_t c0, int32_t c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)),
+                 "r"(c0), "r"(c1)
+                 : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
@@ -341,6 +349,541 @@ emb_gemm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 }
 
 // ---------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2): the two SMs of a TPC run ONE 256-query x 512-row tile.
+// CTA r of the pair stages ITS 128 queries (A half) and ITS 128 rows of each of two 256-row B
+// tiles; the leader's MMAs (M = 256, N = 256) read both CTAs' shared memory, the accumulators
+// of CTA r hold queries [128r, 128r+128) x 512 rows (all 512 TMEM columns of both SMs).  Per
+// K-block a pair moves 32 KB of Q + 64 KB of X for 256 x 512 scores — 25 % less L2->SM traffic
+// than two independent NG=2 CTAs (2 x (32 + 32) KB), which is what bounds the fp32 sweep.
+// ---------------------------------------------------------------------------------------
+constexpr uint32_t PAIR_STAGES = 4;
+constexpr uint32_t PAIR_HALF_B = 128 * 128;                       // 128 rows x 128 B
+constexpr uint32_t PAIR_STAGE_BYTES = GEMM_A_BYTES + 2 * PAIR_HALF_B;   // 48 KB per CTA
+constexpr uint32_t PAIR_TILE_ROWS = 512;
+
+__host__ __device__ inline size_t gemm_pair_smem_bytes() {
+    return 1024 + size_t(PAIR_STAGES) * PAIR_STAGE_BYTES + 2 * PAIR_TILE_ROWS * 4 + GEMM_EPI_WARPS * 128 * 8 + 256;
+}
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    // default semantics (release at CTA scope): a cluster-scope release costs a MEMBAR.ALL.GPU per arrive;
+    // the data this orders is consumed by tcgen05 / the async proxy, which the tcgen05 / proxy fences cover
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+}
+// TMA load issued by either CTA of the pair; the transaction bytes land on the LEADER's barrier
+__device__ __forceinline__ void tma_load_2d_pair(void *dst, const CUtensorMap *map, uint32_t leader_bar, int32_t c0, int32_t c1,
+                                                 uint64_t hint) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1), "l"(hint)
+        : "memory");
+}
+// arrives on the barrier at this offset in BOTH CTAs once all previously issued MMAs have retired
+__device__ __forceinline__ void tc_commit_pair(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(uint16_t(3))
+                 : "memory");
+}
+template <bool BF16>
+__device__ __forceinline__ void tc_mma_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    const uint32_t z = 0;
+    if (BF16)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}" ::"r"(d_tmem),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(z)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}" ::"r"(d_tmem),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(z)
+            : "memory");
+}
+
+template <bool BF16>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+emb_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_x, const GemmParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_gemm[];
+    uint8_t *ring = smem_gemm;
+    float *inr_s = reinterpret_cast<float *>(smem_gemm + PAIR_STAGES * PAIR_STAGE_BYTES);   // [2][512]
+    uint64_t *scratch = reinterpret_cast<uint64_t *>(inr_s + 2 * PAIR_TILE_ROWS);            // [8 warps][128]
+    uint64_t *bars = scratch + GEMM_EPI_WARPS * 128;
+    uint64_t *full = bars, *empty = bars + PAIR_STAGES;       // full: used in the leader only
+    uint64_t *tfull = bars + 2 * PAIR_STAGES, *tempty = tfull + 2;   // tempty: used in the leader only
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const uint32_t cid = blockIdx.x >> 1;
+    const uint32_t n_super = (p.n_qgroups + 1) / 2;
+    const uint32_t grp = (cid % n_super) * 2 + rank;   // this CTA's query group (A half of the pair's M = 256)
+    const uint32_t c = cid / n_super;                  // the pair's row partition
+    const uint64_t n_tiles = (p.n_rows + PAIR_TILE_ROWS - 1) / PAIR_TILE_ROWS;
+    uint64_t my_tiles = (n_tiles > c) ? (n_tiles - c + p.ctas_per_group - 1) / p.ctas_per_group : 0;
+    if (p.tile_limit && my_tiles > p.tile_limit) my_tiles = p.tile_limit;
+    const uint32_t nkb = p.n_kblocks;
+    constexpr int32_t KSTEP = BF16 ? 2 * GEMM_KB : GEMM_KB;
+
+    if (threadIdx.x == 0) {
+        for (uint32_t s = 0; s < PAIR_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (uint32_t a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }   // 4 epilogue warps x 2 CTAs
+        fence_mbar_init();
+        tma_prefetch_desc(&tm_q);
+        tma_prefetch_desc(&tm_x);
+    }
+    if (warp == 1) {   // all 512 TMEM columns of both SMs
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();   // the peer's barriers are initialised before any remote arrive / multicast commit
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs) =====================
+        if (lane == 0) {
+            uint64_t n = 0;
+            for (uint64_t it = 0; it < my_tiles; it++) {
+                const uint64_t row0 = (c + it * p.ctas_per_group) * PAIR_TILE_ROWS;
+                for (uint32_t kb = 0; kb < nkb; kb++, n++) {
+                    const uint32_t s = uint32_t(n % PAIR_STAGES), ph = uint32_t((n / PAIR_STAGES) & 1);
+                    mbar_wait(&empty[s], ph ^ 1);
+                    const uint32_t lbar = mapa_shared(smem_u32(&full[s]), 0);
+                    if (rank == 0) mbar_expect_tx(&full[s], 2 * PAIR_STAGE_BYTES);   // both CTAs' bytes
+                    uint8_t *a_dst = ring + s * PAIR_STAGE_BYTES;
+                    tma_load_2d_pair(a_dst, &tm_q, lbar, int32_t(kb) * KSTEP, int32_t(grp * GEMM_M), TMA_EVICT_LAST);
+#pragma unroll
+                    for (uint32_t j = 0; j < 2; j++)
+                        tma_load_2d_pair(a_dst + GEMM_A_BYTES + j * PAIR_HALF_B, &tm_x, lbar, int32_t(kb) * KSTEP,
+                                         int32_t(row0 + j * 256 + rank * 128), TMA_EVICT_FIRST);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one thread of the leader CTA) =====================
+        if (rank == 0 && lane == 0) {
+            const uint32_t idesc = BF16 ? umma_idesc_bf16(256, 256) : umma_idesc_tf32(256, 256);
+            uint64_t n = 0;
+            for (uint64_t it = 0; it < my_tiles; it++) {
+                const uint32_t ph2 = uint32_t(it & 1);
+                for (uint32_t kb = 0; kb < nkb; kb++, n++) {
+                    const uint32_t s = uint32_t(n % PAIR_STAGES), ph = uint32_t((n / PAIR_STAGES) & 1);
+                    mbar_wait_cluster(&full[s], ph);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(ring + s * PAIR_STAGE_BYTES);
+                    const uint64_t adesc = umma_desc_sw128(a_addr);
+#pragma unroll
+                    for (uint32_t j = 0; j < 2; j++) {
+                        if (kb == 0) { mbar_wait_cluster(&tempty[j], ph2 ^ 1); tc_fence_after(); }   // both CTAs drained D_j
+                        const uint64_t bdesc = umma_desc_sw128(a_addr + GEMM_A_BYTES + j * PAIR_HALF_B);
+#pragma unroll
+                        for (uint32_t k = 0; k < 4; k++)
+                            tc_mma_pair<BF16>(tmem_base + j * 256, adesc + k * 2, bdesc + k * 2, idesc, (kb | k) != 0);
+                        if (kb + 1 == nkb) tc_commit_pair(&tfull[j]);
+                    }
+                    tc_commit_pair(&empty[s]);   // frees this stage in both CTAs
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================== epilogue (both CTAs): thread = TMEM lane = one query =====================
+        const uint32_t ew = warp - 2, quad = warp & 3, sel = ew >> 2;   // sel = accumulator = 256-row half of the tile
+        const uint32_t m = quad * 32 + lane;
+        const uint32_t q = grp * GEMM_M + m;
+        const bool live = q < p.n_queries;
+        const uint32_t et = ew * 32 + lane;
+        const uint32_t lists = p.lists_per_query;
+        const uint32_t my_list = c * 2 + sel;
+        uint64_t *__restrict__ mybuf = p.cand + (size_t(q) * lists + my_list) * p.cap;
+        uint64_t *wscr = scratch + ew * 128;
+        const uint32_t tempty_remote = mapa_shared(smem_u32(&tempty[sel]), 0);
+        uint32_t cnt = 0;
+        float tau = live ? -INFINITY : INFINITY;
+        float best = -INFINITY;
+        for (uint64_t it = 0; it < my_tiles; it++) {
+            const uint32_t ph = uint32_t(it & 1);
+            const uint64_t row0 = (c + it * p.ctas_per_group) * PAIR_TILE_ROWS;
+            float *inr = inr_s + uint32_t(it & 1) * PAIR_TILE_ROWS;
+#pragma unroll
+            for (uint32_t h = 0; h < 2; h++) {
+                const uint64_t r = row0 + et + h * 256;
+                inr[et + h * 256] = r < p.n_rows ? __ldg(p.inv_norm + r) : __int_as_float(0x7fc00000);
+            }
+            if (live) {
+                const unsigned int tg = *reinterpret_cast<volatile unsigned int *>(p.tau + q);
+                if (tg) tau = fmaxf(tau, f32_unordered(tg));
+            }
+            named_bar_sync(1, GEMM_EPI_WARPS * 32);
+            mbar_wait(&tfull[sel], ph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((quad * 32u) << 16) + sel * 256;
+            const float4 *inr4 = reinterpret_cast<const float4 *>(inr + sel * 256);
+            const uint32_t rbase = uint32_t(row0) + sel * 256;
+            for (uint32_t ch = 0; ch < 8; ch++) {
+                uint32_t d[32];
+                tmem_ld32(taddr + ch * 32, d);
+                tmem_ld_wait();
+                float v[32];
+                uint32_t mask = 0;
+#pragma unroll
+                for (uint32_t j4 = 0; j4 < 8; j4++) {
+                    const float4 w = inr4[ch * 8 + j4];
+                    v[4 * j4 + 0] = __uint_as_float(d[4 * j4 + 0]) * w.x;
+                    v[4 * j4 + 1] = __uint_as_float(d[4 * j4 + 1]) * w.y;
+                    v[4 * j4 + 2] = __uint_as_float(d[4 * j4 + 2]) * w.z;
+                    v[4 * j4 + 3] = __uint_as_float(d[4 * j4 + 3]) * w.w;
+                }
+                if (p.max_mode) {
+#pragma unroll
+                    for (uint32_t j = 0; j < 32; j++) best = fmaxf(best, v[j]);
+                    continue;
+                }
+#pragma unroll
+                for (uint32_t j = 0; j < 32; j++) mask |= (v[j] > tau ? 1u : 0u) << j;
+                if (mask) {
+#pragma unroll
+                    for (uint32_t j = 0; j < 32; j++)
+                        if ((mask >> j) & 1u) { mybuf[cnt] = make_key(v[j], rbase + ch * 32 + j); cnt++; }
+                }
+                uint32_t need = __ballot_sync(0xffffffffu, cnt + 32 > p.cap);
+                while (need) {
+                    const uint32_t l = __ffs(need) - 1;
+                    need &= need - 1;
+                    const uint32_t lq = grp * GEMM_M + quad * 32 + l;
+                    uint64_t *lbuf = p.cand + (size_t(lq) * lists + my_list) * p.cap;
+                    const uint32_t lcnt = __shfl_sync(0xffffffffu, cnt, l);
+                    __syncwarp();
+                    for (uint32_t i = lane; i < 128; i += 32) wscr[i] = i < lcnt ? lbuf[i] : KEY_NONE;
+                    warp_bitonic_desc(wscr, 128, lane);
+                    for (uint32_t i = lane; i < p.keep; i += 32) lbuf[i] = wscr[i];
+                    __syncwarp();
+                    if (lane == l) {
+                        cnt = p.keep;
+                        tau = fmaxf(tau, key_score(wscr[p.keep - 1]));
+                        atomicMax(p.tau + q, f32_ordered(tau));
+                    }
+                    __syncwarp();
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(tempty_remote);   // one arrival per warp on the leader's barrier
+        }
+        if (p.max_mode) p.gmax[size_t(q) * lists + my_list] = live ? best : -INFINITY;
+        else if (grp < p.n_qgroups) p.cand_cnt[size_t(q) * lists + my_list] = live ? cnt : 0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();   // no CTA leaves (or frees TMEM) while its peer can still touch its smem / barriers
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// CTA-pair variant with IN-SM fp32 -> bf16 operand conversion (fp32 stores, B > 128).
+// At B = 256 the tf32 sweep is co-limited by the tensor pipe (tf32 runs at half the bf16 rate:
+// 2*256*n*d flop is ~0.54 ms of tf32 at the sustained rate vs 0.47 ms of HBM time).  Here the
+// fp32 rows still stream from HBM exactly once (TMA, 128-byte swizzle), four converter warps
+// round them to bf16 (cvt.rn) into a second ring laid out as the K-major SWIZZLE_64B UMMA
+// operand, and the MMAs run as kind::f16 at twice the tf32 rate, so the sweep is bound by HBM
+// alone.  Q is converted once per batch (f32_to_bf16_kernel) and arrives by TMA (SWIZZLE_64B).
+// Selection only: the merge re-scores in exact fp32; the proof uses eps = GEMM_EPS_BF16X2.
+//   per CTA: 5 stages x (32 KB fp32 X tile, converted IN PLACE into its first 16 KB, + 8 KB bf16 Q):
+//   a stage cycles TMA -> convert -> MMA -> free, so ~3 stages (96 KB) are in flight from HBM per SM.
+// ---------------------------------------------------------------------------------------
+constexpr uint32_t CVT_STAGES = 5;
+constexpr uint32_t CVT_PREFETCH = 0;                     // K-blocks (32 KB per CTA each) prefetched into L2 ahead of the ring
+constexpr uint32_t CVT_RAW_BYTES = 256 * 128;             // 256 rows x 32 fp32
+constexpr uint32_t CVT_XOP_BYTES = 256 * 64;              // 256 rows x 32 bf16 (two 128-row B tiles of 8 KB)
+constexpr uint32_t CVT_QOP_BYTES = 128 * 64;              // 128 queries x 32 bf16
+constexpr uint32_t CVT_STAGE_BYTES = CVT_RAW_BYTES + CVT_QOP_BYTES;   // 40 KB
+constexpr uint32_t CVT_WARPS = 4;
+constexpr int CVT_THREADS = GEMM_THREADS + CVT_WARPS * 32;   // warps 10-13 convert
+constexpr float GEMM_EPS_BF16X2 = 4.1e-3f;                // both operands rounded to bf16: 2*2^-9 + accumulation
+
+__host__ __device__ inline size_t gemm_cvt_smem_bytes() {
+    return 1024 + size_t(CVT_STAGES) * CVT_STAGE_BYTES + 2 * PAIR_TILE_ROWS * 4 + GEMM_EPI_WARPS * 128 * 8 + 256;
+}
+// K-major SWIZZLE_64B descriptor: 64-byte rows, 8-row groups 512 B apart
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
+    const uint32_t lo = ((smem_addr >> 4) & 0x3fffu) | (1u << 16);
+    const uint32_t hi = 32u | (1u << 14) | (4u << 29);
+    return (uint64_t(hi) << 32) | lo;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2_rn(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));   // first source -> upper half
+    return r;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CVT_THREADS, 1)
+emb_gemm_cvt_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_x, const GemmParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_gemm[];
+    // stage: [0, 32 KB) fp32 X as landed ([2 tiles][128 rows][128 B], SW128) -> after conversion
+    //        [0, 16 KB) bf16 X ([2 tiles][128 rows][64 B], SW64); [32 KB, 40 KB) bf16 Q ([128][64 B], SW64)
+    uint8_t *ring = smem_gemm;
+    float *inr_s = reinterpret_cast<float *>(ring + CVT_STAGES * CVT_STAGE_BYTES);
+    uint64_t *scratch = reinterpret_cast<uint64_t *>(inr_s + 2 * PAIR_TILE_ROWS);
+    uint64_t *bars = scratch + GEMM_EPI_WARPS * 128;
+    uint64_t *raw_full = bars;                         // X tile landed (this CTA)
+    uint64_t *op_full = raw_full + CVT_STAGES;         // leader only: both CTAs converted + both Q tiles landed
+    uint64_t *empty = op_full + CVT_STAGES;            // MMAs that read the stage retired (multicast to both CTAs)
+    uint64_t *tfull = empty + CVT_STAGES, *tempty = tfull + 2;   // tempty: leader only
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const uint32_t cid = blockIdx.x >> 1;
+    const uint32_t n_super = (p.n_qgroups + 1) / 2;
+    const uint32_t grp = (cid % n_super) * 2 + rank;
+    const uint32_t c = cid / n_super;
+    const uint64_t n_tiles = (p.n_rows + PAIR_TILE_ROWS - 1) / PAIR_TILE_ROWS;
+    uint64_t my_tiles = (n_tiles > c) ? (n_tiles - c + p.ctas_per_group - 1) / p.ctas_per_group : 0;
+    if (p.tile_limit && my_tiles > p.tile_limit) my_tiles = p.tile_limit;
+    const uint32_t nkb = p.n_kblocks;   // K-blocks of 32 elements
+    const uint64_t n_blocks = my_tiles * nkb;
+
+    if (threadIdx.x == 0) {
+        for (uint32_t s = 0; s < CVT_STAGES; s++) {
+            mbar_init(&raw_full[s], 1);
+            mbar_init(&op_full[s], 1 + 2 * CVT_WARPS);   // leader's expect_tx arrive + one arrive per converter warp of both CTAs
+            mbar_init(&empty[s], 1);
+        }
+        for (uint32_t a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
+        fence_mbar_init();
+        tma_prefetch_desc(&tm_q);
+        tma_prefetch_desc(&tm_x);
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs): fp32 X tile + bf16 Q tile per stage =====================
+        if (lane == 0) {
+            uint64_t it = 0; uint32_t kb = 0;
+            uint64_t pit = 0; uint32_t pkb = 0; uint64_t pn = 0;   // L2 prefetch cursor, CVT_PREFETCH K-blocks ahead
+            for (uint64_t n = 0; n < n_blocks; n++) {
+                for (; pn < n_blocks && pn < n + CVT_PREFETCH; pn++) {
+                    const uint64_t prow0 = (c + pit * p.ctas_per_group) * PAIR_TILE_ROWS;
+#pragma unroll
+                    for (uint32_t j = 0; j < 2; j++)
+                        tma_prefetch_l2_2d(&tm_x, int32_t(pkb * GEMM_KB), int32_t(prow0 + j * 256 + rank * 128));
+                    if (++pkb == nkb) { pkb = 0; pit++; }
+                }
+                const uint64_t row0 = (c + it * p.ctas_per_group) * PAIR_TILE_ROWS;
+                const uint32_t s = uint32_t(n % CVT_STAGES), ph = uint32_t((n / CVT_STAGES) & 1);
+                mbar_wait(&empty[s], ph ^ 1);
+                uint8_t *st = ring + s * CVT_STAGE_BYTES;
+                mbar_expect_tx(&raw_full[s], CVT_RAW_BYTES);
+#pragma unroll
+                for (uint32_t j = 0; j < 2; j++)
+                    tma_load_2d(st + j * PAIR_HALF_B, &tm_x, &raw_full[s], int32_t(kb * GEMM_KB), int32_t(row0 + j * 256 + rank * 128),
+                                TMA_EVICT_FIRST);
+                if (rank == 0) mbar_expect_tx(&op_full[s], 2 * CVT_QOP_BYTES);
+                tma_load_2d_pair(st + CVT_RAW_BYTES, &tm_q, mapa_shared(smem_u32(&op_full[s]), 0), int32_t(kb * GEMM_KB),
+                                 int32_t(grp * GEMM_M), TMA_EVICT_LAST);
+                if (++kb == nkb) { kb = 0; it++; }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader) =====================
+        if (rank == 0 && lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(256, 256);
+            uint64_t it = 0; uint32_t kb = 0;
+            for (uint64_t n = 0; n < n_blocks; n++) {
+                const uint32_t ph2 = uint32_t(it & 1);
+                const uint32_t s = uint32_t(n % CVT_STAGES), ph = uint32_t((n / CVT_STAGES) & 1);
+                mbar_wait_cluster(&op_full[s], ph);
+                tc_fence_after();
+                const uint32_t x_addr = smem_u32(ring + s * CVT_STAGE_BYTES);
+                const uint64_t adesc = umma_desc_sw64(x_addr + CVT_RAW_BYTES);
+#pragma unroll
+                for (uint32_t j = 0; j < 2; j++) {
+                    if (kb == 0) { mbar_wait_cluster(&tempty[j], ph2 ^ 1); tc_fence_after(); }
+                    const uint64_t bdesc = umma_desc_sw64(x_addr + j * (CVT_XOP_BYTES / 2));
+#pragma unroll
+                    for (uint32_t k = 0; k < 2; k++)   // UMMA_K = 16 bf16 = 32 B
+                        tc_mma_pair<true>(tmem_base + j * 256, adesc + k * 2, bdesc + k * 2, idesc, (kb | k) != 0);
+                    if (kb + 1 == nkb) tc_commit_pair(&tfull[j]);
+                }
+                tc_commit_pair(&empty[s]);
+                if (++kb == nkb) { kb = 0; it++; }
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 2 + GEMM_EPI_WARPS) {
+        // ===================== converters (both CTAs): fp32 SW128 tile -> bf16 SW64 operand, in place =====================
+        const uint32_t t = threadIdx.x - (2 + GEMM_EPI_WARPS) * 32;   // 0..127
+        const uint32_t op_full_leader0 = mapa_shared(smem_u32(&op_full[0]), 0);
+        for (uint64_t n = 0; n < n_blocks; n++) {
+            const uint32_t s = uint32_t(n % CVT_STAGES), ph = uint32_t((n / CVT_STAGES) & 1);
+            uint8_t *st = ring + s * CVT_STAGE_BYTES;
+            mbar_wait(&raw_full[s], ph);
+            uint4 w[8];
+#pragma unroll
+            for (uint32_t i = 0; i < 8; i++) {
+                const uint32_t o = t + 128 * i;            // output 16-byte chunk: row = o / 4, chunk = o % 4
+                const uint32_t r = o >> 2, oc = o & 3;     // r in [0,256): B tile r / 128, row r % 128 (tiles are contiguous)
+                const uint8_t *rs = st + r * 128;
+                const uint32_t x7 = r & 7;
+                const float4 a = *reinterpret_cast<const float4 *>(rs + (((2 * oc) ^ x7) << 4));
+                const float4 b = *reinterpret_cast<const float4 *>(rs + (((2 * oc + 1) ^ x7) << 4));
+                w[i].x = pack_bf16x2_rn(a.x, a.y); w[i].y = pack_bf16x2_rn(a.z, a.w);
+                w[i].z = pack_bf16x2_rn(b.x, b.y); w[i].w = pack_bf16x2_rn(b.z, b.w);
+            }
+            named_bar_sync(2, CVT_WARPS * 32);   // every fp32 value is in registers before the tile is overwritten
+#pragma unroll
+            for (uint32_t i = 0; i < 8; i++) {
+                const uint32_t o = t + 128 * i;
+                const uint32_t r = o >> 2, oc = o & 3;
+                *reinterpret_cast<uint4 *>(st + r * 64 + ((oc ^ ((r >> 1) & 3)) << 4)) = w[i];
+            }
+            fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's async-proxy reads
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(op_full_leader0 + s * 8);
+        }
+    } else {
+        // ===================== epilogue (both CTAs): thread = TMEM lane = one query =====================
+        const uint32_t ew = warp - 2, quad = warp & 3, sel = ew >> 2;
+        const uint32_t m = quad * 32 + lane;
+        const uint32_t q = grp * GEMM_M + m;
+        const bool live = q < p.n_queries;
+        const uint32_t et = ew * 32 + lane;
+        const uint32_t lists = p.lists_per_query;
+        const uint32_t my_list = c * 2 + sel;
+        uint64_t *__restrict__ mybuf = p.cand + (size_t(q) * lists + my_list) * p.cap;
+        uint64_t *wscr = scratch + ew * 128;
+        const uint32_t tempty_remote = mapa_shared(smem_u32(&tempty[sel]), 0);
+        uint32_t cnt = 0;
+        float tau = live ? -INFINITY : INFINITY;
+        float best = -INFINITY;
+        for (uint64_t it = 0; it < my_tiles; it++) {
+            const uint32_t ph = uint32_t(it & 1);
+            const uint64_t row0 = (c + it * p.ctas_per_group) * PAIR_TILE_ROWS;
+            float *inr = inr_s + uint32_t(it & 1) * PAIR_TILE_ROWS;
+#pragma unroll
+            for (uint32_t h = 0; h < 2; h++) {
+                const uint64_t r = row0 + et + h * 256;
+                inr[et + h * 256] = r < p.n_rows ? __ldg(p.inv_norm + r) : __int_as_float(0x7fc00000);
+            }
+            if (live) {
+                const unsigned int tg = *reinterpret_cast<volatile unsigned int *>(p.tau + q);
+                if (tg) tau = fmaxf(tau, f32_unordered(tg));
+            }
+            named_bar_sync(1, GEMM_EPI_WARPS * 32);
+            mbar_wait(&tfull[sel], ph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((quad * 32u) << 16) + sel * 256;
+            const float4 *inr4 = reinterpret_cast<const float4 *>(inr + sel * 256);
+            const uint32_t rbase = uint32_t(row0) + sel * 256;
+            for (uint32_t ch = 0; ch < 8; ch++) {
+                uint32_t d[32];
+                tmem_ld32(taddr + ch * 32, d);
+                tmem_ld_wait();
+                float v[32];
+                uint32_t mask = 0;
+#pragma unroll
+                for (uint32_t j4 = 0; j4 < 8; j4++) {
+                    const float4 w = inr4[ch * 8 + j4];
+                    v[4 * j4 + 0] = __uint_as_float(d[4 * j4 + 0]) * w.x;
+                    v[4 * j4 + 1] = __uint_as_float(d[4 * j4 + 1]) * w.y;
+                    v[4 * j4 + 2] = __uint_as_float(d[4 * j4 + 2]) * w.z;
+                    v[4 * j4 + 3] = __uint_as_float(d[4 * j4 + 3]) * w.w;
+                }
+                if (p.max_mode) {
+#pragma unroll
+                    for (uint32_t j = 0; j < 32; j++) best = fmaxf(best, v[j]);
+                    continue;
+                }
+#pragma unroll
+                for (uint32_t j = 0; j < 32; j++) mask |= (v[j] > tau ? 1u : 0u) << j;
+                if (mask) {
+#pragma unroll
+                    for (uint32_t j = 0; j < 32; j++)
+                        if ((mask >> j) & 1u) { mybuf[cnt] = make_key(v[j], rbase + ch * 32 + j); cnt++; }
+                }
+                uint32_t need = __ballot_sync(0xffffffffu, cnt + 32 > p.cap);
+                while (need) {
+                    const uint32_t l = __ffs(need) - 1;
+                    need &= need - 1;
+                    const uint32_t lq = grp * GEMM_M + quad * 32 + l;
+                    uint64_t *lbuf = p.cand + (size_t(lq) * lists + my_list) * p.cap;
+                    const uint32_t lcnt = __shfl_sync(0xffffffffu, cnt, l);
+                    __syncwarp();
+                    for (uint32_t i = lane; i < 128; i += 32) wscr[i] = i < lcnt ? lbuf[i] : KEY_NONE;
+                    warp_bitonic_desc(wscr, 128, lane);
+                    for (uint32_t i = lane; i < p.keep; i += 32) lbuf[i] = wscr[i];
+                    __syncwarp();
+                    if (lane == l) {
+                        cnt = p.keep;
+                        tau = fmaxf(tau, key_score(wscr[p.keep - 1]));
+                        atomicMax(p.tau + q, f32_ordered(tau));
+                    }
+                    __syncwarp();
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(tempty_remote);
+        }
+        if (p.max_mode) p.gmax[size_t(q) * lists + my_list] = live ? best : -INFINITY;
+        else if (grp < p.n_qgroups) p.cand_cnt[size_t(q) * lists + my_list] = live ? cnt : 0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Merge: best K' candidates by tf32 score -> exact fp32 re-score (K1 arithmetic) -> proof.
 // ---------------------------------------------------------------------------------------
 struct GemmMergeParams {
@@ -354,12 +897,13 @@ struct GemmMergeParams {
     int rescale_e5; float similarity;
     uint64_t *out_doc; float *out_score; uint32_t *out_row; uint32_t *out_count; float *out_raw;
     uint8_t *out_unproven;       // [B] 1 => host must re-run this query through the exact sweep
+    float eps;                   // rigorous |approx - exact| bound on the cosine for the sweep's arithmetic
 };
 
 __global__ void __launch_bounds__(512, 2) emb_gemm_merge_kernel(const GemmMergeParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
-    uint64_t *buf = reinterpret_cast<uint64_t *>(smem);          // [2048]
-    uint64_t *exact = buf + 2048;                                 // [64]
+    uint64_t *buf = reinterpret_cast<uint64_t *>(smem);          // [GEMM_MERGE_BUF]
+    uint64_t *exact = buf + GEMM_MERGE_BUF;                       // [64]
     __shared__ uint32_t s_cnt;
     const uint32_t q = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint64_t total = uint64_t(p.ctas_per_group) * p.cap;
@@ -378,18 +922,30 @@ __global__ void __launch_bounds__(512, 2) emb_gemm_merge_kernel(const GemmMergeP
         s_valid = p.ctas_per_group <= 512 ? acc : 0xffffffffu;
     }
     __syncthreads();
-    if (s_valid <= 2048u) {
+    if (s_valid <= GEMM_MERGE_BUF) {
         const uint32_t nv = s_valid;
         const uint32_t np2 = max(64u, next_pow2(nv));
         for (uint32_t l = tid; l < p.ctas_per_group; l += blockDim.x) {
             const uint32_t c = min(cnts[l], p.cap), o = s_off[l];
             for (uint32_t k = 0; k < c; k++) buf[o + k] = src[size_t(l) * p.cap + k];
         }
-        for (uint32_t i = nv + tid; i < np2; i += blockDim.x) buf[i] = KEY_NONE;
-        group_bitonic_desc(buf, np2, tid, blockDim.x, 0);
+        if (nv <= 256u) {   // few candidates (warm thresholds): sort them all
+            for (uint32_t i = nv + tid; i < np2; i += blockDim.x) buf[i] = KEY_NONE;
+            group_bitonic_desc(buf, np2, tid, blockDim.x, 0);
+        } else {
+            // radix select of the keep largest keys, then a one-warp sort of those
+            uint64_t *sel = exact;   // [64] scratch, re-initialised below
+            for (uint32_t i = tid; i < 64; i += blockDim.x) sel[i] = KEY_NONE;
+            __syncthreads();
+            block_select_largest(buf, nv, p.keep, sel);
+            if (warp == 0) warp_bitonic_desc(sel, 64, lane);
+            __syncthreads();
+            for (uint32_t i = tid; i < 64; i += blockDim.x) buf[i] = sel[i];
+            __syncthreads();
+        }
         got = min(nv, p.keep);
     } else {
-        got = block_topn_stream(buf, 2048, p.keep, total, [&](uint64_t i) -> uint64_t {
+        got = block_topn_stream(buf, GEMM_MERGE_BUF, p.keep, total, [&](uint64_t i) -> uint64_t {
             const uint32_t cta = uint32_t(i / p.cap), k = uint32_t(i % p.cap);
             return k < cnts[cta] ? src[i] : KEY_NONE;
         });
@@ -436,7 +992,7 @@ __global__ void __launch_bounds__(512, 2) emb_gemm_merge_kernel(const GemmMergeP
     bool proven = bound_v == -INFINITY;
     if (!proven && n_top == p.limit) {
         const float c_lim = 1.0f + key_score(exact[p.limit - 1]);   // cos = 1 - distance
-        proven = c_lim >= bound_v * iqn + GEMM_EPS_TF32;
+        proven = c_lim >= bound_v * iqn + p.eps;
     }
     for (uint32_t i = tid; i < p.limit; i += blockDim.x) {
         uint64_t doc = 0; float score = 0.f, raw = 0.f; uint32_t row = 0xffffffffu;

@@ -61,7 +61,8 @@ constexpr uint32_t FUSE_MAX_V = OC_MAX_TOPK;
 __global__ void __launch_bounds__(256) fuse_topk_kernel(const FuseParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint64_t *buf = reinterpret_cast<uint64_t *>(smem);               // [capb]
-    float *vsum = reinterpret_cast<float *>(buf + p.capb);            // [v_stride] merged vector score
+    uint64_t *sel = buf + p.capb;                                     // [next_pow2(n_keep)] selection scratch
+    float *vsum = reinterpret_cast<float *>(sel + max(32u, next_pow2(p.n_keep)));   // [v_stride] merged vector score
     uint32_t *vfirst = reinterpret_cast<uint32_t *>(vsum + p.v_stride); // [v_stride] 1 = unique head
     __shared__ unsigned int s_maxo, s_mino;
     __shared__ unsigned long long s_count;
@@ -187,8 +188,19 @@ __global__ void __launch_bounds__(256) fuse_topk_kernel(const FuseParams p) {
                 }
             for (uint32_t j = tid; j < vc; j += blockDim.x) buf[n_valid_ft + j] = load(n_ft_slots + j);
             const uint32_t np2 = max(32u, next_pow2(n_all));
-            for (uint32_t i = n_all + tid; i < np2; i += blockDim.x) buf[i] = KEY_NONE;
-            group_bitonic_desc(buf, np2, tid, blockDim.x, 0);
+            const uint32_t kp2 = max(32u, next_pow2(p.n_keep));
+            if (np2 > 2 * kp2) {
+                // many more candidates than needed: radix-select the n_keep best, sort only those
+                for (uint32_t i = tid; i < kp2; i += blockDim.x) sel[i] = KEY_NONE;
+                __syncthreads();
+                block_select_largest(buf, n_all, p.n_keep, sel);
+                group_bitonic_desc(sel, kp2, tid, blockDim.x, 0);
+                for (uint32_t i = tid; i < kp2; i += blockDim.x) buf[i] = sel[i];
+                __syncthreads();
+            } else {
+                for (uint32_t i = n_all + tid; i < np2; i += blockDim.x) buf[i] = KEY_NONE;
+                group_bitonic_desc(buf, np2, tid, blockDim.x, 0);
+            }
             uint32_t real = min(n_all, p.n_keep);
             __shared__ uint32_t s_real2;
             if (tid == 0) { while (real > 0 && buf[real - 1] == KEY_NONE) real--; s_real2 = real; }

@@ -149,6 +149,91 @@ __device__ __forceinline__ void bulk_g2s_hint(void *dst_smem, const void *src_gm
         : "memory");
 }
 
+// ---------------------------------------------------------------------------------------
+// Block-wide selection of the `keep` largest non-zero (non KEY_NONE) keys of buf[0, nv) into
+// out[0, returned count) — UNSORTED; the caller sorts the (small) result.  Non-zero keys must be
+// unique (rank keys carry the row index).  Radix select, most significant differing byte first,
+// 8 bits per pass, one warp-aggregated shared atomic per distinct bin per warp; stops as soon as
+// the boundary bin is taken whole.  O(nv) per pass instead of the O(nv log^2 nv) of a full sort.
+// All threads of the block must call it (blockDim.x a multiple of 32); out must not alias buf.
+// ---------------------------------------------------------------------------------------
+__device__ inline uint32_t block_select_largest(const uint64_t *buf, uint32_t nv, uint32_t keep, uint64_t *out) {
+    __shared__ uint32_t sl_hist[256];
+    __shared__ unsigned long long sl_or, sl_and, sl_prefix;
+    __shared__ uint32_t sl_need, sl_done, sl_n, sl_nz;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { sl_or = 0ull; sl_and = ~0ull; sl_n = 0; sl_nz = 0; }
+    __syncthreads();
+    {
+        uint64_t o = 0, a = ~0ull; uint32_t nz = 0;
+        for (uint32_t i = tid; i < nv; i += blockDim.x) { const uint64_t k = buf[i]; if (k) { o |= k; a &= k; nz++; } }
+        const uint32_t ol = __reduce_or_sync(0xffffffffu, uint32_t(o)), oh = __reduce_or_sync(0xffffffffu, uint32_t(o >> 32));
+        const uint32_t al = __reduce_and_sync(0xffffffffu, uint32_t(a)), ah = __reduce_and_sync(0xffffffffu, uint32_t(a >> 32));
+        nz = __reduce_add_sync(0xffffffffu, nz);
+        if (lane == 0 && nz) { atomicOr(&sl_or, (uint64_t(oh) << 32) | ol); atomicAnd(&sl_and, (uint64_t(ah) << 32) | al); atomicAdd(&sl_nz, nz); }
+    }
+    __syncthreads();
+    const uint32_t nz = sl_nz;
+    if (nz <= keep) {   // everything valid is kept
+        for (uint32_t i = tid; i < nv; i += blockDim.x) { const uint64_t k = buf[i]; if (k) out[atomicAdd(&sl_n, 1u)] = k; }
+        __syncthreads();
+        return nz;
+    }
+    const uint64_t diff = sl_or ^ sl_and;   // bits on which the keys disagree (non-zero: nz >= 2 unique keys)
+    int shift = ((63 - __clzll((long long)(diff | 1ull))) >> 3) << 3;
+    uint64_t prefix = shift == 56 ? 0ull : (sl_and >> (shift + 8)) << (shift + 8);
+    uint32_t need = keep;
+    for (; shift >= 0; shift -= 8) {
+        for (uint32_t i = tid; i < 256; i += blockDim.x) sl_hist[i] = 0;
+        __syncthreads();
+        for (uint32_t i0 = 0; i0 < nv; i0 += blockDim.x) {   // block-uniform trip count: match_any needs converged lanes
+            const uint32_t i = i0 + tid;
+            const uint64_t k = i < nv ? buf[i] : 0ull;
+            const bool in = k != 0ull && (shift == 56 || (k >> (shift + 8)) == (prefix >> (shift + 8)));
+            const uint32_t bin = in ? (uint32_t(k >> shift) & 255u) : 256u;
+            const uint32_t peers = __match_any_sync(0xffffffffu, bin);
+            if (in && lane == uint32_t(__ffs(peers) - 1)) atomicAdd(&sl_hist[bin], uint32_t(__popc(peers)));
+        }
+        __syncthreads();
+        if (warp == 0) {   // lane l owns bins [255 - 8l - 7, 255 - 8l], walked from the top
+            uint32_t mine = 0;
+#pragma unroll
+            for (uint32_t j = 0; j < 8; j++) mine += sl_hist[255 - 8 * lane - j];
+            uint32_t above = mine;   // inclusive prefix over lanes (lane 0 = highest bins)
+#pragma unroll
+            for (uint32_t o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, above, o);
+                if (lane >= o) above += v;
+            }
+            above -= mine;           // keys in bins above this lane's range
+            if (above < need && above + mine >= need) {
+                uint32_t cum = above;
+                for (uint32_t j = 0; j < 8; j++) {
+                    const uint32_t b = 255 - 8 * lane - j, h = sl_hist[b];
+                    if (cum + h >= need) {
+                        sl_prefix = prefix | (uint64_t(b) << shift);
+                        sl_need = need - cum;
+                        sl_done = (h == need - cum) ? 1u : 0u;
+                        break;
+                    }
+                    cum += h;
+                }
+            }
+        }
+        __syncthreads();
+        prefix = sl_prefix; need = sl_need;
+        if (sl_done) break;
+    }
+    if (shift < 0) shift = 0;   // unique keys: the last byte always resolves
+    // exactly `keep` keys have (key >> shift) >= (prefix >> shift)
+    for (uint32_t i = tid; i < nv; i += blockDim.x) {
+        const uint64_t k = buf[i];
+        if (k != 0ull && (k >> shift) >= (prefix >> shift)) { const uint32_t s = atomicAdd(&sl_n, 1u); if (s < keep) out[s] = k; }
+    }
+    __syncthreads();
+    return keep;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
     v += __shfl_xor_sync(0xffffffffu, v, 16);
     v += __shfl_xor_sync(0xffffffffu, v, 8);

@@ -68,8 +68,12 @@ def test_gemm_path_with_filter_delete_and_zero_query(gpu_ctx, orc):
     emb.close()
 
 
-def test_gemm_equals_exact_sweep_bitwise(gpu_ctx):
-    n, dim, B = 120000, 768, 64
+@pytest.mark.parametrize("n,B,pair", [(120000, 64, "1"), (150001, 300, "1"), (150001, 300, "0"), (4100, 256, "1")])
+def test_gemm_equals_exact_sweep_bitwise(gpu_ctx, monkeypatch, n, B, pair):
+    """B <= 128: one query group per CTA; B > 128: CTA pairs (cta_group::2, OC_GEMM_PAIR=1, the
+    default) or two groups per CTA (OC_GEMM_PAIR=0) — all must equal the exact sweep bit for bit."""
+    monkeypatch.setenv("OC_GEMM_PAIR", pair)
+    dim = 768
     rows = synth.make_vectors(n, dim, seed=13)
     qv, _ = synth.make_vector_queries(rows, B, seed=14)
     emb = ob.EmbeddingFieldStorage(gpu_ctx, "BGEBase")
