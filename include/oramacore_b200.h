@@ -60,7 +60,13 @@ int oc_device_info(oc_ctx *ctx, int *sm_count, size_t *hbm_bytes, char *name, si
 /* Document-sharded multi-GPU (no reference analogue — the reference is
  * single-node).  Rank 0 creates the id, the host runtime broadcasts it, every rank joins.
  * After oc_comm_init, oc_search with params.sharded=1 all-gathers per-shard top-k over
- * NCCL/NVLink and merges on device; every rank receives the global answer. */
+ * NCCL/NVLink and merges on device; every rank receives the global answer.  When corpus df has
+ * to be counted (a filter, multi-term tokens, tombstones: token_score.rs:262-275) the per-token
+ * counters are summed across ranks with one ncclAllReduce before the idf is derived.  Every rank
+ * must issue the same batch with the same flags: OC_SHARD_TOMBSTONES is set on ALL ranks while
+ * ANY rank's string store holds uncommitted deletes (the host runtime routes deletes, so it knows). */
+#define OC_SHARDED 1
+#define OC_SHARD_TOMBSTONES 2
 #define OC_COMM_ID_BYTES 128
 int oc_comm_unique_id(uint8_t out_id[OC_COMM_ID_BYTES]);
 int oc_comm_init(oc_ctx *ctx, int world_size, int rank, const uint8_t id[OC_COMM_ID_BYTES]);
@@ -159,7 +165,7 @@ typedef struct {
     const uint64_t *omc_doc_ids;       /* OMC multipliers sorted by doc id (index/mod.rs:1720-1739) */
     const float *omc_mult;
     uint64_t n_omc;
-    int sharded;                       /* 1 => all-gather + merge across oc_comm ranks       */
+    int sharded;                       /* OC_SHARDED [| OC_SHARD_TOMBSTONES] => merge across oc_comm ranks */
 } oc_search_params;
 
 /* out_doc_ids/out_scores: B x limit (best first, after offset); out_n[b] hits written;

@@ -981,7 +981,13 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
 
     // ------------------------------------------------------------ host: descriptors
     const bool filter = p->filter_bits != nullptr;
-    const bool tombs = has_ft && str->n_deleted > 0;
+    const bool multi_rank = p->sharded && c->comm.world > 1;
+    // sharded: every rank must take the same df decisions (they drive a collective), so the
+    // tombstone state is the caller's global flag (OC_SHARD_TOMBSTONES), not this shard's
+    const bool tombs_local = has_ft && str->n_deleted > 0;
+    if (multi_rank && tombs_local && !(p->sharded & OC_SHARD_TOMBSTONES))
+        return fail(OC_ERR_INVALID, "sharded search: this shard holds tombstones, set OC_SHARD_TOMBSTONES on every rank");
+    const bool tombs = has_ft && (multi_rank ? (p->sharded & OC_SHARD_TOMBSTONES) != 0 : tombs_local);
     const uint32_t n_tiles = has_ft ? (uint32_t)((str->n_rows + BM25_TILE - 1) / BM25_TILE) : 0;
     std::vector<TermDesc> terms;
     std::vector<uint32_t> term_token;
@@ -1095,7 +1101,6 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
                     if (e_to_u[e] != 0xffffffffu) { terms[e].ptr = c->pre_post.as<Posting>() + u_off[e_to_u[e]]; terms[e].flags |= 1u; }
             }
         }
-        if (need_df && p->sharded && c->comm.world > 1) return fail(OC_ERR_UNSUPPORTED, "sharded search with filters/multi-term tokens needs a df all-reduce (not built)");
     }
     // OMC rows for the tile kernel (string rows, ascending)
     std::vector<uint32_t> omc_rows; std::vector<float> omc_row_mult;
@@ -1224,6 +1229,10 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
             if (n_tiles) {
                 bm25_df_kernel<<<(unsigned)(uint64_t(n_tiles) * ntok), BM25_THREADS, 0, c->stream>>>(dp);
                 launched(c);
+            }
+            if (multi_rank) {   // corpus df = sum of the shards' counts (disjoint documents)
+                std::string err;
+                if (!c->comm.all_reduce_sum_u32(c->df_dev.p, c->df_dev.p, ntok, c->stream, &err)) return fail(OC_ERR_COMM, "%s", err.c_str());
             }
             std::vector<uint32_t> dfh(ntok);
             CU(cudaMemcpyAsync(dfh.data(), c->df_dev.p, ntok * 4, cudaMemcpyDeviceToHost, c->stream));

@@ -1,5 +1,6 @@
-// comm.h — NCCL over NVLink for the one collective the path has: an all-gather of
-// per-shard top-k records per query batch.  libnccl is bound with
+// comm.h — NCCL over NVLink for the collectives the path has: an all-gather of per-shard
+// top-k records per query batch and, only when corpus df must be counted
+// (filters / multi-term tokens / tombstones), an all-reduce of the per-token df counters.  libnccl is bound with
 // dlopen/dlsym (no link-time dependency, no header needed): the torch-bundled
 // libnccl.so.2 already mapped into a torchrun worker is reused, else the system one.
 #pragma once
@@ -17,6 +18,7 @@ struct OcComm {
     typedef int (*GetUniqueId_t)(UniqueId *);
     typedef int (*CommInitRank_t)(Comm *, int, UniqueId, int);
     typedef int (*AllGather_t)(const void *, void *, size_t, int, Comm, cudaStream_t);
+    typedef int (*AllReduce_t)(const void *, void *, size_t, int, int, Comm, cudaStream_t);
     typedef int (*CommDestroy_t)(Comm);
     typedef const char *(*GetErrorString_t)(int);
 
@@ -28,6 +30,7 @@ struct OcComm {
         GetUniqueId_t GetUniqueId = nullptr;
         CommInitRank_t CommInitRank = nullptr;
         AllGather_t AllGather = nullptr;
+        AllReduce_t AllReduce = nullptr;
         CommDestroy_t CommDestroy = nullptr;
         GetErrorString_t GetErrorString = nullptr;
     };
@@ -45,9 +48,10 @@ struct OcComm {
         a.GetUniqueId = (GetUniqueId_t)dlsym(a.h, "ncclGetUniqueId");
         a.CommInitRank = (CommInitRank_t)dlsym(a.h, "ncclCommInitRank");
         a.AllGather = (AllGather_t)dlsym(a.h, "ncclAllGather");
+        a.AllReduce = (AllReduce_t)dlsym(a.h, "ncclAllReduce");
         a.CommDestroy = (CommDestroy_t)dlsym(a.h, "ncclCommDestroy");
         a.GetErrorString = (GetErrorString_t)dlsym(a.h, "ncclGetErrorString");
-        if (!a.GetUniqueId || !a.CommInitRank || !a.AllGather || !a.CommDestroy) {
+        if (!a.GetUniqueId || !a.CommInitRank || !a.AllGather || !a.AllReduce || !a.CommDestroy) {
             if (err) *err = "libnccl is missing required symbols";
             a.h = nullptr;
             return false;
@@ -81,6 +85,12 @@ struct OcComm {
     bool all_gather(const void *send, void *recv, size_t bytes, cudaStream_t s, std::string *err) {
         int rc = api().AllGather(send, recv, bytes, /*ncclInt8*/ 0, comm, s);
         if (rc != 0) { if (err) *err = "ncclAllGather: " + estr(rc); return false; }
+        return true;
+    }
+    // in-place-capable sum of `count` uint32 counters; ncclUint32 = 3, ncclSum = 0
+    bool all_reduce_sum_u32(const void *send, void *recv, size_t count, cudaStream_t s, std::string *err) {
+        int rc = api().AllReduce(send, recv, count, /*ncclUint32*/ 3, /*ncclSum*/ 0, comm, s);
+        if (rc != 0) { if (err) *err = "ncclAllReduce: " + estr(rc); return false; }
         return true;
     }
     void destroy() {

@@ -914,12 +914,12 @@ __global__ void __launch_bounds__(512, 2) emb_gemm_merge_kernel(const GemmMergeP
     __shared__ uint32_t s_off[512];
     __shared__ uint32_t s_valid;
     uint32_t got;
-    for (uint32_t l = tid; l < p.ctas_per_group && l < 512; l += blockDim.x) s_off[l] = min(cnts[l], p.cap);   // parallel loads
-    __syncthreads();
-    if (tid == 0) {   // exclusive scan in shared memory (<= 512 entries)
-        uint32_t acc = 0;
-        for (uint32_t l = 0; l < p.ctas_per_group && l < 512; l++) { const uint32_t c = s_off[l]; s_off[l] = acc; acc += c; }
-        s_valid = p.ctas_per_group <= 512 ? acc : 0xffffffffu;
+    {   // exclusive scan of the list lengths (one list per thread; blockDim.x == 512)
+        const uint32_t mine = (tid < p.ctas_per_group) ? min(cnts[tid], p.cap) : 0u;
+        uint32_t tot;
+        const uint32_t off = block_exclusive_scan(mine, &tot);
+        if (tid < 512) s_off[tid] = off;
+        if (tid == 0) s_valid = p.ctas_per_group <= 512 ? tot : 0xffffffffu;
     }
     __syncthreads();
     if (s_valid <= GEMM_MERGE_BUF) {

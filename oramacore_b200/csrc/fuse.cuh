@@ -163,24 +163,16 @@ __global__ void __launch_bounds__(256) fuse_topk_kernel(const FuseParams p) {
     // Most tiles emit no candidate once the query's threshold has warmed up: compact the valid
     // slots first (per-thread counts + block exclusive scan) and sort only those; fall back to
     // the streaming top-n when they do not fit the key buffer.
-    __shared__ uint32_t s_scan[256];
-    __shared__ uint32_t s_total_valid;
     uint32_t got;
     {
         uint32_t mine = 0;
         if (has_ft)
             for (uint32_t t = tid; t < p.n_tiles; t += blockDim.x) mine += min(p.cand_cnt[size_t(q) * p.n_tiles + t], p.n_keep);
-        s_scan[tid] = mine;
-        __syncthreads();
-        if (tid == 0) {
-            uint32_t acc = 0;
-            for (uint32_t i = 0; i < blockDim.x; i++) { const uint32_t c = s_scan[i]; s_scan[i] = acc; acc += c; }
-            s_total_valid = acc;
-        }
-        __syncthreads();
-        const uint32_t n_valid_ft = s_total_valid, n_all = n_valid_ft + vc;
+        uint32_t n_valid_ft;
+        const uint32_t my_pos = block_exclusive_scan(mine, &n_valid_ft);
+        const uint32_t n_all = n_valid_ft + vc;
         if (n_all <= p.capb) {
-            uint32_t pos = s_scan[tid];
+            uint32_t pos = my_pos;
             if (has_ft)
                 for (uint32_t t = tid; t < p.n_tiles; t += blockDim.x) {
                     const uint32_t c = min(p.cand_cnt[size_t(q) * p.n_tiles + t], p.n_keep);

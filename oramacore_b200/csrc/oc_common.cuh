@@ -234,6 +234,38 @@ __device__ inline uint32_t block_select_largest(const uint64_t *buf, uint32_t nv
     return keep;
 }
 
+// exclusive prefix sum of one value per thread across the block (blockDim.x <= 1024, a multiple of 32);
+// *total receives the block sum.  Every thread must call it.
+__device__ inline uint32_t block_exclusive_scan(uint32_t v, uint32_t *total) {
+    __shared__ uint32_t bs_w[32];
+    __shared__ uint32_t bs_tot;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (uint32_t o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) bs_w[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t w = lane < nw ? bs_w[lane] : 0u;
+        uint32_t winc = w;
+#pragma unroll
+        for (uint32_t o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
+        }
+        bs_w[lane] = winc - w;
+        if (lane == 31) bs_tot = winc;
+    }
+    __syncthreads();
+    const uint32_t r = bs_w[warp] + inc - v;
+    *total = bs_tot;
+    __syncthreads();   // scratch may be reused by the next call
+    return r;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
     v += __shfl_xor_sync(0xffffffffu, v, 16);
     v += __shfl_xor_sync(0xffffffffu, v, 8);

@@ -85,28 +85,34 @@ __global__ void __launch_bounds__(256) shard_pack_kernel(const ShardPackParams p
     if (has_ft) {
         const uint64_t total = uint64_t(p.n_tiles) * p.n_keep;
         // compact the (mostly empty) per-tile candidate lists, sort only the valid keys
-        __shared__ uint32_t s_scan[256];
         __shared__ uint32_t s_nvalid;
         uint32_t mine = 0;
         for (uint32_t t = tid; t < p.n_tiles; t += blockDim.x) mine += min(p.cand_cnt[size_t(q) * p.n_tiles + t], p.n_keep);
-        s_scan[tid] = mine;
-        __syncthreads();
-        if (tid == 0) {
-            uint32_t acc = 0;
-            for (uint32_t i = 0; i < blockDim.x; i++) { const uint32_t c = s_scan[i]; s_scan[i] = acc; acc += c; }
-            s_nvalid = acc;
-        }
+        uint32_t n_valid;
+        const uint32_t my_pos = block_exclusive_scan(mine, &n_valid);
+        if (tid == 0) s_nvalid = n_valid;
         __syncthreads();
         if (s_nvalid <= p.capb) {
-            uint32_t pos = s_scan[tid];
+            uint32_t pos = my_pos;
             for (uint32_t t = tid; t < p.n_tiles; t += blockDim.x) {
                 const size_t s2 = size_t(q) * p.n_tiles + t;
                 const uint32_t c = min(p.cand_cnt[s2], p.n_keep);
                 for (uint32_t k = 0; k < c; k++) buf[pos++] = p.cand_key[s2 * p.n_keep + k];
             }
             const uint32_t nv = s_nvalid, np2 = max(32u, next_pow2(nv));
-            for (uint32_t i = nv + tid; i < np2; i += blockDim.x) buf[i] = KEY_NONE;
-            group_bitonic_desc(buf, np2, tid, blockDim.x, 0);
+            const uint32_t kp2 = max(32u, next_pow2(p.n_keep));
+            if (np2 > 2 * kp2) {   // radix-select the n_keep best, sort only those (same as fuse_topk_kernel)
+                uint64_t *sel = buf + p.capb;
+                for (uint32_t i = tid; i < kp2; i += blockDim.x) sel[i] = KEY_NONE;
+                __syncthreads();
+                block_select_largest(buf, nv, p.n_keep, sel);
+                group_bitonic_desc(sel, kp2, tid, blockDim.x, 0);
+                for (uint32_t i = tid; i < kp2; i += blockDim.x) buf[i] = sel[i];
+                __syncthreads();
+            } else {
+                for (uint32_t i = nv + tid; i < np2; i += blockDim.x) buf[i] = KEY_NONE;
+                group_bitonic_desc(buf, np2, tid, blockDim.x, 0);
+            }
             got = min(nv, p.n_keep);
         } else {
             got = block_topn_stream(buf, p.capb, p.n_keep, total, [&](uint64_t i) -> uint64_t {
@@ -340,7 +346,7 @@ static int run_sharded_merge(oc_ctx *c, const oc_search_params *p, const oc::Fus
     pp.v_erow = c->v_row.as<uint32_t>();
     pp.n_rows_str = n_rows_str; pp.n_rows_emb = n_rows_emb;
     pp.out = c->shard_send.as<uint8_t>();
-    const size_t pack_smem = size_t(fp.capb) * 8 + 64;
+    const size_t pack_smem = size_t(fp.capb) * 8 + size_t(std::max<uint32_t>(32, next_pow2(fp.n_keep))) * 8 + 64;
     static size_t pack_cfg = 0;
     if (pack_smem > pack_cfg) { CU(cudaFuncSetAttribute(shard_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pack_smem)); pack_cfg = pack_smem; }
     shard_pack_kernel<<<B, 256, pack_smem, c->stream>>>(pp);

@@ -150,9 +150,10 @@ class EmbeddingFieldStorage:
         assert r.ndim == 2 and r.shape[1] == self.dim and r.shape[0] == d.shape[0]
         check(lib().oc_emb_insert(self._h, _p(d), _p(r), d.shape[0]))
 
-    def delete(self, doc_id: int):
-        d = np.asarray([doc_id], np.uint64)
-        check(lib().oc_emb_delete(self._h, _p(d), 1))
+    def delete(self, doc_id):
+        """One DocumentId or a sequence of them."""
+        d = np.ascontiguousarray(np.atleast_1d(np.asarray(doc_id, np.uint64)).ravel())
+        check(lib().oc_emb_delete(self._h, _p(d), int(d.shape[0])))
 
     def info(self) -> dict:
         i = _lib.EmbInfo()
@@ -225,9 +226,10 @@ class StringFieldStorage:
         """compact(version) (string_field.rs:186-191)."""
         check(lib().oc_str_commit(self._h))
 
-    def delete(self, doc_id: int):
-        d = np.asarray([doc_id], np.uint64)
-        check(lib().oc_str_delete(self._h, _p(d), 1))
+    def delete(self, doc_id):
+        """One DocumentId or a sequence of them."""
+        d = np.ascontiguousarray(np.atleast_1d(np.asarray(doc_id, np.uint64)).ravel())
+        check(lib().oc_str_delete(self._h, _p(d), int(d.shape[0])))
 
     def info(self) -> dict:
         i = _lib.StrInfo()
@@ -272,6 +274,7 @@ class TokenScoreParams:
     omc_doc_ids: Optional[np.ndarray] = None   # ascending
     omc_mult: Optional[np.ndarray] = None
     sharded: bool = False
+    shard_tombstones: bool = False   # OC_SHARD_TOMBSTONES: some rank's string store holds uncommitted deletes
 
 
 class TokenScoreContext:
@@ -322,7 +325,7 @@ class TokenScoreContext:
             om = np.ascontiguousarray(params.omc_mult, np.float32)
             keep += [od, om]
             sp.omc_doc_ids, sp.omc_mult, sp.n_omc = _p(od), _p(om), od.shape[0]
-        sp.sharded = 1 if params.sharded else 0
+        sp.sharded = (1 | (2 if params.shard_tombstones else 0)) if params.sharded else 0
         docs = np.empty((B, params.limit_hint), np.uint64)
         scores = np.empty((B, params.limit_hint), np.float32)
         n = np.empty(B, np.uint32)

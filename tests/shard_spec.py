@@ -5,11 +5,23 @@ import numpy as np
 f32 = np.float32
 
 
-def local_products(orc, ix, st, mode, text, qv, limit, similarity, threshold=None):
+def local_filtered_df(sd, filter_bits, n_terms_by_field):
+    """Per-shard corpus df under a filter (token_score.rs:262-275 restricted to this shard's
+    documents): what every rank feeds the df all-reduce.  One int64 array per field."""
+    out = []
+    for fi, f in enumerate(sd.fields):
+        docs = sd.row_doc_ids[f.post_row] if sd.row_doc_ids is not None else f.post_row.astype(np.uint64)
+        ok = ((filter_bits[(docs >> np.uint64(6)).astype(np.int64)] >> (docs & np.uint64(63))) & np.uint64(1)).astype(np.int64)
+        cs = np.concatenate([[0], np.cumsum(ok)])
+        out.append((cs[f.term_offsets[1:].astype(np.int64)] - cs[f.term_offsets[:-1].astype(np.int64)]).astype(np.int64))
+    return out
+
+
+def local_products(orc, ix, st, mode, text, qv, limit, similarity, threshold=None, filter_bits=None, filter_nbits=0):
     """What one shard contributes for one query (restated with the oracle's pieces)."""
     out = {"count_ft": 0, "max_ft": f32(0), "min_ft": f32(0), "ft": {}, "v": []}
     if mode in (0, 2):
-        d, s = orc.fulltext(ix, text, threshold=threshold)
+        d, s = orc.fulltext(ix, text, threshold=threshold, filter_bits=filter_bits, filter_nbits=filter_nbits)
         out["count_ft"] = len(d)
         out["ft"] = {int(a): f32(b) for a, b in zip(d, s)}
         if len(s):
@@ -17,7 +29,7 @@ def local_products(orc, ix, st, mode, text, qv, limit, similarity, threshold=Non
             out["min_ft"] = min(f32(0), f32(s.min()))
     if mode in (1, 2):
         # local top-`limit` by distance with the rank key, then rescale / threshold (kept prefix)
-        dv, sv = orc.vector(st, qv, limit, similarity)
+        dv, sv = orc.vector(st, qv, limit, similarity, filter_bits, filter_nbits)
         for doc, score in zip(dv, sv):
             out["v"].append((int(doc), f32(score)))
     return out

@@ -62,6 +62,30 @@ def main():
         t = ctx.last_timing()
         if rank == 0:
             print(f"sharded {name} {kw} omc={omc}: ok on {world} ranks; comm_ms={t['comm_ms']:.3f} device_ms={t['device_ms']:.3f}")
+    # ---- corpus df counted on device and summed across ranks (one ncclAllReduce): filter, then tombstones
+    allowed = np.sort(rng.choice(n, size=n // 3, replace=False))
+    fb = orc.make_filter_bits(allowed.tolist(), n)
+    gone = [int(d) for d in rng.choice(n, size=40, replace=False)]
+    mine = np.array([d for d in gone if lo <= d < hi], dtype=np.uint64)
+    alive = orc.make_filter_bits([d for d in range(n) if d not in set(gone)], n)
+    for name, mode, kw, filt, tomb in [("hybrid", 2, dict(limit=10, similarity=0.0), fb, False),
+                                       ("fulltext", 0, dict(limit=10), fb, False),
+                                       ("fulltext", 0, dict(limit=10), None, True)]:
+        if tomb and len(mine):
+            strs.delete(mine)                    # only the owning shard tombstones the doc; the flag is global
+        extra = dict(filtered_doc_ids=filt, filter_nbits=n) if filt is not None else {}
+        hits = ob.search(ctx, emb if mode else None, strs, name, texts=texts, q_vecs=qv if mode else None, sharded=True,
+                         shard_tombstones=tomb, **kw, **extra)
+        ofb = filt if filt is not None else alive
+        sb = orc.SearchBatch(ix, st)
+        for i in range(B):
+            sb.add(mode, q_vec=qv[i], text=texts[i], filter_bits=ofb, filter_nbits=n, **kw)
+        od, os_, on, oc = sb.run(4)
+        for i, h in enumerate(hits):
+            assert h.count == int(oc[i]), (name, rank, i, h.count, int(oc[i]))
+            assert_topk_equal(h.doc_ids, h.scores, od[i, :on[i]], os_[i, :on[i]], atol=1e-5)
+        if rank == 0:
+            print(f"sharded {name} filter={filt is not None} tombstones={tomb}: ok on {world} ranks (df all-reduce)")
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:

@@ -45,6 +45,34 @@ def _worker(rank, world, port, q):
                 ok &= count == int(oc[i])
                 ok &= docs == od[i, :on[i]].tolist()
                 ok &= bool(np.allclose(scores, os_[i, :on[i]], rtol=0, atol=1e-6))
+    # ---- with a filter the corpus df is counted per shard and summed with one all_reduce before idf
+    import torch
+    rng = np.random.default_rng(11)
+    allowed = np.sort(rng.choice(n, size=n // 3, replace=False))
+    fb = orc.make_filter_bits(allowed.tolist(), n)
+    ldf = shard_spec.local_filtered_df(sd, fb, None)
+    gdf_f = []
+    for a in ldf:
+        t = torch.from_numpy(a.copy())
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)     # the df all-reduce (ncclAllReduce on the GPU path)
+        gdf_f.append(np.maximum(t.numpy(), 1).astype(np.uint32))
+    ix_f = orc.StrIndex(sd, global_df=gdf_f)
+    for mode in (0, 2):
+        local = [shard_spec.local_products(orc, ix_f, st, mode, texts[i], qv[i], limit, 0.0, filter_bits=fb, filter_nbits=n)
+                 for i in range(B)]
+        gathered = [None] * world
+        dist.all_gather_object(gathered, local)
+        if rank == 0:
+            full_ix, full_st = orc.StrIndex(data), orc.EmbStore(rows)
+            sb = orc.SearchBatch(full_ix, full_st)
+            for i in range(B):
+                sb.add(mode, limit=limit, similarity=0.0, q_vec=qv[i], text=texts[i], filter_bits=fb, filter_nbits=n)
+            od, os_, on, oc = sb.run(2)
+            for i in range(B):
+                docs, scores, count = shard_spec.merge([g[i] for g in gathered], mode, limit, 0, limit)
+                ok &= count == int(oc[i])
+                ok &= docs == od[i, :on[i]].tolist()
+                ok &= bool(np.allclose(scores, os_[i, :on[i]], rtol=0, atol=1e-6))
     if rank == 0:
         q.put(ok)
     dist.barrier()
