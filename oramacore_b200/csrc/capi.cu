@@ -500,7 +500,10 @@ static int run_vector_stage(oc_ctx *c, oc_emb *e, const float *q_dev, uint32_t B
     // CTA pairs (cta_group::2): two SMs share one 256-query x 512-row tile (25 % less L2->SM traffic)
     const char *penv = getenv("OC_GEMM_PAIR");
     const uint32_t n_pairs = c->prop.multiProcessorCount / 2;
-    const bool pair = NG == 2 && !(penv && penv[0] == '0') && n_pairs >= n_super;
+    // default: fp32 stores only (there the pair feeds the converting sweep); for bf16 stores the pair kernel
+    // measured ~4 % slower than two groups per CTA on the tensor-bound 10M x 1024 workload (OC_GEMM_PAIR=1 forces it)
+    const bool pair_wanted = penv ? penv[0] == '1' : e->esz == 4;
+    const bool pair = NG == 2 && pair_wanted && !(penv && penv[0] == '0') && n_pairs >= n_super;
     const uint32_t cpg = pair ? std::max<uint32_t>(1, n_pairs / n_super)
                               : std::max<uint32_t>(1, c->prop.multiProcessorCount / n_super);
     const uint32_t grid = pair ? 2 * cpg * n_super : cpg * n_super;

@@ -90,11 +90,14 @@ def test_gemm_equals_exact_sweep_bitwise(gpu_ctx, monkeypatch, n, B, pair):
     emb.close()
 
 
-@pytest.mark.parametrize("n,dim,model,B", [(30000, 1024, "BGELarge", 5), (30000, 1024, "BGELarge", 200),
-                                            (50000, 768, "BGEBase", 64), (20000, 384, "BGESmall", 130)])
-def test_bf16_store_parity(gpu_ctx, orc, n, dim, model, B):
+@pytest.mark.parametrize("n,dim,model,B,pair", [(30000, 1024, "BGELarge", 5, None), (30000, 1024, "BGELarge", 200, None),
+                                                 (50000, 768, "BGEBase", 64, None), (20000, 384, "BGESmall", 130, None),
+                                                 (30000, 1024, "BGELarge", 200, "1")])   # "1": force the CTA-pair kernel
+def test_bf16_store_parity(gpu_ctx, orc, monkeypatch, n, dim, model, B, pair):
     """OC_DTYPE_BF16 store (BASELINE configs[4] shape, reduced): rows are bf16 values; every score is
     exact fp32 arithmetic on those values, so the oracle runs on the bf16-rounded rows."""
+    if pair is not None:
+        monkeypatch.setenv("OC_GEMM_PAIR", pair)
     rows = ob.from_bf16(ob.to_bf16(synth.make_vectors(n, dim, seed=n + dim)))
     qv, planted = synth.make_vector_queries(rows, B, seed=n + 1)
     emb = ob.EmbeddingFieldStorage(gpu_ctx, model, dtype="bf16")
