@@ -42,6 +42,16 @@ WORKLOADS = {
 }
 
 
+# oc_timing.scan_variant (include/oramacore_b200.h OC_SCAN_*) -> (kernel, description)
+SCAN_VARIANTS = {
+    0: ("emb_scan_kernel", "exact fp32 sweep"),
+    1: ("emb_gemm_kernel", "tcgen05 kind::tf32 on the fp32 rows + exact fp32 re-score"),
+    2: ("emb_gemm_pair_kernel", "tcgen05 cta_group::2 kind::tf32 on the fp32 rows + exact fp32 re-score"),
+    3: ("emb_gemm_cvt_kernel", "tcgen05 cta_group::2 kind::f16, fp32 rows streamed once and rounded to bf16 in the SM, + exact fp32 re-score"),
+    4: ("emb_gemm_kernel", "tcgen05 kind::f16 on the bf16 rows + exact fp32 re-score"),
+    5: ("emb_gemm_pair_kernel", "tcgen05 cta_group::2 kind::f16 on the bf16 rows + exact fp32 re-score"),
+}
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -257,7 +267,7 @@ def main():
     if rank == 0:
         sampler.start()
     dev_ms = scan_ms = bm_ms = fuse_ms = comm_ms = 0.0
-    scan_bytes = scan_launches = postings = h2d = d2h = unproven = tensor_core = 0
+    scan_bytes = scan_launches = postings = h2d = d2h = unproven = tensor_core = variant = 0
     sync_all()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -266,7 +276,7 @@ def main():
         dev_ms += t["device_ms"]; scan_ms += t["scan_ms"]; bm_ms += t["bm25_ms"]; fuse_ms += t["fuse_ms"]
         comm_ms += t["comm_ms"]; scan_bytes += t["scan_bytes"]; scan_launches += t["scan_launches"]
         postings += t["bm25_postings"]; h2d, d2h = t["h2d_bytes"], t["d2h_bytes"]
-        unproven += t["scan_unproven"]; tensor_core = max(tensor_core, t["scan_tensor_core"])
+        unproven += t["scan_unproven"]; tensor_core = max(tensor_core, t["scan_tensor_core"]); variant = max(variant, t["scan_variant"])
     sync_all()
     wall = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
@@ -315,17 +325,17 @@ def main():
         ach = (scan_bytes / 1e9) / (scan_ms * 1e-3)
         n_local = hi - lo
         tflops = (2.0 * B * n_local * w["dim"] / 1e12) / (scan_ms / K * 1e-3) if tensor_core else None
-        kind = "kind::f16 (bf16 rows)" if w.get("dtype") == "bf16" else "kind::tf32 (fp32 rows)"
-        line["scan"] = {"kernel": f"emb_gemm_kernel (tcgen05 {kind} + exact fp32 re-score)" if tensor_core else "emb_scan_kernel (exact fp32 sweep)",
+        kname, kdesc = SCAN_VARIANTS.get(variant, ("emb_scan_kernel", "exact fp32 sweep"))
+        line["scan"] = {"kernel": f"{kname} ({kdesc})",
                         "unproven_queries_rerun_exact_per_step": unproven / K,
                         "tensor_tflops_per_gpu": tflops}
         pk_json = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
         if tensor_core and w.get("dtype") == "bf16" and B >= 512:
             tpeak = float(pk_json.get("bf16_tflops_sustained", 1400.0))
-            line["roofline_tensor"] = {"kernel": "emb_gemm_kernel", "bound": "tensor", "achieved": tflops, "peak": tpeak,
+            line["roofline_tensor"] = {"kernel": kname, "bound": "tensor", "achieved": tflops, "peak": tpeak,
                                        "unit": "TFLOP/s", "frac": tflops / tpeak,
                                        "peak_source": "of measured (sustained)" if pk_json else "of fallback"}
-        line["roofline"] = {"kernel": "emb_gemm_kernel" if tensor_core else "emb_scan_kernel", "bound": "hbm", "achieved": ach, "peak": peak,
+        line["roofline"] = {"kernel": kname, "bound": "hbm", "achieved": ach, "peak": peak,
                             "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "peak_source": f"of {peak_src}",
                             "launches_per_step": scan_launches / K,
                             "algorithmic_bytes_per_launch": scan_bytes / max(scan_launches, 1),

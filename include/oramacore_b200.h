@@ -198,7 +198,15 @@ typedef struct {
     uint32_t scan_tensor_core;   /* 1 => the batched tcgen05 (tf32 select + exact re-score) scan ran */
     uint32_t scan_unproven;      /* queries whose tensor-core result failed the exactness proof and were
                                     re-run through the exact sweep                                      */
+    uint32_t scan_variant;       /* OC_SCAN_*: which sweep kernel served the batch                      */
+    uint32_t reserved0;
 } oc_timing;
+#define OC_SCAN_EXACT 0          /* emb_scan_kernel: exact fp32 sweep (B < 8, limit > 32, tiny stores)          */
+#define OC_SCAN_TC_TF32 1        /* emb_gemm_kernel: kind::tf32 on the fp32 rows, one CTA per SM               */
+#define OC_SCAN_TC_TF32_PAIR 2   /* emb_gemm_pair_kernel: same, CTA pairs (cta_group::2)                       */
+#define OC_SCAN_TC_CVT_PAIR 3    /* emb_gemm_cvt_kernel: fp32 rows rounded to bf16 in the SM, kind::f16, pairs */
+#define OC_SCAN_TC_BF16 4        /* emb_gemm_kernel on a bf16 store (kind::f16)                                */
+#define OC_SCAN_TC_BF16_PAIR 5   /* emb_gemm_pair_kernel on a bf16 store                                       */
 int oc_last_timing(oc_ctx *ctx, oc_timing *out);
 /* Total kernels this library has launched on ctx since oc_init. */
 uint64_t oc_launch_count(oc_ctx *ctx);

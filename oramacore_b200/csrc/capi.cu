@@ -121,13 +121,13 @@ struct oc_ctx {
     uint64_t launches = 0;
     uint32_t call_launches = 0, call_scan_launches = 0;
     // workspaces
-    DevBuf in_blob, q_pad, q_inv, eff_norm, filter_dev, scan_cand, v_doc, v_score, v_row, v_cnt, v_srow, v_ft, v_present, v_raw;
+    DevBuf in_blob, in_blob0, q_pad, q_inv, eff_norm, filter_dev, scan_cand, v_doc, v_score, v_row, v_cnt, v_srow, v_ft, v_present, v_raw;
     DevBuf seg, df_dev, row_ok, tau, cand_key, cand_ft, cand_cnt, tile_cnt, tile_max, tile_min, min_hint;
     DevBuf out_blob, shard_send, shard_recv;
     bool gemm_pending = false; const float *gemm_inv_norm = nullptr;
     DevBuf q_bf16, pre_post, g_tau, g_cand, g_cnt, g_flag, g_max, r_qpad, r_qinv, r_map, r_doc, r_score, r_row, r_cnt, r_raw;
 
-    HostBuf h_in, h_out;
+    HostBuf h_in, h_out, h_in0;   // h_in0 / in_blob0: query vectors + filter, uploaded before the descriptors
     OcComm comm;
 };
 
@@ -583,6 +583,7 @@ static int run_vector_stage(oc_ctx *c, oc_emb *e, const float *q_dev, uint32_t B
     // the proof flags travel back with the results; oc_*search re-runs flagged queries (fix_unproven)
     c->gemm_pending = true; c->gemm_inv_norm = inv_norm;
     c->timing.scan_tensor_core = 1;
+    c->timing.scan_variant = cvt ? OC_SCAN_TC_CVT_PAIR : bf16 ? (pair ? OC_SCAN_TC_BF16_PAIR : OC_SCAN_TC_BF16) : (pair ? OC_SCAN_TC_TF32_PAIR : OC_SCAN_TC_TF32);
     return OC_OK;
 }
 
@@ -982,8 +983,45 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
     CU(cudaSetDevice(c->device));
     begin_call(c);
 
-    // ------------------------------------------------------------ host: descriptors
+    // staged segments go in one copy per contiguous run; pinned caller buffers are DMA'd directly
+    auto upload = [&](const Packer &pk, HostBuf &hb, DevBuf &db) -> int {
+        OCTRY(hb.ensure(pk.total + 256));
+        OCTRY(db.ensure(pk.total + 256));
+        pk.fill(hb.p);
+        size_t run0 = 0;
+        for (size_t i = 0; i <= pk.segs.size(); i++) {
+            const bool brk = i == pk.segs.size() || pk.segs[i].direct;
+            if (brk) {
+                const size_t end = i == pk.segs.size() ? pk.total : pk.segs[i].off;
+                if (end > run0) CU(cudaMemcpyAsync(db.as<uint8_t>() + run0, hb.as<uint8_t>() + run0, end - run0, cudaMemcpyHostToDevice, c->stream));
+                if (i < pk.segs.size()) {
+                    CU(cudaMemcpyAsync(db.as<uint8_t>() + pk.segs[i].off, pk.segs[i].src, pk.segs[i].bytes, cudaMemcpyHostToDevice, c->stream));
+                    run0 = pk.segs[i].off + pk.segs[i].bytes;
+                }
+            }
+        }
+        return OC_OK;
+    };
+    // ------------------------------------------------------------ vector stage first: the query vectors
+    // (+ filter) go up alone and the matrix sweep starts; the host-side descriptor work below overlaps it
     const bool filter = p->filter_bits != nullptr;
+    const size_t fwords = filter ? (p->filter_nbits + 63) / 64 : 0;
+    const uint64_t *filter_dev = nullptr;
+    size_t h2d_early = 0;
+    if (has_v) {
+        Packer pk0;
+        const size_t o_qv = pk0.add(p->q_vecs, size_t(B) * emb->dim * 4, is_pinned_host(p->q_vecs));
+        const size_t o_flt = filter ? pk0.add(p->filter_bits, fwords * 8) : 0;
+        CU(cudaEventRecord(c->ev[EV_START], c->stream));
+        OCTRY(upload(pk0, c->h_in0, c->in_blob0));
+        CU(cudaEventRecord(c->ev[EV_H2D], c->stream));
+        h2d_early = pk0.total;
+        if (filter) filter_dev = reinterpret_cast<const uint64_t *>(c->in_blob0.as<uint8_t>() + o_flt);
+        OCTRY(run_vector_stage(c, emb, reinterpret_cast<const float *>(c->in_blob0.as<uint8_t>() + o_qv), B, vlimit, p->similarity,
+                               filter_dev, p->filter_nbits));
+    }
+
+    // ------------------------------------------------------------ host: descriptors
     const bool multi_rank = p->sharded && c->comm.world > 1;
     // sharded: every rank must take the same df decisions (they drive a collective), so the
     // tombstone state is the caller's global flag (OC_SHARD_TOMBSTONES), not this shard's
@@ -1124,11 +1162,9 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
     }
     const bool omc_tile = !omc_rows.empty();
 
-    // ------------------------------------------------------------ H2D: one packed blob
+    // ------------------------------------------------------------ H2D: descriptors in one packed blob
     Packer pk;
-    const size_t o_qv = has_v ? pk.add(p->q_vecs, size_t(B) * emb->dim * 4, is_pinned_host(p->q_vecs)) : 0;
-    const size_t fwords = filter ? (p->filter_nbits + 63) / 64 : 0;
-    const size_t o_flt = filter ? pk.add(p->filter_bits, fwords * 8) : 0;
+    const size_t o_flt = (filter && !has_v) ? pk.add(p->filter_bits, fwords * 8) : 0;
     const size_t o_terms = has_ft ? pk.add(terms.data(), terms.size() * sizeof(TermDesc)) : 0;
     const size_t o_tokens = has_ft ? pk.add(tokens.data(), tokens.size() * sizeof(TokenDesc)) : 0;
     const size_t o_ttok = has_ft ? pk.add(term_token.data(), term_token.size() * 4) : 0;
@@ -1139,43 +1175,22 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
     const size_t o_omcm = n_omc ? pk.add(p->omc_mult, size_t(n_omc) * 4) : 0;
     const size_t o_omcr = omc_tile ? pk.add(omc_rows.data(), omc_rows.size() * 4) : 0;
     const size_t o_omcrm = omc_tile ? pk.add(omc_row_mult.data(), omc_row_mult.size() * 4) : 0;
-    OCTRY(c->h_in.ensure(pk.total + 256));
-    OCTRY(c->in_blob.ensure(pk.total + 256));
-    pk.fill(c->h_in.p);
-    CU(cudaEventRecord(c->ev[EV_START], c->stream));
-    {   // staged segments go in one copy per contiguous run; pinned caller buffers are DMA'd directly
-        size_t run0 = 0;
-        for (size_t i = 0; i <= pk.segs.size(); i++) {
-            const bool brk = i == pk.segs.size() || pk.segs[i].direct;
-            if (brk) {
-                const size_t end = i == pk.segs.size() ? pk.total : pk.segs[i].off;
-                if (end > run0) CU(cudaMemcpyAsync(c->in_blob.as<uint8_t>() + run0, c->h_in.as<uint8_t>() + run0, end - run0, cudaMemcpyHostToDevice, c->stream));
-                if (i < pk.segs.size()) {
-                    CU(cudaMemcpyAsync(c->in_blob.as<uint8_t>() + pk.segs[i].off, pk.segs[i].src, pk.segs[i].bytes, cudaMemcpyHostToDevice, c->stream));
-                    run0 = pk.segs[i].off + pk.segs[i].bytes;
-                }
-            }
-        }
-    }
-    CU(cudaEventRecord(c->ev[EV_H2D], c->stream));
-    c->timing.h2d_bytes = pk.total;
+    if (!has_v) CU(cudaEventRecord(c->ev[EV_START], c->stream));
+    OCTRY(upload(pk, c->h_in, c->in_blob));
+    if (!has_v) CU(cudaEventRecord(c->ev[EV_H2D], c->stream));   // hybrid/vector: this copy rides inside the device window
+    c->timing.h2d_bytes = h2d_early + pk.total;
     uint8_t *din = c->in_blob.as<uint8_t>();
-    const uint64_t *filter_dev = filter ? reinterpret_cast<const uint64_t *>(din + o_flt) : nullptr;
+    if (filter && !has_v) filter_dev = reinterpret_cast<const uint64_t *>(din + o_flt);
 
-    // ------------------------------------------------------------ vector stage
-    if (has_v) {
-        OCTRY(run_vector_stage(c, emb, reinterpret_cast<const float *>(din + o_qv), B, vlimit, p->similarity, filter_dev,
-                               p->filter_nbits));
-        if (c->gemm_pending && p->sharded && c->comm.world > 1) {
-            // sharded: every rank must enter the collective exactly once per batch, so the local
-            // proof flags are resolved here, before the exchange (one extra stream sync per batch)
-            OCTRY(c->h_out.ensure(B));
-            CU(cudaMemcpyAsync(c->h_out.p, c->g_flag.p, B, cudaMemcpyDeviceToHost, c->stream));
-            CU(cudaStreamSynchronize(c->stream));
-            uint32_t redone = 0;
-            OCTRY(fix_unproven(c, emb, c->h_out.as<uint8_t>(), B, vlimit, p->similarity, &redone));
-            c->gemm_pending = false;
-        }
+    if (has_v && c->gemm_pending && p->sharded && c->comm.world > 1) {
+        // sharded: every rank must enter the collective exactly once per batch, so the local
+        // proof flags are resolved here, before the exchange (one extra stream sync per batch)
+        OCTRY(c->h_out.ensure(B));
+        CU(cudaMemcpyAsync(c->h_out.p, c->g_flag.p, B, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        uint32_t redone = 0;
+        OCTRY(fix_unproven(c, emb, c->h_out.as<uint8_t>(), B, vlimit, p->similarity, &redone));
+        c->gemm_pending = false;
     }
 
     // ------------------------------------------------------------ fulltext stage + fusion (re-runnable)
