@@ -199,7 +199,7 @@ typedef struct {
     uint32_t scan_unproven;      /* queries whose tensor-core result failed the exactness proof and were
                                     re-run through the exact sweep                                      */
     uint32_t scan_variant;       /* OC_SCAN_*: which sweep kernel served the batch                      */
-    uint32_t reserved0;
+    float scan_sweep_ms;         /* device time of the sweep launch(es) alone (scan_ms also holds the threshold pass) */
 } oc_timing;
 #define OC_SCAN_EXACT 0          /* emb_scan_kernel: exact fp32 sweep (B < 8, limit > 32, tiny stores)          */
 #define OC_SCAN_TC_TF32 1        /* emb_gemm_kernel: kind::tf32 on the fp32 rows, one CTA per SM               */
