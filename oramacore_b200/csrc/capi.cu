@@ -453,8 +453,15 @@ static int make_tmap_2d(CUtensorMap *m, const void *base, uint64_t n_rows, uint3
     cuuint64_t strides[1] = {cuuint64_t(stride) * (bf16 ? 2 : 4)};
     cuuint32_t box[2] = {(bf16 && !sw64) ? 2 * GEMM_KB : GEMM_KB, box_rows};   // 128 bytes of K (64 when sw64)
     cuuint32_t estr[2] = {1, 1};
+    // L2 promotion granule = the 128-byte box row: with 256 B every tile load also pulled the neighbouring
+    // K-block into L2, and the converting sweep re-fetched 17 % of the matrix from DRAM (ncu: 3.59 GB read
+    // vs 3.12 GB with 128 B; algorithmic 3.08 GB).  OC_TMA_PROMO=256|none: profiling switch.
+    const char *penv = getenv("OC_TMA_PROMO");
+    const CUtensorMapL2promotion promo = !penv ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                         : penv[0] == '2' ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                                         : penv[0] == 'n' ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
     CUresult r = fn(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, promo,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(OC_ERR_CUDA, "cuTensorMapEncodeTiled failed: %d", (int)r);
     return OC_OK;
@@ -1189,9 +1196,9 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
     const size_t o_omcrm = omc_tile ? pk.add(omc_row_mult.data(), omc_row_mult.size() * 4) : 0;
     // hybrid: the descriptors, the shared-contribution precompute, the filter bitmap and the (term, tile) plan do
     // not depend on the vector results: they run on the side stream while the main stream sweeps the matrix
-    // opt-in (OC_SIDE_STREAM=1): it shortens the step by ~1 % but the co-running kernels slow the sweep itself
+    // (OC_SIDE_STREAM=0 disables it: the step gets ~2.5 % longer, the sweep itself ~4 % shorter — A/B switch)
     const char *senv = getenv("OC_SIDE_STREAM");
-    const bool side = senv && senv[0] == '1' && has_v && has_ft && !need_df && !derived_now;
+    const bool side = !(senv && senv[0] == '0') && has_v && has_ft && !need_df && !derived_now;
     if (!has_v) CU(cudaEventRecord(c->ev[EV_START], c->stream));
     if (side) CU(cudaStreamWaitEvent(c->side, c->ev[EV_H2D], 0));   // the filter bitmap went up with the query vectors
     OCTRY(upload(pk, c->h_in, c->in_blob, side ? c->side : c->stream));
