@@ -117,6 +117,7 @@ struct oc_ctx {
     cudaStream_t side = nullptr;      // descriptor upload + BM25 plan/precompute while the main stream sweeps the matrix
     cudaEvent_t ev_side = nullptr;
     bool sweep_timed = false;         // EV_SWEEP0/1 recorded in this call (tensor-core path)
+    bool side_dirty = false;          // work was queued on the side stream and not yet joined (an error path returned early)
     cudaDeviceProp prop{};
     std::mutex mu;
     cudaEvent_t ev[EV_N]{};
@@ -1200,9 +1201,11 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
     // not depend on the vector results: they run on the side stream while the main stream sweeps the matrix
     // (OC_SIDE_STREAM=0 disables it: the step gets ~2.5 % longer, the sweep itself ~4 % shorter — A/B switch)
     const char *senv = getenv("OC_SIDE_STREAM");
-    const bool side = !(senv && senv[0] == '0') && has_v && has_ft && !need_df && !derived_now;
+    // (single-GPU only for now: the sharded path was measured and validated without it)
+    const bool side = !(senv && senv[0] == '0') && has_v && has_ft && !need_df && !derived_now && !multi_rank;
     if (!has_v) CU(cudaEventRecord(c->ev[EV_START], c->stream));
-    if (side) CU(cudaStreamWaitEvent(c->side, c->ev[EV_H2D], 0));   // the filter bitmap went up with the query vectors
+    if (c->side_dirty) { CU(cudaStreamSynchronize(c->side)); c->side_dirty = false; }   // leftover of a failed call
+    if (side) { CU(cudaStreamWaitEvent(c->side, c->ev[EV_H2D], 0)); c->side_dirty = true; }   // the filter bitmap went up with the query vectors
     OCTRY(upload(pk, c->h_in, c->in_blob, side ? c->side : c->stream));
     if (!has_v) CU(cudaEventRecord(c->ev[EV_H2D], c->stream));   // hybrid/vector: this copy rides inside the device window
     c->timing.h2d_bytes = h2d_early + pk.total;
@@ -1268,6 +1271,7 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
         if (on_side) {   // join: everything below needs the vector hits (main stream) and the plan (side stream)
             CU(cudaEventRecord(c->ev_side, c->side));
             CU(cudaStreamWaitEvent(c->stream, c->ev_side, 0));
+            c->side_dirty = false;
             CU(cudaEventRecord(c->ev[EV_BM0], c->stream));
         }
         if (need_df) {
