@@ -15,6 +15,12 @@ use std::ffi::{c_char, c_int, c_void, CStr};
 pub const OC_MODE_FULLTEXT: c_int = 0;
 pub const OC_MODE_VECTOR: c_int = 1;
 pub const OC_MODE_HYBRID: c_int = 2;
+pub const OC_DTYPE_F32: c_int = 0;
+pub const OC_DTYPE_BF16: c_int = 1;
+/// `OcSearchParams::sharded`: merge across `oc_comm` ranks; add `OC_SHARD_TOMBSTONES` on every rank while
+/// any rank's string store holds uncommitted deletes (the df all-reduce must be entered by all ranks).
+pub const OC_SHARDED: c_int = 1;
+pub const OC_SHARD_TOMBSTONES: c_int = 2;
 
 #[repr(C)]
 pub struct OcSearchParams {
@@ -61,6 +67,14 @@ extern "C" {
                              post_row: *const u32, post_tf: *const u16, post_len: *const u16,
                              global_df: *const u32) -> c_int;
     pub fn oc_str_delete(s: *mut OcStr, doc_ids: *const u64, n: u64) -> c_int;
+    /// StringFieldStorage::insert (string_field.rs:155-177): buffered until `oc_str_commit`
+    pub fn oc_str_insert(s: *mut OcStr, field: u32, doc_id: u64, field_len: u16, n_terms: u32,
+                         term_ids: *const u32, tfs: *const u16) -> c_int;
+    /// compaction (string_field.rs:186-191): merges pending inserts / deletes into the device layout
+    pub fn oc_str_commit(s: *mut OcStr) -> c_int;
+    /// page-locked host buffers: query vectors placed here are DMA'd without staging
+    pub fn oc_pinned_alloc(bytes: usize, out: *mut *mut c_void) -> c_int;
+    pub fn oc_pinned_free(p: *mut c_void);
     pub fn oc_search(ctx: *mut OcCtx, emb: *mut OcEmb, s: *mut OcStr, p: *const OcSearchParams,
                      out_doc_ids: *mut u64, out_scores: *mut f32, out_n: *mut u32, out_count: *mut u64) -> c_int;
 }
