@@ -173,6 +173,22 @@ typedef struct {
 int oc_search(oc_ctx *ctx, oc_emb *emb, oc_str *str, const oc_search_params *p,
               uint64_t *out_doc_ids, float *out_scores, uint32_t *out_n, uint64_t *out_count);
 
+/* ---- micro-batching front --------------------------------------------------------------
+ * The reference runs one search per request task, many at a time (bin/oramacore.rs:76-79,
+ * SURVEY.md §8b "Threading"); the GPU path earns its throughput on batches.  A batcher coalesces
+ * concurrent single-query oc_search calls: the first submitter of a group leads it, waits up to
+ * max_wait_us (or until max_batch queries are in), runs ONE oc_search for the group and scatters
+ * the per-query results to the blocked callers.  Coalesced: queries with the same (mode, limit,
+ * offset, similarity, threshold, bm25_k, bm25_b), no filter, no OMC, not sharded; any other call
+ * is passed straight to oc_search.  p->n_queries must be 1; outputs as for oc_search with B = 1. */
+typedef struct oc_batcher oc_batcher;
+int oc_batcher_create(oc_ctx *ctx, oc_emb *emb, oc_str *str, uint32_t max_batch, uint32_t max_wait_us, oc_batcher **out);
+void oc_batcher_destroy(oc_batcher *b);
+int oc_batcher_search(oc_batcher *b, const oc_search_params *p, uint64_t *out_doc_ids, float *out_scores,
+                      uint32_t *out_n, uint64_t *out_count);
+/* queries that went through a coalesced batch / number of batches / calls passed straight through */
+int oc_batcher_stats(oc_batcher *b, uint64_t *n_queries, uint64_t *n_batches, uint64_t *n_direct);
+
 /* ---- pinned host buffers (optional) ----------------------------------------------------------
  * Query vectors handed to oc_search from memory obtained here (or otherwise page-locked) are
  * DMA'd straight from the caller's buffer; pageable buffers are staged through a pinned blob. */

@@ -23,6 +23,7 @@ EXPORTED_SYMBOLS = [
     "oc_comm_init", "oc_emb_create", "oc_emb_destroy", "oc_emb_reserve", "oc_emb_insert", "oc_emb_delete",
     "oc_emb_info", "oc_emb_search", "oc_str_create", "oc_str_destroy", "oc_str_set_rows", "oc_str_load_field",
     "oc_str_insert", "oc_str_commit", "oc_str_delete", "oc_str_info", "oc_search", "oc_pinned_alloc", "oc_pinned_free", "oc_last_timing", "oc_launch_count",
+    "oc_batcher_create", "oc_batcher_destroy", "oc_batcher_search", "oc_batcher_stats",
 ]
 
 
@@ -117,6 +118,11 @@ def lib():
     L.oc_str_delete.argtypes = [vp, vp, u64]
     L.oc_str_info.argtypes = [vp, C.POINTER(StrInfo)]
     L.oc_search.argtypes = [vp, vp, vp, C.POINTER(SearchParams), vp, vp, vp, vp]
+    L.oc_batcher_create.argtypes = [vp, vp, vp, u32, u32, C.POINTER(vp)]
+    L.oc_batcher_destroy.argtypes = [vp]
+    L.oc_batcher_destroy.restype = None
+    L.oc_batcher_search.argtypes = [vp, C.POINTER(SearchParams), vp, vp, vp, vp]
+    L.oc_batcher_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
     L.oc_pinned_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
     L.oc_pinned_free.argtypes = [vp]
     L.oc_pinned_free.restype = None

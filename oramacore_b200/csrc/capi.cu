@@ -980,6 +980,7 @@ static int launch_tile(oc_ctx *c, const Bm25Params &bp, uint32_t grid, bool mult
 }
 
 #include "shard.cuh"
+#include "batcher.h"
 
 extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_params *p, uint64_t *out_doc_ids,
                          float *out_scores, uint32_t *out_n, uint64_t *out_count) {
@@ -1431,4 +1432,35 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
     memcpy(out_n, h + o_n, size_t(B) * 4);
     memcpy(out_count, h + o_cnt, size_t(B) * 8);
     return finish_timing(c, has_v && emb->n_rows > 0, has_ft, true, did_comm);
+}
+
+// ------------------------------------------------------------------------------------ micro-batching front
+struct OcSearchExec {
+    oc_ctx *c; oc_emb *e; oc_str *s;
+    int operator()(const oc_search_params *p, uint64_t *docs, float *scores, uint32_t *n, uint64_t *count) const {
+        return oc_search(c, e, s, p, docs, scores, n, count);
+    }
+};
+struct oc_batcher {
+    ocb::Batcher<OcSearchExec> q;
+    oc_batcher(OcSearchExec x, uint32_t dim, uint32_t mb, uint32_t mw) : q(x, dim, mb, mw) {}
+};
+extern "C" int oc_batcher_create(oc_ctx *c, oc_emb *emb, oc_str *str, uint32_t max_batch, uint32_t max_wait_us, oc_batcher **out) {
+    if (!c || !out || (!emb && !str)) return fail(OC_ERR_INVALID, "bad arguments");
+    if ((emb && emb->ctx != c) || (str && str->ctx != c)) return fail(OC_ERR_INVALID, "store belongs to another ctx");
+    if (max_batch == 0 || max_batch > 4096) return fail(OC_ERR_INVALID, "max_batch %u outside 1..4096", max_batch);
+    *out = new oc_batcher(OcSearchExec{c, emb, str}, emb ? emb->dim : 0, max_batch, max_wait_us);
+    return OC_OK;
+}
+extern "C" void oc_batcher_destroy(oc_batcher *b) { delete b; }
+extern "C" int oc_batcher_search(oc_batcher *b, const oc_search_params *p, uint64_t *out_doc_ids, float *out_scores,
+                                 uint32_t *out_n, uint64_t *out_count) {
+    if (!b || !p || !out_doc_ids || !out_scores || !out_n || !out_count) return fail(OC_ERR_INVALID, "NULL argument");
+    if (p->n_queries != 1) return fail(OC_ERR_INVALID, "oc_batcher_search takes one query per call (n_queries = %u)", p->n_queries);
+    return b->q.submit(p, out_doc_ids, out_scores, out_n, out_count);
+}
+extern "C" int oc_batcher_stats(oc_batcher *b, uint64_t *n_queries, uint64_t *n_batches, uint64_t *n_direct) {
+    if (!b) return fail(OC_ERR_INVALID, "NULL argument");
+    b->q.stats(n_queries, n_batches, n_direct);
+    return OC_OK;
 }

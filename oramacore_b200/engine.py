@@ -297,6 +297,17 @@ class TokenScoreContext:
         """Same call, results as arrays: (doc_ids [B,limit], scores [B,limit], n [B], count [B]).
         `texts` is a sequence of TextQuery or a pre-packed TextQueryBatch (term resolution happens
         before the hot path in the reference as well: token_score.rs:196-209)."""
+        sp, keep, B = self._build_params(params, texts, q_vecs)
+        docs = np.empty((B, params.limit_hint), np.uint64)
+        scores = np.empty((B, params.limit_hint), np.float32)
+        n = np.empty(B, np.uint32)
+        cnt = np.empty(B, np.uint64)
+        check(lib().oc_search(self.ctx._h, self.emb._h if self.emb else None, self.str._h if self.str else None,
+                              C.byref(sp), _p(docs), _p(scores), _p(n), _p(cnt)))
+        return docs, scores, n, cnt
+
+    def _build_params(self, params: TokenScoreParams, texts=None, q_vecs: Optional[np.ndarray] = None):
+        """oc_search_params for a batch; `keep` holds the arrays the struct points into."""
         if texts is not None and not isinstance(texts, TextQueryBatch):
             texts = TextQueryBatch(texts)
         B = texts.n_queries if texts is not None else int(np.asarray(q_vecs).reshape(-1, self.emb.dim).shape[0])
@@ -326,13 +337,7 @@ class TokenScoreContext:
             keep += [od, om]
             sp.omc_doc_ids, sp.omc_mult, sp.n_omc = _p(od), _p(om), od.shape[0]
         sp.sharded = (1 | (2 if params.shard_tombstones else 0)) if params.sharded else 0
-        docs = np.empty((B, params.limit_hint), np.uint64)
-        scores = np.empty((B, params.limit_hint), np.float32)
-        n = np.empty(B, np.uint32)
-        cnt = np.empty(B, np.uint64)
-        check(lib().oc_search(self.ctx._h, self.emb._h if self.emb else None, self.str._h if self.str else None,
-                              C.byref(sp), _p(docs), _p(scores), _p(n), _p(cnt)))
-        return docs, scores, n, cnt
+        return sp, keep, B
 
     def execute(self, params: TokenScoreParams, results: Dict[int, float], text: Optional[TextQuery] = None,
                 q_vec: Optional[np.ndarray] = None) -> int:
@@ -343,6 +348,42 @@ class TokenScoreContext:
         for d, s in zip(hits.doc_ids, hits.scores):
             results[int(d)] = np.float32(s)
         return hits.count
+
+
+class SearchBatcher:
+    """Micro-batching front (oc_batcher_*, csrc/batcher.h): many threads call search() with ONE query
+    each — the way the reference's request tasks call TokenScoreContext::execute — and the library
+    coalesces concurrent calls that share (mode, limit, offset, similarity, threshold) into one
+    batched oc_search.  ctypes releases the GIL while a caller is blocked in the library."""
+
+    def __init__(self, tsc: TokenScoreContext, max_batch: int = 256, max_wait_us: int = 200):
+        self.tsc = tsc
+        h = C.c_void_p()
+        check(lib().oc_batcher_create(tsc.ctx._h, tsc.emb._h if tsc.emb else None, tsc.str._h if tsc.str else None,
+                                      int(max_batch), int(max_wait_us), C.byref(h)))
+        self._h = h
+
+    def search(self, params: TokenScoreParams, text: Optional[TextQuery] = None,
+               q_vec: Optional[np.ndarray] = None) -> SearchHits:
+        sp, keep, B = self.tsc._build_params(params, None if text is None else [text],
+                                             None if q_vec is None else np.asarray(q_vec, np.float32).reshape(1, -1))
+        assert B == 1
+        L = params.limit_hint
+        docs, scores = np.empty(L, np.uint64), np.empty(L, np.float32)
+        n, cnt = np.zeros(1, np.uint32), np.zeros(1, np.uint64)
+        check(lib().oc_batcher_search(self._h, C.byref(sp), _p(docs), _p(scores), _p(n), _p(cnt)))
+        k = int(n[0])
+        return SearchHits(docs[:k].copy(), scores[:k].copy(), int(cnt[0]))
+
+    def stats(self) -> dict:
+        q, b, d = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        check(lib().oc_batcher_stats(self._h, C.byref(q), C.byref(b), C.byref(d)))
+        return {"queries": q.value, "batches": b.value, "direct": d.value}
+
+    def close(self):
+        if self._h:
+            lib().oc_batcher_destroy(self._h)
+            self._h = None
 
 
 def search(ctx: Context, emb: Optional[EmbeddingFieldStorage], strs: Optional[StringFieldStorage], mode: str,

@@ -461,3 +461,51 @@ def test_concurrent_callers_share_one_ctx(gpu_ctx, orc):
         t.join()
     assert not errs, errs
     emb.close(); strs.close()
+
+
+def test_batcher_coalesces_single_query_callers(gpu_ctx, orc):
+    """oc_batcher_*: 8 threads submit one hybrid query each (the reference's one-search-per-task
+    shape); results must equal the direct batched oc_search and calls must be coalesced."""
+    import threading
+    n, dim, vocab, B = 30000, 384, 2000, 48
+    rows = synth.make_vectors(n, dim, seed=71)
+    qv, _ = synth.make_vector_queries(rows, B, seed=72)
+    data = synth.make_text_corpus(n, vocab, seed=73)
+    texts = synth.make_text_queries(vocab, B, seed=74)
+    emb = ob.EmbeddingFieldStorage(gpu_ctx, "BGESmall")
+    emb.insert_batch(np.arange(n, dtype=np.uint64), rows)
+    strs = ob.StringFieldStorage(gpu_ctx, data)
+    tsc = ob.TokenScoreContext(gpu_ctx, emb, strs)
+    params = ob.TokenScoreParams(mode=ob.MODE_HYBRID, limit_hint=10, similarity=0.0)
+    direct = tsc.execute_batch(params, texts, qv)
+    bat = ob.SearchBatcher(tsc, max_batch=16, max_wait_us=20000)
+    got, errs = [None] * B, []
+
+    def worker(t):
+        try:
+            for i in range(t, B, 8):
+                got[i] = bat.search(params, texts[i], qv[i])
+        except Exception as e:   # noqa: BLE001
+            errs.append(repr(e))
+
+    th = [threading.Thread(target=worker, args=(t,)) for t in range(8)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    assert not errs, errs
+    for i in range(B):
+        assert got[i].count == direct[i].count
+        # a query's result does not depend on which other queries share its batch (bit-identical BM25,
+        # exact fp32 re-score of the vector hits)
+        assert np.array_equal(got[i].doc_ids, direct[i].doc_ids) and np.array_equal(got[i].scores, direct[i].scores)
+    st = bat.stats()
+    assert st["queries"] == B and st["batches"] < B, st
+    # a filtered query is not coalesced: it goes straight through
+    fb = orc.make_filter_bits(list(range(0, n, 2)), n)
+    pf = ob.TokenScoreParams(mode=ob.MODE_FULLTEXT, limit_hint=10, filtered_doc_ids=fb, filter_nbits=n)
+    h = bat.search(pf, texts[0], None)
+    ref = tsc.execute_batch(pf, [texts[0]], None)[0]
+    assert h.count == ref.count and np.array_equal(h.doc_ids, ref.doc_ids)
+    assert bat.stats()["direct"] == 1
+    bat.close(); strs.close(); emb.close()
