@@ -11,6 +11,7 @@ use std::ffi::{c_char, c_int, c_void, CStr};
 #[repr(C)] pub struct OcCtx { _p: [u8; 0] }
 #[repr(C)] pub struct OcEmb { _p: [u8; 0] }
 #[repr(C)] pub struct OcStr { _p: [u8; 0] }
+#[repr(C)] pub struct OcBatcher { _p: [u8; 0] }
 
 pub const OC_MODE_FULLTEXT: c_int = 0;
 pub const OC_MODE_VECTOR: c_int = 1;
@@ -74,6 +75,13 @@ extern "C" {
     pub fn oc_str_commit(s: *mut OcStr) -> c_int;
     /// page-locked host buffers: query vectors placed here are DMA'd without staging
     pub fn oc_pinned_alloc(bytes: usize, out: *mut *mut c_void) -> c_int;
+    /// micro-batching front: one query per call from many threads, coalesced into batched `oc_search`
+    pub fn oc_batcher_create(ctx: *mut OcCtx, emb: *mut OcEmb, s: *mut OcStr, max_batch: u32, max_wait_us: u32,
+                             out: *mut *mut OcBatcher) -> c_int;
+    pub fn oc_batcher_destroy(b: *mut OcBatcher);
+    pub fn oc_batcher_search(b: *mut OcBatcher, p: *const OcSearchParams, out_doc_ids: *mut u64, out_scores: *mut f32,
+                             out_n: *mut u32, out_count: *mut u64) -> c_int;
+    pub fn oc_batcher_stats(b: *mut OcBatcher, n_queries: *mut u64, n_batches: *mut u64, n_direct: *mut u64) -> c_int;
     pub fn oc_pinned_free(p: *mut c_void);
     pub fn oc_search(ctx: *mut OcCtx, emb: *mut OcEmb, s: *mut OcStr, p: *const OcSearchParams,
                      out_doc_ids: *mut u64, out_scores: *mut f32, out_n: *mut u32, out_count: *mut u64) -> c_int;
