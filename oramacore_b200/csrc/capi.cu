@@ -8,7 +8,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <mutex>
+#include <utility>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -48,6 +50,18 @@ extern "C" const char *oc_last_error(void) { return g_err; }
 extern "C" int oc_version(void) { return 100; }
 extern "C" void oc_abi_sizes(size_t out[4]) {
     out[0] = sizeof(oc_search_params); out[1] = sizeof(oc_timing); out[2] = sizeof(oc_emb_info_t); out[3] = sizeof(oc_str_info_t);
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per (device, function): remember what was configured
+// per device so several contexts on different GPUs in one process each get their kernels configured
+static bool smem_cfg_needed(int device, const void *fn, size_t smem) {
+    static std::mutex mu;
+    static std::map<std::pair<int, const void *>, size_t> done;
+    std::lock_guard<std::mutex> g(mu);
+    size_t &v = done[std::make_pair(device, fn)];
+    if (smem <= v) return false;
+    v = smem;
+    return true;
 }
 
 // ------------------------------------------------------------------------------------ buffers
@@ -343,11 +357,8 @@ extern "C" int oc_emb_info(oc_emb *e, oc_emb_info_t *out) {
 // ---- scan launch plumbing
 template <int NCH, int QB, typename T>
 static int launch_scan_t(oc_ctx *c, const ScanParams &sp, uint32_t grid, size_t smem) {
-    static size_t configured = 0;  // per instantiation
-    if (smem > configured) {
+    if (smem_cfg_needed(c->device, (const void *)emb_scan_kernel<NCH, QB, T>, smem))
         CU(cudaFuncSetAttribute(emb_scan_kernel<NCH, QB, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
     emb_scan_kernel<NCH, QB, T><<<grid, SCAN_THREADS, smem, c->stream>>>(sp);
     launched(c, true);
     CU(cudaGetLastError());
@@ -424,11 +435,8 @@ static int run_exact_sweeps(oc_ctx *c, oc_emb *e, const float *inv_norm, const f
     mp.capb = std::max<uint32_t>(2048, next_pow2(2 * limit));
     mp.row_doc_ids = e->row_doc; mp.rescale_e5 = e->e5; mp.similarity = similarity;
     mp.out_doc = o.doc; mp.out_score = o.score; mp.out_row = o.row; mp.out_count = o.cnt; mp.out_raw = o.raw;
-    static size_t merge_cfg = 0;
-    if (size_t(mp.capb) * 8 > merge_cfg) {
+    if (smem_cfg_needed(c->device, (const void *)emb_scan_merge_kernel, size_t(mp.capb) * 8))
         CU(cudaFuncSetAttribute(emb_scan_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(mp.capb * 8)));
-        merge_cfg = size_t(mp.capb) * 8;
-    }
     emb_scan_merge_kernel<<<nq, 256, mp.capb * 8, c->stream>>>(mp);
     launched(c);
     CU(cudaGetLastError());
@@ -554,8 +562,7 @@ static int run_vector_stage(oc_ctx *c, oc_emb *e, const float *q_dev, uint32_t B
     gp.n_qgroups = n_qgroups; gp.ctas_per_group = cpg; gp.keep = keep; gp.cap = cap; gp.lists_per_query = lists;
     gp.tau = c->g_tau.as<unsigned int>(); gp.cand = c->g_cand.as<uint64_t>(); gp.cand_cnt = c->g_cnt.as<uint32_t>();
     gp.gmax = c->g_max.as<float>();
-    static bool gemm_cfg = false;
-    if (!gemm_cfg) {
+    if (smem_cfg_needed(c->device, (const void *)emb_gemm_cvt_kernel, gemm_cvt_smem_bytes())) {   // all sweep variants at once
         CU(cudaFuncSetAttribute(emb_gemm_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes(1)));
         CU(cudaFuncSetAttribute(emb_gemm_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes(2)));
         CU(cudaFuncSetAttribute(emb_gemm_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes(1)));
@@ -563,7 +570,6 @@ static int run_vector_stage(oc_ctx *c, oc_emb *e, const float *q_dev, uint32_t B
         CU(cudaFuncSetAttribute(emb_gemm_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_pair_smem_bytes()));
         CU(cudaFuncSetAttribute(emb_gemm_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_pair_smem_bytes()));
         CU(cudaFuncSetAttribute(emb_gemm_cvt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_cvt_smem_bytes()));
-        gemm_cfg = true;
     }
     auto launch_gemm = [&]() -> int {
         if (cvt) emb_gemm_cvt_kernel<<<grid, CVT_THREADS, gemm_cvt_smem_bytes(), c->stream>>>(tm_q, tm_x, gp);
@@ -954,11 +960,9 @@ static inline float host_idf(float total_documents, uint64_t corpus_df) {
 
 template <bool MULTI, bool THRESH, bool OMC>
 static int launch_tile_t(oc_ctx *c, const Bm25Params &bp, uint32_t grid, size_t smem) {
-    static size_t configured = 0;  // per instantiation; static smem counts against the 227 KB cap
-    if (smem > configured) {
+    // (static smem counts against the 227 KB cap)
+    if (smem_cfg_needed(c->device, (const void *)bm25_tile_kernel<MULTI, THRESH, OMC>, smem))
         CU(cudaFuncSetAttribute(bm25_tile_kernel<MULTI, THRESH, OMC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
     bm25_tile_kernel<MULTI, THRESH, OMC><<<grid, BM25_THREADS, smem, c->stream>>>(bp);
     launched(c);
     CU(cudaGetLastError());
@@ -1375,8 +1379,8 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
     fp.out_n = reinterpret_cast<uint32_t *>(dout + o_n); fp.out_count = reinterpret_cast<unsigned long long *>(dout + o_cnt);
     fp.out_min = reinterpret_cast<float *>(dout + o_min);
     fuse_smem = size_t(fp.capb) * 8 + size_t(std::max<uint32_t>(32, next_pow2(n_keep))) * 8 + size_t(vlimit) * 8 + 64;
-    static size_t fuse_cfg = 0;
-    if (fuse_smem > fuse_cfg) { CU(cudaFuncSetAttribute(fuse_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fuse_smem)); fuse_cfg = fuse_smem; }
+    if (smem_cfg_needed(c->device, (const void *)fuse_topk_kernel, fuse_smem))
+        CU(cudaFuncSetAttribute(fuse_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fuse_smem));
 
     if (p->sharded && c->comm.world > 1) {
         CU(cudaEventRecord(c->ev[EV_FUSE0], c->stream));
@@ -1457,7 +1461,11 @@ extern "C" int oc_batcher_search(oc_batcher *b, const oc_search_params *p, uint6
                                  uint32_t *out_n, uint64_t *out_count) {
     if (!b || !p || !out_doc_ids || !out_scores || !out_n || !out_count) return fail(OC_ERR_INVALID, "NULL argument");
     if (p->n_queries != 1) return fail(OC_ERR_INVALID, "oc_batcher_search takes one query per call (n_queries = %u)", p->n_queries);
-    return b->q.submit(p, out_doc_ids, out_scores, out_n, out_count);
+    g_err[0] = 0;
+    const int rc = b->q.submit(p, out_doc_ids, out_scores, out_n, out_count);
+    // the batch ran on its leader's thread: that is where oc_last_error() holds the detail
+    if (rc != OC_OK && g_err[0] == 0) return fail(rc, "the coalesced oc_search of this query's batch failed (detail on the leading caller's thread)");
+    return rc;
 }
 extern "C" int oc_batcher_stats(oc_batcher *b, uint64_t *n_queries, uint64_t *n_batches, uint64_t *n_direct) {
     if (!b) return fail(OC_ERR_INVALID, "NULL argument");

@@ -347,8 +347,8 @@ static int run_sharded_merge(oc_ctx *c, const oc_search_params *p, const oc::Fus
     pp.n_rows_str = n_rows_str; pp.n_rows_emb = n_rows_emb;
     pp.out = c->shard_send.as<uint8_t>();
     const size_t pack_smem = size_t(fp.capb) * 8 + size_t(std::max<uint32_t>(32, next_pow2(fp.n_keep))) * 8 + 64;
-    static size_t pack_cfg = 0;
-    if (pack_smem > pack_cfg) { CU(cudaFuncSetAttribute(shard_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pack_smem)); pack_cfg = pack_smem; }
+    if (smem_cfg_needed(c->device, (const void *)shard_pack_kernel, pack_smem))
+        CU(cudaFuncSetAttribute(shard_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pack_smem));
     shard_pack_kernel<<<B, 256, pack_smem, c->stream>>>(pp);
     launched(c);
     CU(cudaGetLastError());
@@ -363,8 +363,8 @@ static int run_sharded_merge(oc_ctx *c, const oc_search_params *p, const oc::Fus
     sp.omc_doc = fp.omc_doc; sp.omc_mult = fp.omc_mult; sp.n_omc = fp.n_omc;
     sp.out_doc = fp.out_doc; sp.out_score = fp.out_score; sp.out_n = fp.out_n; sp.out_count = fp.out_count; sp.out_min = fp.out_min;
     const size_t fsmem = size_t(sp.capb) * 8 + size_t(fp.v_stride) * 36 + 64;
-    static size_t sf_cfg = 0;
-    if (fsmem > sf_cfg) { CU(cudaFuncSetAttribute(shard_fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem)); sf_cfg = fsmem; }
+    if (smem_cfg_needed(c->device, (const void *)shard_fuse_kernel, fsmem))
+        CU(cudaFuncSetAttribute(shard_fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
     shard_fuse_kernel<<<B, 256, fsmem, c->stream>>>(sp);
     launched(c);
     CU(cudaGetLastError());
