@@ -111,6 +111,53 @@ def test_exact_vs_prefix(orc):
     assert count >= 1
 
 
+def test_exact_prefix_counts(orc):
+    # fulltext_search.rs:603-757 (test_fulltext_exact): originals only when exact, prefix hits otherwise
+    h = build_index([(1, {"text": "Christopher Nolan"}), (2, {"text": "Foxes"}), (3, {"text": "Fox"})])
+    assert _search_ft(orc, h, "christoph", exact=True)[2] == 0
+    assert _search_ft(orc, h, "christoph", exact=False)[2] == 1
+    assert _search_ft(orc, h, "Fox", exact=True)[2] == 1
+    assert _search_ft(orc, h, "Foxes", exact=True)[2] == 1
+    assert _search_ft(orc, h, "Fox", exact=False)[2] == 2
+
+
+def test_exact_with_threshold_picks_the_right_doc(orc):
+    # fulltext_search.rs:758-887: exact "Fox table" matches both docs (shared "table"); threshold 1.0 keeps
+    # only the document holding BOTH exact terms
+    h = build_index([(1, {"text": "Foxes table"}), (2, {"text": "Fox table"})])
+    assert _search_ft(orc, h, "Fox table", exact=True)[2] == 2
+    assert _search_ft(orc, h, "Foxes table", exact=True)[2] == 2
+    docs, _, count = _search_ft(orc, h, "Fox table", exact=True, threshold=1.0)
+    assert count == 1 and docs == [2]
+    docs, _, count = _search_ft(orc, h, "Foxes table", exact=True, threshold=1.0)
+    assert count == 1 and docs == [1]
+
+
+def test_field_boost_raises_the_score(orc):
+    # src/tests/boost_integration.rs:12-135: "machine learning" over title + content; boosting the field that holds
+    # the phrase densely (doc1's title) raises doc1's score by more than 8 %, and more than boosting content does
+    docs = [(1, {"title": "machine learning",
+                 "content": "This comprehensive document provides detailed information about various algorithms and techniques "
+                            "used in modern data processing applications. The field includes machine learning which encompasses "
+                            "many different approaches and methodologies for analysis and prediction."}),
+            (2, {"title": "data analysis techniques",
+                 "content": "Advanced machine learning models and frameworks for comprehensive data analysis, statistical "
+                            "processing, and predictive modeling in various business applications and research contexts."}),
+            (3, {"title": "statistical methods",
+                 "content": "Comprehensive overview of machine learning methodologies combined with traditional statistical "
+                            "approaches for effective data analysis, pattern recognition, and business intelligence applications."})]
+    h = build_index(docs, fields=("title", "content"))
+
+    def score_of_doc1(boost):
+        d, s, count = _search_ft(orc, h, "machine learning", boost=boost, properties=["title", "content"])
+        assert count > 0
+        return dict(zip(d, s))[1]
+
+    none, title, content = score_of_doc1({}), score_of_doc1({"title": 3.0, "content": 1.0}), score_of_doc1({"title": 1.0, "content": 3.0})
+    assert title > none and title > content
+    assert title / none > 1.08
+
+
 def test_vector_contract(orc):
     rng = np.random.default_rng(0)
     rows = rng.standard_normal((500, 64)).astype(np.float32)
