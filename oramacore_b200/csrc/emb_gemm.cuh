@@ -7,26 +7,27 @@
 //
 //   * operands: fp32 rows straight from HBM, consumed by tcgen05.mma kind::tf32 (the tensor
 //     core reads the fp32 bits and drops the low 13 mantissa bits) — no converted copy of
-//     the store, algorithmic bytes = n_rows * stride * 4 per batch;
-//   * CTA tile: M = 128 queries (A operand) x N = 256 rows (B operand), K-blocks of 32 floats
-//     = one 128-byte swizzle row; TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) fills a
-//     4-stage ring (16 KB of Q + 32 KB of X per stage), a single thread issues 4
-//     tcgen05.mma per K-block into a 128-lane x 256-column fp32 accumulator in TMEM,
-//     double buffered (2 x 256 = all 512 TMEM columns) so the epilogue of tile i overlaps the
-//     MMAs of tile i+1;
-//   * query groups of 128 run as separate CTAs that walk the same row tiles at the same
-//     time, so the second group's reads hit L2 and HBM traffic stays one sweep per batch;
-//   * epilogue: 4 warps, thread = TMEM lane = ONE QUERY: tcgen05.ld the 256 scores of the
-//     tile, scale by the row's inverse norm, threshold-gated push into that query's private
-//     candidate buffer; the threshold is the query's running K'-th best, shared across CTAs
-//     through an atomicMax'd global array (any subset's K'-th best bounds the global one);
-//   * tf32 scores are only used to SELECT candidates.  The merge kernel re-scores the best
-//     K' candidates per query in exact fp32 with K1's arithmetic (bit-identical scores) and
-//     PROVES the answer: every non-candidate row has approx <= a_K', and
-//     |approx - exact| <= eps_tf32 (both operands truncated to 11 significant bits:
-//     2*2^-10 of |x||q|, plus fp32 accumulation), so when the limit-th exact score is
-//     >= a_K' + eps the exact top-`limit` is inside the candidate set.  Queries that fail
-//     the proof are re-run through the exact K1 sweep by the host (rare).
+//     the store, algorithmic bytes = n_rows * stride * 4 per batch; bf16 stores use kind::f16;
+//   * CTA tile: M = 128 queries (A operand) x N = 256 rows (B operand), K-blocks of 128 bytes
+//     = one swizzle row; TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) fills the shared-memory
+//     ring, a single thread issues the tcgen05.mma into 128-lane x 256-column fp32
+//     accumulators in TMEM (all 512 columns: NG=1 double-buffers one group's accumulator across
+//     tiles, NG=2 holds one accumulator per query group so two groups share each X tile);
+//   * epilogue: 8 warps, thread = TMEM lane = ONE QUERY: tcgen05.ld the scores of the tile,
+//     scale by the row's inverse norm, threshold-gated push into that query's private
+//     candidate buffer; the threshold is the query's running K'-th best, seeded by a one-tile
+//     threshold pass of the same kernel and shared across CTAs through an atomicMax'd global
+//     array (any subset's K'-th best bounds the global one);
+//   * the sweep's scores are only used to SELECT candidates.  The merge kernel re-scores the
+//     best K' candidates per query in exact fp32 with K1's arithmetic (bit-identical scores) and
+//     PROVES the answer: every non-candidate row has approx <= max(final threshold, K'-th
+//     selected), and |approx - exact| <= eps for the sweep's arithmetic (GEMM_EPS_* below), so
+//     when the limit-th exact score clears bound + eps the exact top-`limit` is inside the
+//     candidate set.  Queries that fail the proof are re-run through the exact K1 sweep by the
+//     host (rare).
+//   * variants in this file: emb_gemm_kernel<NG, BF16> (one CTA per SM), emb_gemm_pair_kernel
+//     (cta_group::2 CTA pairs), emb_gemm_cvt_kernel (pairs + fp32 -> bf16 conversion inside the
+//     SM: the default for fp32 stores at B > 128), gemm_tau_from_max_kernel, emb_gemm_merge_kernel.
 #pragma once
 #include <cuda.h>
 
