@@ -35,8 +35,9 @@ def local_products(orc, ix, st, mode, text, qv, limit, similarity, threshold=Non
     return out
 
 
-def merge(shards, mode, limit, offset, n_keep):
-    """shards: list of local_products (non-E5 model: rank key order == score order)."""
+def merge(shards, mode, limit, offset, n_keep, omc=None):
+    """shards: list of local_products (non-E5 model: rank key order == score order).
+    omc: {doc: multiplier} applied after fusion (search.rs:39-48), before top-N."""
     allv = sorted([v for s in shards for v in s["v"]], key=lambda t: (-t[1], t[0]))[:limit] if mode != 0 else []
     vmap = {}
     for d, sc in allv:
@@ -59,6 +60,8 @@ def merge(shards, mode, limit, offset, n_keep):
                 final[d] = f32(f32(v - mn) / den)
             for d, v in vmap.items():
                 final[d] = f32(final.get(d, f32(0)) + f32(f32(v - mn) / den))
+    if omc:
+        final = {d: (f32(v * f32(omc[d])) if d in omc else v) for d, v in final.items()}
     items = sorted([(d, s) for d, s in final.items() if not np.isnan(s)], key=lambda t: (-t[1], t[0]))[:n_keep]
     items = items[offset:offset + limit]
     return [d for d, _ in items], [s for _, s in items], count

@@ -45,6 +45,33 @@ def _worker(rank, world, port, q):
                 ok &= count == int(oc[i])
                 ok &= docs == od[i, :on[i]].tolist()
                 ok &= bool(np.allclose(scores, os_[i, :on[i]], rtol=0, atol=1e-6))
+    # ---- OMC multipliers, offset and the all-tokens threshold go through the same single exchange
+    rng0 = np.random.default_rng(7)
+    omc_doc = np.sort(rng0.choice(n, size=400, replace=False)).astype(np.uint64)
+    omc_mult = rng0.choice([2.0, 3.0, 0.5], size=400).astype(np.float32)
+    omc = {int(d): m for d, m in zip(omc_doc, omc_mult)}
+    for mode, kw in ((2, dict(limit=5, offset=3, similarity=0.0)), (0, dict(limit=limit, offset=0, threshold=1.0)),
+                     (2, dict(limit=limit, offset=0, similarity=0.0, use_omc=True))):
+        kw = dict(kw)
+        use_omc = kw.pop("use_omc", False)
+        thr = kw.get("threshold")
+        local = [shard_spec.local_products(orc, ix, st, mode, texts[i], qv[i], kw["limit"], kw.get("similarity", 0.0), threshold=thr)
+                 for i in range(B)]
+        gathered = [None] * world
+        dist.all_gather_object(gathered, local)
+        if rank == 0:
+            full_ix, full_st = orc.StrIndex(data), orc.EmbStore(rows)
+            sb = orc.SearchBatch(full_ix, full_st)
+            for i in range(B):
+                sb.add(mode, q_vec=qv[i], text=texts[i], omc_doc=omc_doc if use_omc else None,
+                       omc_mult=omc_mult if use_omc else None, **kw)
+            od, os_, on, oc = sb.run(2)
+            for i in range(B):
+                docs, scores, count = shard_spec.merge([g[i] for g in gathered], mode, kw["limit"], kw["offset"],
+                                                       kw["limit"] + kw["offset"], omc=omc if use_omc else None)
+                ok &= count == int(oc[i])
+                ok &= docs == od[i, :on[i]].tolist()
+                ok &= bool(np.allclose(scores, os_[i, :on[i]], rtol=0, atol=1e-6))
     # ---- with a filter the corpus df is counted per shard and summed with one all_reduce before idf
     import torch
     rng = np.random.default_rng(11)
