@@ -43,6 +43,13 @@ def test_relations(orc):
     s = [add(w=w) for w in (0.5, 1.0, 1.5, 2.0, 3.0)]                       # :867-909
     assert all(b > a for a, b in zip(s, s[1:]))
     assert 1.0 < s[3] / s[1] < 1.5
+    # two fields of one doc (weights 2 and 1) beat the single-field closed form (:619-668)
+    single = orc.idf(100.0, 10) * f32(2.2) * f32(5.0) / f32(6.2)
+    assert add(w=2.0) + add(w=1.0) > single
+    # 2x field weight is a meaningful gain (:715-779: ratio > 1.05)
+    assert add(w=2.0) / add(w=1.0) > 1.05
+    # title (weight 3, tf 3, len = avg = 50) contributes more than content (weight 1, tf 3, len = avg = 200) (:781-866)
+    assert add(tf=3, len=50, avg=50.0, w=3.0) > add(tf=3, len=200, avg=200.0, w=1.0) > 0
     # canonical <= sum of per-field (:986-1043)
     idf = orc.idf(100.0, 10)
     n1, n2 = orc.normalized_tf(3, 50, 40.0), orc.normalized_tf(2, 100, 80.0)
