@@ -81,4 +81,27 @@ inline SearchOutput search(Context &ctx, oc_emb *emb, oc_str *str, const oc_sear
     return o;
 }
 
+// Micro-batching front for request tasks that call one search each (oc_batcher_*): thread-safe, blocks the
+// caller for its batch's latency.  p.n_queries must be 1.
+class SearchBatcher {
+public:
+    SearchBatcher(Context &ctx, oc_emb *emb, oc_str *str, uint32_t max_batch = 256, uint32_t max_wait_us = 200) {
+        check(oc_batcher_create(ctx.get(), emb, str, max_batch, max_wait_us, &h_));
+    }
+    ~SearchBatcher() { oc_batcher_destroy(h_); }
+    SearchBatcher(const SearchBatcher &) = delete;
+    SearchBatcher &operator=(const SearchBatcher &) = delete;
+    std::vector<TokenScore> search(const oc_search_params &p, uint64_t *count = nullptr) {
+        std::vector<uint64_t> docs(p.limit); std::vector<float> sc(p.limit);
+        uint32_t n = 0; uint64_t cnt = 0;
+        check(oc_batcher_search(h_, &p, docs.data(), sc.data(), &n, &cnt));
+        if (count) *count = cnt;
+        std::vector<TokenScore> out;
+        for (uint32_t i = 0; i < n; i++) out.push_back({docs[i], sc[i]});
+        return out;
+    }
+private:
+    oc_batcher *h_ = nullptr;
+};
+
 }  // namespace oramacore_b200
