@@ -30,8 +30,22 @@ struct BatchKey {
 inline BatchKey key_of(const oc_search_params *p) {
     return BatchKey{p->mode, p->limit, p->offset, p->similarity, p->threshold, p->bm25_k, p->bm25_b};
 }
-inline bool batchable(const oc_search_params *p) {
-    return p->n_queries == 1 && !p->filter_bits && p->n_omc == 0 && !p->sharded;
+// has_emb / has_str: the stores the batcher was created with.  A call that oc_search would reject
+// (unknown mode, missing store, NULL query arrays) is NOT batchable: it goes straight to the
+// executor so the caller gets oc_search's normal error instead of a merge that dereferences NULL.
+inline bool batchable(const oc_search_params *p, bool has_emb = true, bool has_str = true) {
+    if (p->n_queries != 1 || p->filter_bits || p->n_omc != 0 || p->sharded) return false;
+    if (p->mode != OC_MODE_FULLTEXT && p->mode != OC_MODE_VECTOR && p->mode != OC_MODE_HYBRID) return false;
+    const bool need_v = p->mode != OC_MODE_FULLTEXT, need_ft = p->mode != OC_MODE_VECTOR;
+    if (need_v && (!has_emb || !p->q_vecs)) return false;
+    if (need_ft) {
+        if (!has_str || !p->q_token_offsets) return false;
+        const uint32_t t0 = p->q_token_offsets[0], t1 = p->q_token_offsets[1];
+        if (t1 < t0) return false;
+        if (t1 > t0 && !p->token_term_offsets) return false;
+        if (t1 > t0 && p->token_term_offsets[t1] > p->token_term_offsets[t0] && (!p->term_field || !p->term_id)) return false;
+    }
+    return true;
 }
 
 struct BatchReq {
@@ -106,11 +120,11 @@ struct MergedBatch {
 template <class Exec>   // int Exec(const oc_search_params*, uint64_t* docs, float* scores, uint32_t* n, uint64_t* count)
 class Batcher {
 public:
-    Batcher(Exec exec, uint32_t dim, uint32_t max_batch, uint32_t max_wait_us)
-        : exec_(exec), dim_(dim), max_batch_(max_batch ? max_batch : 1), max_wait_us_(max_wait_us) {}
+    Batcher(Exec exec, uint32_t dim, uint32_t max_batch, uint32_t max_wait_us, bool has_emb = true, bool has_str = true)
+        : exec_(exec), dim_(dim), max_batch_(max_batch ? max_batch : 1), max_wait_us_(max_wait_us), has_emb_(has_emb), has_str_(has_str) {}
 
     int submit(const oc_search_params *p, uint64_t *docs, float *scores, uint32_t *n, uint64_t *count) {
-        if (!batchable(p) || max_batch_ == 1) {
+        if (!batchable(p, has_emb_, has_str_) || max_batch_ == 1) {
             direct_++;
             return exec_(p, docs, scores, n, count);
         }
@@ -155,6 +169,7 @@ public:
 private:
     Exec exec_;
     uint32_t dim_, max_batch_, max_wait_us_;
+    bool has_emb_, has_str_;
     std::mutex mu_;
     std::condition_variable cv_slot_, cv_leader_, cv_done_;
     std::vector<BatchReq *> pending_;

@@ -30,6 +30,25 @@ def make_vectors(n: int, dim: int, seed: int = SEED_VECTORS, chunk: int = 65536)
     return out
 
 
+def make_clustered_vectors(n: int, dim: int, n_centroids: int = 2000, sigma: float = 0.1, seed: int = SEED_VECTORS,
+                           chunk: int = 65536) -> np.ndarray:
+    """Near-duplicate clusters (the normal case for real text embeddings, and the adversarial one for a
+    low-precision candidate selection): row = c_k + sigma*N(0,I) with c_k ~ N(0,I), k uniform, so
+    cos(row, c_k) ~ 1/sqrt(1+sigma^2) (0.995 at sigma = 0.1) and two members of one cluster sit at
+    ~1/(1+sigma^2) = 0.990 with a spread of ~1e-3: hundreds of rows within 0.01 of every query's best
+    hit.  Rows of a cluster are scattered over the row space; norms vary like make_vectors'."""
+    rng = np.random.default_rng(seed)
+    cent = rng.standard_normal((n_centroids, dim), dtype=np.float32)
+    out = np.empty((n, dim), np.float32)
+    for i in range(0, n, chunk):
+        m = min(chunk, n - i)
+        k = rng.integers(0, n_centroids, size=m)
+        x = cent[k] + np.float32(sigma) * rng.standard_normal((m, dim), dtype=np.float32)
+        s = np.exp(0.25 * rng.standard_normal(m, dtype=np.float32)).astype(np.float32)
+        out[i:i + m] = x * s[:, None]
+    return out
+
+
 def make_vector_queries(rows: np.ndarray, b: int, seed: int = SEED_VQUERIES, noise: float = 0.3) -> Tuple[np.ndarray, np.ndarray]:
     """q = x_j + 0.3*N(0,I) for uniformly drawn j; returns (queries, j)."""
     rng = np.random.default_rng(seed)

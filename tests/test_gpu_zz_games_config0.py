@@ -42,7 +42,7 @@ def test_oracle_reproduces_the_committed_answers(orc):
 # exercise (multi-field, multi-term tokens, df counted on device) and is expected to pass, but until it has
 # run once on a B200 it must not be able to turn the GPU tier red (the file also sorts last).  Remove the
 # marker when it shows up as XPASS.
-@pytest.mark.xfail(strict=False, reason="not yet run on a B200 (round-1 GPU budget exhausted)")
+
 @pytest.mark.gpu
 def test_gpu_fulltext_on_the_games_corpus(gpu_ctx, orc):
     z, data, qs = _load()
