@@ -67,6 +67,9 @@ int oc_device_info(oc_ctx *ctx, int *sm_count, size_t *hbm_bytes, char *name, si
  * ANY rank's string store holds uncommitted deletes (the host runtime routes deletes, so it knows). */
 #define OC_SHARDED 1
 #define OC_SHARD_TOMBSTONES 2
+#define OC_SHARD_COUNT_DF 4      /* count corpus df across ranks (one ncclAllReduce) instead of using the per-term
+                                    global_df tables: required, on EVERY rank, while any rank's string store lacks
+                                    them (an oc_str_commit on a shard drops its table) */
 #define OC_COMM_ID_BYTES 128
 int oc_comm_unique_id(uint8_t out_id[OC_COMM_ID_BYTES]);
 int oc_comm_init(oc_ctx *ctx, int world_size, int rank, const uint8_t id[OC_COMM_ID_BYTES]);
@@ -120,14 +123,25 @@ int oc_str_load_field(oc_str *s, uint32_t field, float avg_field_len, uint32_t n
                       const uint16_t *post_len, const uint32_t *global_df);
 /* StringFieldStorage::insert(DocumentId, IndexedValue{field_length:u16, terms}) (string_field.rs:155-177),
  * with terms already resolved to the field's term ids by the host dictionary: buffered on the host,
- * visible to searches after oc_str_commit. Re-inserting a document replaces its postings in that field. */
+ * visible to searches after oc_str_commit. Re-inserting a document (before or after a commit) replaces its
+ * postings in that field: the last insert wins.  A term id may appear once per call. */
 int oc_str_insert(oc_str *s, uint32_t field, uint64_t doc_id, uint16_t field_len, uint32_t n_terms,
                   const uint32_t *term_ids, const uint16_t *tfs);
-/* == compact(version) (string_field.rs:186-191): merges pending inserts / deletes into the committed
- * device-resident layout (rows = ascending doc ids, avg_field_len and document_count refreshed). */
+/* == compact(version) (string_field.rs:186-191): merges pending inserts / deletes into the NEXT snapshot of the
+ * device-resident layout (rows = ascending doc ids; avg_field_len and document_count refreshed unless the caller
+ * owns the corpus-wide values, see oc_str_set_global) and publishes it with a pointer swap — the reference's
+ * CURRENT + versions/<n> scheme (embedding_field.rs:91-95).  The build runs WITHOUT the context lock on the
+ * store's own stream: oc_search keeps serving the previous version meanwhile.  A failed commit changes nothing
+ * (the pending ops stay queued).  One commit at a time per store. */
 int oc_str_commit(oc_str *s);
-/* StringFieldStorage::delete (string_field.rs:180-182): tombstones rows until the next commit / load. */
+/* StringFieldStorage::delete (string_field.rs:180-182).  Ops apply in call order like the reference's compact:
+ * the committed rows of the document are tombstoned at once and its still-pending inserts are cancelled; an
+ * insert after the delete is a new document. */
 int oc_str_delete(oc_str *s, const uint64_t *doc_ids, uint64_t n);
+/* This store is one shard of a larger index: document_count (N of the idf, token_score.rs:221) and
+ * avg_field_len[n_fields] (NULL = keep) are corpus-wide values owned by the caller; oc_str_commit keeps them
+ * instead of recomputing shard-local ones.  Call again after commits to refresh them. */
+int oc_str_set_global(oc_str *s, uint64_t document_count, const float *avg_field_len);
 
 typedef struct {
     uint64_t total_documents;  /* rows                              */
@@ -135,6 +149,8 @@ typedef struct {
     uint64_t unique_terms_count;
     uint32_t n_fields;
     uint64_t device_bytes;
+    uint64_t version;          /* published snapshot, bumped by every load / commit (== CURRENT)  */
+    uint64_t pending_postings; /* inserted, not yet committed (cf. pending_ops, embedding_field.rs:303-310) */
 } oc_str_info_t;
 int oc_str_info(oc_str *s, oc_str_info_t *out);
 

@@ -22,7 +22,7 @@ EXPORTED_SYMBOLS = [
     "oc_last_error", "oc_version", "oc_abi_sizes", "oc_init", "oc_shutdown", "oc_device_info", "oc_comm_unique_id",
     "oc_comm_init", "oc_emb_create", "oc_emb_destroy", "oc_emb_reserve", "oc_emb_insert", "oc_emb_delete",
     "oc_emb_info", "oc_emb_search", "oc_str_create", "oc_str_destroy", "oc_str_set_rows", "oc_str_load_field",
-    "oc_str_insert", "oc_str_commit", "oc_str_delete", "oc_str_info", "oc_search", "oc_pinned_alloc", "oc_pinned_free", "oc_last_timing", "oc_launch_count",
+    "oc_str_insert", "oc_str_commit", "oc_str_delete", "oc_str_info", "oc_str_set_global", "oc_search", "oc_pinned_alloc", "oc_pinned_free", "oc_last_timing", "oc_launch_count",
     "oc_batcher_create", "oc_batcher_destroy", "oc_batcher_search", "oc_batcher_stats",
 ]
 
@@ -40,7 +40,8 @@ class EmbInfo(C.Structure):
 
 class StrInfo(C.Structure):
     _fields_ = [("total_documents", C.c_uint64), ("total_postings", C.c_uint64),
-                ("unique_terms_count", C.c_uint64), ("n_fields", C.c_uint32), ("device_bytes", C.c_uint64)]
+                ("unique_terms_count", C.c_uint64), ("n_fields", C.c_uint32), ("device_bytes", C.c_uint64),
+                ("version", C.c_uint64), ("pending_postings", C.c_uint64)]
 
 
 class SearchParams(C.Structure):
@@ -115,6 +116,7 @@ def lib():
     L.oc_str_load_field.argtypes = [vp, u32, f32, u32, vp, vp, vp, vp, vp]
     L.oc_str_insert.argtypes = [vp, u32, u64, C.c_uint16, u32, vp, vp]
     L.oc_str_commit.argtypes = [vp]
+    L.oc_str_set_global.argtypes = [vp, u64, vp]
     L.oc_str_delete.argtypes = [vp, vp, u64]
     L.oc_str_info.argtypes = [vp, C.POINTER(StrInfo)]
     L.oc_search.argtypes = [vp, vp, vp, C.POINTER(SearchParams), vp, vp, vp, vp]

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <utility>
 #include <string>
@@ -718,36 +719,79 @@ extern "C" int oc_emb_search(oc_emb *e, const float *queries, uint32_t B, uint32
 }
 
 // ------------------------------------------------------------------------------------ string store
+// Snapshot model (the reference keeps `CURRENT` + `versions/<n>` per field and swaps the pointer after
+// compact(), embedding_field.rs:91-95 / string_field.rs:186-191): searches work on the published,
+// immutable StrSnap they grabbed at call entry; oc_str_commit builds the next snapshot WITHOUT the
+// ctx lock (host merge + upload on the store's own stream) and publishes it with a pointer swap, so
+// searches keep running on the previous version while a commit is in flight.  Ops that arrive during
+// a commit: inserts queue for the next one, deletes hit the old snapshot at once and are replayed on
+// the new one before it is published.
 struct StrField {
     float avg_len = 0;
     uint32_t n_terms = 0;
     std::vector<uint64_t> term_offsets;  // host copy (n_terms+1)
-    std::vector<uint32_t> global_df;     // optional
+    std::vector<uint32_t> global_df;     // optional: per-term corpus df across all shards
     PostingRaw *raw = nullptr;           // device: (row, tf, field_len) as loaded
     Posting *post = nullptr;             // device: (row, tf') derived for b_cached
     float b_cached = -1.f;
     uint64_t n_post = 0;
     std::vector<PostingRaw> host_post;   // host copy of the committed postings (term-major), kept for oc_str_commit
-    struct Pending { uint64_t doc; uint32_t term; uint16_t tf, len; };
-    std::vector<Pending> pending;        // StringFieldStorage::insert since the last commit
 };
-struct oc_str {
-    oc_ctx *ctx;
+struct StrSnap {
+    int device = 0;
+    uint64_t version = 0;
     std::vector<StrField> fields;
     uint64_t n_rows = 0, document_count = 0;
-    bool explicit_doc_count = false;     // set_rows gave a (global) N: commit must not overwrite it
     std::vector<uint64_t> row_doc_host;  // empty => identity
     uint64_t *row_doc = nullptr;         // device or NULL
     uint32_t *alive = nullptr;           // device bitmap (allocated on first delete)
     std::vector<uint32_t> alive_host;
     uint64_t n_deleted = 0;
+    ~StrSnap() {
+        int dev = -1;
+        cudaGetDevice(&dev);
+        if (dev != device) cudaSetDevice(device);
+        for (auto &f : fields) { cudaFree(f.post); cudaFree(f.raw); }
+        cudaFree(row_doc); cudaFree(alive);
+        if (dev >= 0 && dev != device) cudaSetDevice(dev);
+    }
+    // row of a DocumentId, or ~0ull
+    uint64_t row_of(uint64_t doc) const {
+        if (row_doc_host.empty()) return doc < n_rows ? doc : ~0ull;
+        auto it = std::lower_bound(row_doc_host.begin(), row_doc_host.end(), doc);
+        return (it == row_doc_host.end() || *it != doc) ? ~0ull : uint64_t(it - row_doc_host.begin());
+    }
 };
+struct PendingPost { uint64_t doc, seq; uint32_t term; uint16_t tf, len; };   // term == ~0u: "document inserted with no term"
+struct oc_str {
+    oc_ctx *ctx = nullptr;
+    std::mutex mu;                                   // cur / pending / logs (short critical sections; never held across device work of a search)
+    std::shared_ptr<StrSnap> cur;                    // the published snapshot ("CURRENT")
+    uint64_t version = 0;
+    std::vector<std::vector<PendingPost>> pending;   // per field: StringFieldStorage::insert since the last commit
+    uint64_t seq = 0;                                // op sequence: a delete only cancels inserts that came before it
+    std::unordered_map<uint64_t, uint64_t> pending_deleted;   // doc -> seq of its latest delete
+    bool committing = false;
+    std::vector<uint64_t> deletes_during_commit;
+    bool global_stats = false;                       // document_count / avg_field_len are corpus-wide values owned by the caller (shard of a larger index)
+    cudaStream_t load_stream = nullptr;
+};
+static std::shared_ptr<StrSnap> str_snapshot(oc_str *s) {
+    std::lock_guard<std::mutex> g(s->mu);
+    return s->cur;
+}
 
 extern "C" int oc_str_create(oc_ctx *c, uint32_t n_fields, oc_str **out) {
     if (!c || !out || n_fields == 0) return fail(OC_ERR_INVALID, "bad arguments");
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
     oc_str *s = new oc_str();
     s->ctx = c;
-    s->fields.resize(n_fields);
+    s->cur = std::make_shared<StrSnap>();
+    s->cur->device = c->device;
+    s->cur->fields.resize(n_fields);
+    s->pending.resize(n_fields);
+    CU(cudaStreamCreateWithFlags(&s->load_stream, cudaStreamNonBlocking));
     *out = s;
     return OC_OK;
 }
@@ -755,39 +799,67 @@ extern "C" void oc_str_destroy(oc_str *s) {
     if (!s) return;
     cudaSetDevice(s->ctx->device);
     cudaStreamSynchronize(s->ctx->stream);
-    for (auto &f : s->fields) { cudaFree(f.post); cudaFree(f.raw); }
-    cudaFree(s->row_doc); cudaFree(s->alive);
+    if (s->load_stream) { cudaStreamSynchronize(s->load_stream); cudaStreamDestroy(s->load_stream); }
+    s->cur.reset();
     delete s;
 }
 
+// Bulk load (oc_str_set_rows + oc_str_load_field per field) starts a fresh snapshot; both run under the
+// ctx lock, i.e. never concurrently with a search on this ctx.
 extern "C" int oc_str_set_rows(oc_str *s, uint64_t n_rows, const uint64_t *row_doc_ids, uint64_t document_count) {
     if (!s) return fail(OC_ERR_INVALID, "str is NULL");
     if (n_rows > 0xfffffff0ull) return fail(OC_ERR_UNSUPPORTED, "more than 2^32 rows per store");
     oc_ctx *c = s->ctx;
     std::lock_guard<std::mutex> g(c->mu);
     CU(cudaSetDevice(c->device));
-    cudaFree(s->row_doc); s->row_doc = nullptr; s->row_doc_host.clear();
-    cudaFree(s->alive); s->alive = nullptr; s->alive_host.clear(); s->n_deleted = 0;
-    s->n_rows = n_rows; s->document_count = document_count;
-    s->explicit_doc_count = document_count != n_rows;
-    if (row_doc_ids && n_rows) {
+    if (row_doc_ids)
         for (uint64_t i = 1; i < n_rows; i++)
             if (row_doc_ids[i] <= row_doc_ids[i - 1]) return fail(OC_ERR_INVALID, "row_doc_ids must be strictly ascending");
-        s->row_doc_host.assign(row_doc_ids, row_doc_ids + n_rows);
-        CU(cudaMalloc(&s->row_doc, n_rows * 8));
-        CU(cudaMemcpy(s->row_doc, row_doc_ids, n_rows * 8, cudaMemcpyHostToDevice));
+    auto ns = std::make_shared<StrSnap>();
+    ns->device = c->device;
+    ns->n_rows = n_rows; ns->document_count = document_count;
+    if (row_doc_ids && n_rows) {
+        ns->row_doc_host.assign(row_doc_ids, row_doc_ids + n_rows);
+        CU(cudaMalloc(&ns->row_doc, n_rows * 8));
+        CU(cudaMemcpy(ns->row_doc, row_doc_ids, n_rows * 8, cudaMemcpyHostToDevice));
     }
+    std::lock_guard<std::mutex> g2(s->mu);
+    if (s->committing) return fail(OC_ERR_INVALID, "oc_str_set_rows while a commit is in flight");
+    ns->fields.resize(s->cur->fields.size());
+    ns->version = ++s->version;
+    s->cur = ns;
+    // a document count that differs from the row count can only be a corpus-wide N (this store is a shard)
+    s->global_stats = document_count != n_rows;
+    for (auto &p : s->pending) p.clear();
+    s->pending_deleted.clear();
+    return OC_OK;
+}
+
+extern "C" int oc_str_set_global(oc_str *s, uint64_t document_count, const float *avg_field_len) {
+    if (!s) return fail(OC_ERR_INVALID, "str is NULL");
+    oc_ctx *c = s->ctx;
+    std::lock_guard<std::mutex> g(c->mu);
+    std::lock_guard<std::mutex> g2(s->mu);
+    StrSnap &S = *s->cur;
+    S.document_count = document_count;
+    if (avg_field_len)
+        for (size_t i = 0; i < S.fields.size(); i++)
+            if (S.fields[i].avg_len != avg_field_len[i]) { S.fields[i].avg_len = avg_field_len[i]; S.fields[i].b_cached = -1.f; }
+    s->global_stats = true;
     return OC_OK;
 }
 
 extern "C" int oc_str_load_field(oc_str *s, uint32_t field, float avg_field_len, uint32_t n_terms,
                                  const uint64_t *term_offsets, const uint32_t *post_row, const uint16_t *post_tf,
                                  const uint16_t *post_len, const uint32_t *global_df) {
-    if (!s || field >= s->fields.size() || !term_offsets) return fail(OC_ERR_INVALID, "bad arguments");
+    if (!s || !term_offsets) return fail(OC_ERR_INVALID, "bad arguments");
     oc_ctx *c = s->ctx;
     std::lock_guard<std::mutex> g(c->mu);
     CU(cudaSetDevice(c->device));
-    StrField &f = s->fields[field];
+    std::shared_ptr<StrSnap> snap = str_snapshot(s);
+    StrSnap &S = *snap;
+    if (field >= S.fields.size()) return fail(OC_ERR_INVALID, "field %u out of range", field);
+    StrField &f = S.fields[field];
     cudaFree(f.post); f.post = nullptr; cudaFree(f.raw); f.raw = nullptr; f.b_cached = -1.f;
     const uint64_t np = term_offsets[n_terms];
     if (np && (!post_row || !post_tf || !post_len)) return fail(OC_ERR_INVALID, "posting arrays are NULL");
@@ -797,156 +869,237 @@ extern "C" int oc_str_load_field(oc_str *s, uint32_t field, float avg_field_len,
     }
     f.avg_len = avg_field_len; f.n_terms = n_terms; f.n_post = np;
     f.host_post.resize(np);
-    for (uint64_t i = 0; i < np; i++) { f.host_post[i].row = post_row[i]; f.host_post[i].tf = post_tf[i]; f.host_post[i].len = post_len[i]; }
+    for (uint64_t i = 0; i < np; i++) {
+        if (post_row[i] >= S.n_rows && S.n_rows) return fail(OC_ERR_INVALID, "posting row %u >= n_rows", post_row[i]);
+        f.host_post[i].row = post_row[i]; f.host_post[i].tf = post_tf[i]; f.host_post[i].len = post_len[i];
+    }
     f.term_offsets.assign(term_offsets, term_offsets + n_terms + 1);
     f.global_df.clear();
     if (global_df) f.global_df.assign(global_df, global_df + n_terms);
     if (np) {
         CU(cudaMalloc(&f.post, (np + 4) * sizeof(Posting)));
         CU(cudaMalloc(&f.raw, (np + 4) * sizeof(PostingRaw)));
-        // interleave (row, tf, len) into 8-byte records through a bounded pinned staging buffer
-        const uint64_t CH = 8u << 20;
-        OCTRY(c->h_in.ensure(std::min<uint64_t>(np, CH) * sizeof(PostingRaw)));
-        for (uint64_t off = 0; off < np; off += CH) {
-            const uint64_t m = std::min<uint64_t>(CH, np - off);
-            PostingRaw *h = c->h_in.as<PostingRaw>();
-            for (uint64_t i = 0; i < m; i++) {
-                if (post_row[off + i] >= s->n_rows && s->n_rows) return fail(OC_ERR_INVALID, "posting row %u >= n_rows", post_row[off + i]);
-                h[i].row = post_row[off + i]; h[i].tf = post_tf[off + i]; h[i].len = post_len[off + i];
-            }
-            CU(cudaMemcpyAsync(f.raw + off, h, m * sizeof(PostingRaw), cudaMemcpyHostToDevice, c->stream));
-            CU(cudaStreamSynchronize(c->stream));
-        }
+        CU(cudaMemcpyAsync(f.raw, f.host_post.data(), np * sizeof(PostingRaw), cudaMemcpyHostToDevice, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
     }
     return OC_OK;
 }
 
+// tombstones `rows` of snapshot S (host bitmap + device copy on stream st)
+static int snap_tombstone(StrSnap &S, const std::vector<uint64_t> &rows, cudaStream_t st) {
+    if (rows.empty() || S.n_rows == 0) return OC_OK;
+    const uint64_t words = (S.n_rows + BM25_TILE - 1) / BM25_TILE * (BM25_TILE / 32);
+    if (S.alive_host.empty()) {
+        S.alive_host.assign(words, 0xffffffffu);
+        CU(cudaMalloc(&S.alive, words * 4));
+    }
+    for (uint64_t r : rows)
+        if (S.alive_host[r >> 5] & (1u << (r & 31))) { S.alive_host[r >> 5] &= ~(1u << (r & 31)); S.n_deleted++; }
+    CU(cudaMemcpyAsync(S.alive, S.alive_host.data(), words * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));
+    return OC_OK;
+}
+
+// StringFieldStorage::delete (string_field.rs:180-182).  Ops apply in order, as the reference's compact
+// does: a delete tombstones the committed rows of the document now and cancels its inserts that are
+// still pending (inserted before this call); an insert after the delete is a new document.
 extern "C" int oc_str_delete(oc_str *s, const uint64_t *doc_ids, uint64_t n) {
     if (!s || (!doc_ids && n)) return fail(OC_ERR_INVALID, "NULL argument");
     oc_ctx *c = s->ctx;
-    std::lock_guard<std::mutex> g(c->mu);
+    std::lock_guard<std::mutex> g(c->mu);      // the device bitmap is read by searches on the ctx stream
     CU(cudaSetDevice(c->device));
-    const uint64_t words = (s->n_rows + BM25_TILE - 1) / BM25_TILE * (BM25_TILE / 32);
-    if (s->alive_host.empty()) {
-        s->alive_host.assign(words, 0xffffffffu);
-        CU(cudaMalloc(&s->alive, words * 4));
-    }
+    std::lock_guard<std::mutex> g2(s->mu);
+    StrSnap &S = *s->cur;
+    std::vector<uint64_t> rows;
     for (uint64_t i = 0; i < n; i++) {
-        uint64_t r;
-        if (s->row_doc_host.empty()) { r = doc_ids[i]; if (r >= s->n_rows) continue; }
-        else {
-            auto it = std::lower_bound(s->row_doc_host.begin(), s->row_doc_host.end(), doc_ids[i]);
-            if (it == s->row_doc_host.end() || *it != doc_ids[i]) continue;
-            r = uint64_t(it - s->row_doc_host.begin());
-        }
-        if (s->alive_host[r >> 5] & (1u << (r & 31))) { s->alive_host[r >> 5] &= ~(1u << (r & 31)); s->n_deleted++; }
+        s->pending_deleted[doc_ids[i]] = ++s->seq;
+        if (s->committing) s->deletes_during_commit.push_back(doc_ids[i]);
+        const uint64_t r = S.row_of(doc_ids[i]);
+        if (r != ~0ull) rows.push_back(r);
     }
-    CU(cudaMemcpy(s->alive, s->alive_host.data(), words * 4, cudaMemcpyHostToDevice));
-    return OC_OK;
+    return snap_tombstone(S, rows, c->stream);
 }
 
 // StringFieldStorage::insert(DocumentId, IndexedValue{field_length, terms}) (string_field.rs:155-177):
-// buffered on the host; visible to searches after oc_str_commit (== compact, :186-191).
+// buffered on the host; visible to searches after oc_str_commit (== compact, :186-191).  Inserting a
+// document again (before or after a commit) replaces its postings in that field: last insert wins.
 extern "C" int oc_str_insert(oc_str *s, uint32_t field, uint64_t doc_id, uint16_t field_len, uint32_t n_terms,
                              const uint32_t *term_ids, const uint16_t *tfs) {
-    if (!s || field >= s->fields.size() || (n_terms && (!term_ids || !tfs))) return fail(OC_ERR_INVALID, "bad arguments");
-    std::lock_guard<std::mutex> g(s->ctx->mu);
-    StrField &f = s->fields[field];
-    for (uint32_t i = 0; i < n_terms; i++) f.pending.push_back({doc_id, term_ids[i], tfs[i], field_len});
+    if (!s || (n_terms && (!term_ids || !tfs))) return fail(OC_ERR_INVALID, "bad arguments");
+    std::lock_guard<std::mutex> g(s->mu);
+    if (field >= s->pending.size()) return fail(OC_ERR_INVALID, "field %u out of range", field);
+    for (uint32_t i = 0; i < n_terms; i++)
+        if (term_ids[i] == 0xffffffffu) return fail(OC_ERR_INVALID, "term id 0xffffffff is reserved");
+    const uint64_t q = ++s->seq;
+    auto &pv = s->pending[field];
+    if (n_terms == 0) pv.push_back({doc_id, q, 0xffffffffu, 0, field_len});
+    for (uint32_t i = 0; i < n_terms; i++) pv.push_back({doc_id, q, term_ids[i], tfs[i], field_len});
     return OC_OK;
 }
 
-static int str_upload_field(oc_str *s, StrField &f);
-
-// Merges pending inserts and deletes into the committed, device-resident layout: rows are
-// re-derived as the ascending doc ids, postings re-sorted term-major / row-ascending,
-// avg_field_len and document_count refreshed (unless a global count was given), tombstones dropped.
+// Merges pending inserts and deletes into the next snapshot: rows are the ascending doc ids, postings
+// term-major / row-ascending, avg_field_len and document_count refreshed (unless the caller owns the
+// corpus-wide values), tombstones dropped.  Everything is built in temporaries; the published snapshot
+// is replaced only after every field validated and uploaded, so a failed commit changes nothing.
 extern "C" int oc_str_commit(oc_str *s) {
     if (!s) return fail(OC_ERR_INVALID, "str is NULL");
     oc_ctx *c = s->ctx;
-    std::lock_guard<std::mutex> g(c->mu);
-    CU(cudaSetDevice(c->device));
-    // surviving old rows -> doc ids
-    std::vector<uint64_t> docs;
-    std::vector<uint8_t> old_alive(s->n_rows, 1);
-    for (uint64_t r = 0; r < s->n_rows; r++) {
-        const bool alive = s->alive_host.empty() || (s->alive_host[r >> 5] >> (r & 31)) & 1u;
-        old_alive[r] = alive;
-        if (alive) docs.push_back(s->row_doc_host.empty() ? r : s->row_doc_host[r]);
+    std::shared_ptr<StrSnap> base;
+    std::vector<std::vector<PendingPost>> pend;
+    std::unordered_map<uint64_t, uint64_t> pdel;
+    std::vector<uint32_t> base_alive;
+    bool global_stats;
+    {
+        std::lock_guard<std::mutex> g(s->mu);
+        if (s->committing) return fail(OC_ERR_INVALID, "a commit of this store is already in flight");
+        s->committing = true;
+        s->deletes_during_commit.clear();
+        base = s->cur;
+        pend.resize(s->pending.size());
+        for (size_t i = 0; i < pend.size(); i++) pend[i].swap(s->pending[i]);
+        pdel.swap(s->pending_deleted);
+        base_alive = base->alive_host;
+        global_stats = s->global_stats;
     }
-    for (auto &f : s->fields) for (auto &pn : f.pending) docs.push_back(pn.doc);
+    // on failure: put the taken ops back (in front of whatever arrived meanwhile) and leave `cur` alone
+    auto abort_commit = [&](int rc) {
+        std::lock_guard<std::mutex> g(s->mu);
+        for (size_t i = 0; i < pend.size(); i++) {
+            pend[i].insert(pend[i].end(), s->pending[i].begin(), s->pending[i].end());
+            s->pending[i].swap(pend[i]);
+        }
+        for (auto &kv : pdel) { auto it = s->pending_deleted.find(kv.first); if (it == s->pending_deleted.end() || it->second < kv.second) s->pending_deleted[kv.first] = kv.second; }
+        s->committing = false;
+        return rc;
+    };
+    if (cudaSetDevice(c->device) != cudaSuccess) return abort_commit(fail(OC_ERR_CUDA, "cudaSetDevice failed"));
+    const StrSnap &B = *base;
+    const size_t nf = B.fields.size();
+    // ---- pending ops in order: drop inserts cancelled by a later delete, keep the last insert per (field, doc)
+    for (size_t fi = 0; fi < nf; fi++) {
+        auto &pv = pend[fi];
+        std::unordered_map<uint64_t, uint64_t> last;   // doc -> seq of its last surviving insert in this field
+        for (auto &pn : pv) {
+            auto d = pdel.find(pn.doc);
+            if (d != pdel.end() && pn.seq < d->second) continue;
+            uint64_t &l = last[pn.doc];
+            if (pn.seq > l) l = pn.seq;
+        }
+        size_t w = 0;
+        for (auto &pn : pv) {
+            auto it = last.find(pn.doc);
+            if (it != last.end() && it->second == pn.seq) pv[w++] = pn;
+        }
+        pv.resize(w);
+    }
+    // ---- row space of the next snapshot
+    std::vector<uint64_t> docs;
+    std::vector<uint8_t> old_alive(B.n_rows, 1);
+    for (uint64_t r = 0; r < B.n_rows; r++) {
+        const bool alive = base_alive.empty() || ((base_alive[r >> 5] >> (r & 31)) & 1u);
+        old_alive[r] = alive;
+        if (alive) docs.push_back(B.row_doc_host.empty() ? r : B.row_doc_host[r]);
+    }
+    for (auto &pv : pend) for (auto &pn : pv) docs.push_back(pn.doc);
     std::sort(docs.begin(), docs.end());
     docs.erase(std::unique(docs.begin(), docs.end()), docs.end());
-    if (docs.size() > 0xfffffff0ull) return fail(OC_ERR_UNSUPPORTED, "more than 2^32 rows per store");
+    if (docs.size() > 0xfffffff0ull) return abort_commit(fail(OC_ERR_UNSUPPORTED, "more than 2^32 rows per store"));
     auto row_of = [&](uint64_t d) { return (uint32_t)(std::lower_bound(docs.begin(), docs.end(), d) - docs.begin()); };
-    std::vector<uint32_t> remap(s->n_rows, 0xffffffffu);
-    for (uint64_t r = 0; r < s->n_rows; r++) if (old_alive[r]) remap[r] = row_of(s->row_doc_host.empty() ? r : s->row_doc_host[r]);
+    std::vector<uint32_t> remap(B.n_rows, 0xffffffffu);
+    for (uint64_t r = 0; r < B.n_rows; r++) if (old_alive[r]) remap[r] = row_of(B.row_doc_host.empty() ? r : B.row_doc_host[r]);
+    auto ns = std::make_shared<StrSnap>();
+    ns->device = c->device;
+    ns->fields.resize(nf);
     struct Rec { uint32_t term, row; uint16_t tf, len; };
-    for (auto &f : s->fields) {
+    for (size_t fi = 0; fi < nf; fi++) {
+        const StrField &of = B.fields[fi];
+        StrField &f = ns->fields[fi];
         std::vector<Rec> recs;
-        recs.reserve(f.host_post.size() + f.pending.size());
-        // a re-inserted document replaces its old postings in this field
-        std::vector<uint8_t> replaced(docs.size(), 0);
-        for (auto &pn : f.pending) replaced[row_of(pn.doc)] = 1;
-        for (uint32_t t = 0; t < f.n_terms; t++)
-            for (uint64_t i = f.term_offsets[t]; i < f.term_offsets[t + 1]; i++) {
-                const uint32_t nr = remap[f.host_post[i].row];
-                if (nr != 0xffffffffu && !replaced[nr]) recs.push_back({t, nr, f.host_post[i].tf, f.host_post[i].len});
+        recs.reserve(of.host_post.size() + pend[fi].size());
+        std::vector<uint8_t> replaced(docs.size(), 0);   // a re-inserted document replaces its old postings in this field
+        for (auto &pn : pend[fi]) replaced[row_of(pn.doc)] = 1;
+        for (uint32_t t = 0; t < of.n_terms; t++)
+            for (uint64_t i = of.term_offsets[t]; i < of.term_offsets[t + 1]; i++) {
+                const uint32_t nr = remap[of.host_post[i].row];
+                if (nr != 0xffffffffu && !replaced[nr]) recs.push_back({t, nr, of.host_post[i].tf, of.host_post[i].len});
             }
-        uint32_t max_term = f.n_terms;
-        for (auto &pn : f.pending) { recs.push_back({pn.term, row_of(pn.doc), pn.tf, pn.len}); max_term = std::max(max_term, pn.term + 1); }
+        uint32_t max_term = of.n_terms;
+        for (auto &pn : pend[fi]) {
+            if (pn.term == 0xffffffffu) continue;
+            recs.push_back({pn.term, row_of(pn.doc), pn.tf, pn.len});
+            max_term = std::max(max_term, pn.term + 1);
+        }
         std::sort(recs.begin(), recs.end(), [](const Rec &a, const Rec &b) { return a.term != b.term ? a.term < b.term : a.row < b.row; });
         f.n_terms = max_term;
         f.term_offsets.assign(size_t(max_term) + 1, 0);
         f.host_post.resize(recs.size());
         std::vector<uint16_t> len_of_row(docs.size(), 0);
         for (size_t i = 0; i < recs.size(); i++) {
-            if (i && recs[i].term == recs[i - 1].term && recs[i].row == recs[i - 1].row) return fail(OC_ERR_INVALID, "duplicate (term, doc) posting");
+            if (i && recs[i].term == recs[i - 1].term && recs[i].row == recs[i - 1].row)
+                return abort_commit(fail(OC_ERR_INVALID, "field %zu: term %u listed twice in one insert of a document", fi, recs[i].term));
             f.term_offsets[recs[i].term + 1]++;
             f.host_post[i].row = recs[i].row; f.host_post[i].tf = recs[i].tf; f.host_post[i].len = recs[i].len;
             len_of_row[recs[i].row] = recs[i].len;
         }
         for (uint32_t t = 0; t < max_term; t++) f.term_offsets[t + 1] += f.term_offsets[t];
-        double sum = 0; uint64_t cnt = 0;
-        for (uint16_t l : len_of_row) if (l) { sum += l; cnt++; }
-        if (cnt) f.avg_len = (float)(sum / (double)cnt);   // info().avg_field_length
-        f.pending.clear();
-        f.global_df.clear();
+        f.avg_len = of.avg_len;
+        if (!global_stats) {
+            double sum = 0; uint64_t cnt = 0;
+            for (uint16_t l : len_of_row) if (l) { sum += l; cnt++; }
+            if (cnt) f.avg_len = (float)(sum / (double)cnt);   // info().avg_field_length
+        }
         f.n_post = recs.size();
+        // per-term corpus df of a shard cannot be refreshed locally: sharded searches on this snapshot count
+        // df across ranks (OC_SHARD_COUNT_DF) until the caller loads new global tables
     }
-    // rows
     const bool identity = !docs.empty() && docs.front() == 0 && docs.back() == docs.size() - 1;
-    cudaFree(s->row_doc); s->row_doc = nullptr; s->row_doc_host.clear();
-    cudaFree(s->alive); s->alive = nullptr; s->alive_host.clear(); s->n_deleted = 0;
-    if (!s->explicit_doc_count) s->document_count = docs.size();
-    s->n_rows = docs.size();
-    if (!identity && !docs.empty()) {
-        s->row_doc_host = docs;
-        CU(cudaMalloc(&s->row_doc, docs.size() * 8));
-        CU(cudaMemcpy(s->row_doc, docs.data(), docs.size() * 8, cudaMemcpyHostToDevice));
+    ns->n_rows = docs.size();
+    ns->document_count = global_stats ? B.document_count : docs.size();
+    // ---- upload on the store's own stream (searches keep the ctx stream)
+    auto upload = [&]() -> int {
+        if (!identity && !docs.empty()) {
+            ns->row_doc_host = docs;
+            CU(cudaMalloc(&ns->row_doc, docs.size() * 8));
+            CU(cudaMemcpyAsync(ns->row_doc, docs.data(), docs.size() * 8, cudaMemcpyHostToDevice, s->load_stream));
+        }
+        for (auto &f : ns->fields) {
+            const uint64_t np = f.host_post.size();
+            if (!np) continue;
+            CU(cudaMalloc(&f.post, (np + 4) * sizeof(Posting)));
+            CU(cudaMalloc(&f.raw, (np + 4) * sizeof(PostingRaw)));
+            CU(cudaMemcpyAsync(f.raw, f.host_post.data(), np * sizeof(PostingRaw), cudaMemcpyHostToDevice, s->load_stream));
+        }
+        CU(cudaStreamSynchronize(s->load_stream));
+        return OC_OK;
+    };
+    const int urc = upload();
+    if (urc != OC_OK) return abort_commit(urc);
+    // ---- publish: replay the deletes that arrived while we were building, then swap the pointer
+    {
+        std::lock_guard<std::mutex> g(s->mu);
+        std::vector<uint64_t> rows;
+        for (uint64_t d : s->deletes_during_commit) { const uint64_t r = ns->row_of(d); if (r != ~0ull) rows.push_back(r); }
+        const int trc = snap_tombstone(*ns, rows, s->load_stream);
+        if (trc != OC_OK) { s->committing = false; return trc; }   // (pending ops were consumed; the old snapshot stays published)
+        ns->version = ++s->version;
+        s->cur = ns;
+        s->deletes_during_commit.clear();
+        s->committing = false;
     }
-    for (auto &f : s->fields) OCTRY(str_upload_field(s, f));
-    return OC_OK;
-}
-
-static int str_upload_field(oc_str *s, StrField &f) {
-    oc_ctx *c = s->ctx;
-    cudaFree(f.post); f.post = nullptr; cudaFree(f.raw); f.raw = nullptr; f.b_cached = -1.f;
-    const uint64_t np = f.host_post.size();
-    if (!np) return OC_OK;
-    CU(cudaMalloc(&f.post, (np + 4) * sizeof(Posting)));
-    CU(cudaMalloc(&f.raw, (np + 4) * sizeof(PostingRaw)));
-    CU(cudaMemcpyAsync(f.raw, f.host_post.data(), np * sizeof(PostingRaw), cudaMemcpyHostToDevice, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
     return OC_OK;
 }
 
 extern "C" int oc_str_info(oc_str *s, oc_str_info_t *out) {
     if (!s || !out) return fail(OC_ERR_INVALID, "NULL argument");
-    out->total_documents = s->n_rows - s->n_deleted; out->n_fields = (uint32_t)s->fields.size();
+    std::lock_guard<std::mutex> g(s->mu);
+    const StrSnap &S = *s->cur;
+    out->total_documents = S.n_rows - S.n_deleted; out->n_fields = (uint32_t)S.fields.size();
     out->total_postings = 0; out->unique_terms_count = 0;
-    for (auto &f : s->fields) { out->total_postings += f.n_post; out->unique_terms_count += f.n_terms; }
-    out->device_bytes = out->total_postings * 16 + (s->row_doc ? s->n_rows * 8 : 0);
+    for (auto &f : S.fields) { out->total_postings += f.n_post; out->unique_terms_count += f.n_terms; }
+    out->device_bytes = out->total_postings * 16 + (S.row_doc ? S.n_rows * 8 : 0);
+    out->version = S.version;
+    out->pending_postings = 0;
+    for (auto &p : s->pending) out->pending_postings += p.size();
     return OC_OK;
 }
 
@@ -1005,6 +1158,10 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
     const uint32_t vlimit = p->limit;  // limit_hint = limit, NOT limit+offset (search.rs:330-336)
     if (p->sharded && !c->comm.ready()) return fail(OC_ERR_COMM, "sharded search without oc_comm_init");
 
+    // the published snapshot of the string store: grabbed once, immutable for the whole call (a commit may
+    // publish the next version meanwhile); declared before the lock so a last reference dies outside it
+    std::shared_ptr<StrSnap> snap = str ? str_snapshot(str) : nullptr;
+    StrSnap *S = snap.get();
     std::lock_guard<std::mutex> g(c->mu);
     CU(cudaSetDevice(c->device));
     begin_call(c);
@@ -1051,11 +1208,11 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
     const bool multi_rank = p->sharded && c->comm.world > 1;
     // sharded: every rank must take the same df decisions (they drive a collective), so the
     // tombstone state is the caller's global flag (OC_SHARD_TOMBSTONES), not this shard's
-    const bool tombs_local = has_ft && str->n_deleted > 0;
+    const bool tombs_local = has_ft && S->n_deleted > 0;
     if (multi_rank && tombs_local && !(p->sharded & OC_SHARD_TOMBSTONES))
         return fail(OC_ERR_INVALID, "sharded search: this shard holds tombstones, set OC_SHARD_TOMBSTONES on every rank");
     const bool tombs = has_ft && (multi_rank ? (p->sharded & OC_SHARD_TOMBSTONES) != 0 : tombs_local);
-    const uint32_t n_tiles = has_ft ? (uint32_t)((str->n_rows + BM25_TILE - 1) / BM25_TILE) : 0;
+    const uint32_t n_tiles = has_ft ? (uint32_t)((S->n_rows + BM25_TILE - 1) / BM25_TILE) : 0;
     std::vector<TermDesc> terms;
     std::vector<uint32_t> term_token;
     std::vector<uint64_t> term_key;     // (field << 32 | term id) of each expanded term
@@ -1065,10 +1222,14 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
     std::vector<PreDesc> pre_descs;
     std::vector<uint2> pre_items;
     bool any_multi = false, need_df = false, derived_now = false;
+    // sharded: df comes from the replicated per-term table, or — OC_SHARD_COUNT_DF on every rank, e.g. after a
+    // commit dropped the table — from counting + all-reduce.  A shard-local list length is never a corpus df.
+    const bool count_df = multi_rank && (p->sharded & OC_SHARD_COUNT_DF) != 0;
+    bool df_local_only = false;
     uint64_t postings_walked = 0;
     const bool thr = p->threshold >= 0.0f;
     if (has_ft) {
-        for (auto &f : str->fields)   // streamed posting format depends on (avg_field_len, b): derive once
+        for (auto &f : S->fields)   // streamed posting format depends on (avg_field_len, b): derive once
             if (f.n_post && f.b_cached != p->bm25_b) {
                 bm25_derive_postings_kernel<<<(unsigned)((f.n_post + 255) / 256), 256, 0, c->stream>>>(f.raw, f.n_post, f.avg_len, p->bm25_b, f.post);
                 launched(c);
@@ -1076,7 +1237,7 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
                 f.b_cached = p->bm25_b;
                 derived_now = true;   // queued on the main stream: this call keeps the BM25 prologue there too
             }
-        const float N = (float)str->document_count;  // token_score.rs:221
+        const float N = (float)S->document_count;  // token_score.rs:221
         queries.resize(B);
         for (uint32_t q = 0; q < B; q++) {
             const uint32_t t0 = p->q_token_offsets[q], t1 = p->q_token_offsets[q + 1];
@@ -1092,8 +1253,8 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
                 uint64_t df_known = 0;
                 for (uint32_t e = p->token_term_offsets[t]; e < p->token_term_offsets[t + 1]; e++) {
                     const uint32_t fi = p->term_field[e], ti = p->term_id[e];
-                    if (fi >= str->fields.size()) return fail(OC_ERR_INVALID, "term field %u out of range", fi);
-                    const StrField &f = str->fields[fi];
+                    if (fi >= S->fields.size()) return fail(OC_ERR_INVALID, "term field %u out of range", fi);
+                    const StrField &f = S->fields[fi];
                     if (ti >= f.n_terms) continue;  // unknown term: no postings
                     TermDesc td{};
                     td.ptr = f.post + f.term_offsets[ti];
@@ -1101,6 +1262,7 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
                     td.weight = p->term_weight ? p->term_weight[e] : 1.0f;
                     td.avg_len = f.avg_len;
                     df_known = f.global_df.empty() ? td.len : f.global_df[ti];
+                    if (multi_rank && f.global_df.empty()) df_local_only = true;
                     postings_walked += td.len;
                     term_key.push_back((uint64_t(fi) << 32) | ti);
                     terms.push_back(td);
@@ -1109,7 +1271,7 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
                 tk.term_end = (uint32_t)terms.size();
                 const uint32_t nt = tk.term_end - tk.term_begin;
                 uint8_t need = 0;
-                if (nt == 1 && !filter && !tombs) tk.idf = host_idf(N, std::max<uint64_t>(1, df_known));
+                if (nt == 1 && !filter && !tombs && !count_df) tk.idf = host_idf(N, std::max<uint64_t>(1, df_known));
                 else if (nt == 0) tk.idf = host_idf(N, 1);
                 else { need = 1; need_df = true; tk.idf = 0.f; }
                 if (nt != 1) { any_multi = any_multi || nt > 1; }
@@ -1119,6 +1281,9 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
             qd.token_end = (uint32_t)tokens.size();
             queries[q] = qd;
         }
+        if (df_local_only && !count_df)
+            return fail(OC_ERR_INVALID, "sharded search: a field of this shard has no corpus-wide df table (dropped by a commit?): "
+                                        "reload it or pass OC_SHARD_COUNT_DF on every rank");
         // ---- batch-level sharing of per-posting contributions (single-term tokens with a host-known idf)
         {
             struct U { uint32_t first_e; uint32_t uses; };
@@ -1178,11 +1343,11 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
         for (uint32_t i = 0; i < n_omc; i++) {
             if (i && p->omc_doc_ids[i] <= p->omc_doc_ids[i - 1]) return fail(OC_ERR_INVALID, "omc_doc_ids must be ascending");
             uint64_t r;
-            if (str->row_doc_host.empty()) { r = p->omc_doc_ids[i]; if (r >= str->n_rows) continue; }
+            if (S->row_doc_host.empty()) { r = p->omc_doc_ids[i]; if (r >= S->n_rows) continue; }
             else {
-                auto it = std::lower_bound(str->row_doc_host.begin(), str->row_doc_host.end(), p->omc_doc_ids[i]);
-                if (it == str->row_doc_host.end() || *it != p->omc_doc_ids[i]) continue;
-                r = uint64_t(it - str->row_doc_host.begin());
+                auto it = std::lower_bound(S->row_doc_host.begin(), S->row_doc_host.end(), p->omc_doc_ids[i]);
+                if (it == S->row_doc_host.end() || *it != p->omc_doc_ids[i]) continue;
+                r = uint64_t(it - S->row_doc_host.begin());
             }
             omc_rows.push_back((uint32_t)r); omc_row_mult.push_back(p->omc_mult[i]);
         }
@@ -1260,7 +1425,7 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
         if (filter || tombs) {
             OCTRY(c->row_ok.ensure(ok_words * 4));
             rows_ok_kernel<<<(unsigned)((ok_words + 255) / 256), 256, 0, ps>>>(
-                str->row_doc, str->n_rows, tombs ? str->alive : nullptr, filter_dev, p->filter_nbits,
+                S->row_doc, S->n_rows, tombs ? S->alive : nullptr, filter_dev, p->filter_nbits,
                 c->row_ok.as<uint32_t>(), ok_words);
             launched(c);
             row_ok = c->row_ok.as<uint32_t>();
@@ -1300,7 +1465,7 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
             std::vector<uint32_t> dfh(ntok);
             CU(cudaMemcpyAsync(dfh.data(), c->df_dev.p, ntok * 4, cudaMemcpyDeviceToHost, c->stream));
             CU(cudaStreamSynchronize(c->stream));
-            const float N = (float)str->document_count;
+            const float N = (float)S->document_count;
             for (size_t t = 0; t < ntok; t++)
                 if (tok_need_df[t]) tokens[t].idf = host_idf(N, std::max<uint32_t>(1u, dfh[t]));
             CU(cudaMemcpyAsync(din + o_tokens, tokens.data(), ntok * sizeof(TokenDesc), cudaMemcpyHostToDevice, c->stream));
@@ -1311,7 +1476,7 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
             OCTRY(c->v_ft.ensure(size_t(B) * vlimit * 4));
             OCTRY(c->v_present.ensure(size_t(B) * vlimit));
             map_docs_to_rows_kernel<<<(B * vlimit + 255) / 256, 256, 0, c->stream>>>(
-                c->v_doc.as<uint64_t>(), c->v_cnt.as<uint32_t>(), vlimit, B, str->row_doc, str->n_rows, c->v_srow.as<uint32_t>());
+                c->v_doc.as<uint64_t>(), c->v_cnt.as<uint32_t>(), vlimit, B, S->row_doc, S->n_rows, c->v_srow.as<uint32_t>());
             launched(c);
             CU(cudaMemsetAsync(c->v_ft.p, 0, size_t(B) * vlimit * 4, c->stream));
             CU(cudaMemsetAsync(c->v_present.p, 0, size_t(B) * vlimit, c->stream));
@@ -1332,7 +1497,7 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
         bp.queries = reinterpret_cast<const QueryDesc *>(din + o_queries);
         bp.term_token = reinterpret_cast<const uint32_t *>(din + o_ttok);
         bp.seg = c->seg.as<uint32_t>();
-        bp.n_queries = B; bp.n_tiles = n_tiles; bp.n_rows = str->n_rows;
+        bp.n_queries = B; bp.n_tiles = n_tiles; bp.n_rows = S->n_rows;
         bp.k = p->bm25_k; bp.b = p->bm25_b;
         bp.row_ok_bits = row_ok;
         bp.omc_row = omc_tile ? reinterpret_cast<const uint32_t *>(din + o_omcr) : nullptr;
@@ -1364,7 +1529,7 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
     }
     if (has_ft) {
         fp.cand_key = bp.cand_key; fp.cand_ft = bp.cand_ft; fp.cand_cnt = bp.cand_cnt; fp.tile_count = bp.tile_count;
-        fp.tile_max = bp.tile_max; fp.tile_min = bp.tile_min; fp.str_row_doc_ids = str->row_doc;
+        fp.tile_max = bp.tile_max; fp.tile_min = bp.tile_min; fp.str_row_doc_ids = S->row_doc;
     }
     if (has_v) {
         fp.v_doc = c->v_doc.as<uint64_t>(); fp.v_score = c->v_score.as<float>(); fp.v_count = c->v_cnt.as<uint32_t>();
@@ -1384,7 +1549,7 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
 
     if (p->sharded && c->comm.world > 1) {
         CU(cudaEventRecord(c->ev[EV_FUSE0], c->stream));
-        OCTRY(run_sharded_merge(c, p, fp, has_ft ? (uint32_t)str->n_rows : 0, has_v ? (uint32_t)emb->n_rows : 0, B));
+        OCTRY(run_sharded_merge(c, p, fp, has_ft ? (uint32_t)S->n_rows : 0, has_v ? (uint32_t)emb->n_rows : 0, B));
         CU(cudaEventRecord(c->ev[EV_FUSE1], c->stream));
         did_comm = true;
     } else {

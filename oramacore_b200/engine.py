@@ -235,7 +235,14 @@ class StringFieldStorage:
         i = _lib.StrInfo()
         check(lib().oc_str_info(self._h, C.byref(i)))
         return {"total_documents": i.total_documents, "total_postings": i.total_postings,
-                "unique_terms_count": i.unique_terms_count, "n_fields": i.n_fields, "device_bytes": i.device_bytes}
+                "unique_terms_count": i.unique_terms_count, "n_fields": i.n_fields, "device_bytes": i.device_bytes,
+                "version": i.version, "pending_postings": i.pending_postings}
+
+    def set_global(self, document_count: int, avg_field_len: Optional[Sequence[float]] = None):
+        """This store is one shard: N of the idf and the per-field avg_field_len are corpus-wide values
+        owned by the caller (kept across commits)."""
+        a = None if avg_field_len is None else np.ascontiguousarray(avg_field_len, np.float32)
+        check(lib().oc_str_set_global(self._h, int(document_count), _p(a)))
 
 
 class TextQueryBatch:
@@ -275,6 +282,7 @@ class TokenScoreParams:
     omc_mult: Optional[np.ndarray] = None
     sharded: bool = False
     shard_tombstones: bool = False   # OC_SHARD_TOMBSTONES: some rank's string store holds uncommitted deletes
+    shard_count_df: bool = False     # OC_SHARD_COUNT_DF: some rank's store lacks the corpus-wide df tables
 
 
 class TokenScoreContext:
@@ -336,15 +344,16 @@ class TokenScoreContext:
             om = np.ascontiguousarray(params.omc_mult, np.float32)
             keep += [od, om]
             sp.omc_doc_ids, sp.omc_mult, sp.n_omc = _p(od), _p(om), od.shape[0]
-        sp.sharded = (1 | (2 if params.shard_tombstones else 0)) if params.sharded else 0
+        sp.sharded = (1 | (2 if params.shard_tombstones else 0) | (4 if params.shard_count_df else 0)) if params.sharded else 0
         return sp, keep, B
 
     def execute(self, params: TokenScoreParams, results: Dict[int, float], text: Optional[TextQuery] = None,
                 q_vec: Optional[np.ndarray] = None) -> int:
         """Reference-shaped call: `results.extend(scores)` for one query; returns the match count.
-        Only the top (limit_hint + offset) entries are materialised (the rest never leave the GPU)."""
-        p = TokenScoreParams(**{**params.__dict__, "limit_hint": params.limit_hint + params.offset, "offset": 0})
-        hits = self.execute_batch(p, None if text is None else [text], q_vec)[0]
+        limit and offset are passed through unchanged (the vector stage's candidate depth is limit_hint =
+        limit, NOT limit + offset: search.rs:330-336), so `results` receives the rows [offset, offset+limit)
+        of the ranking — the rest of the score map never leaves the GPU."""
+        hits = self.execute_batch(params, None if text is None else [text], q_vec)[0]
         for d, s in zip(hits.doc_ids, hits.scores):
             results[int(d)] = np.float32(s)
         return hits.count
