@@ -228,10 +228,12 @@ typedef struct {
     uint64_t bm25_postings;  /* postings walked by the scorer (x8 B = algorithmic bytes)    */
     uint64_t h2d_bytes, d2h_bytes;
     uint32_t scan_tensor_core;   /* 1 => the batched tcgen05 (tf32 select + exact re-score) scan ran */
-    uint32_t scan_unproven;      /* queries whose tensor-core result failed the exactness proof and were
-                                    re-run through the exact sweep                                      */
+    uint32_t scan_unproven;      /* queries whose candidate buffers overflowed in the tensor-core scan and were
+                                    re-run through the exact sweep (device_ms includes that re-run)     */
     uint32_t scan_variant;       /* OC_SCAN_*: which sweep kernel served the batch                      */
     float scan_sweep_ms;         /* device time of the sweep launch(es) alone (scan_ms also holds the threshold pass) */
+    float rerun_ms;              /* device time of re-running flagged queries (exact sweep + second tail), in device_ms */
+    uint32_t scan_rescored;      /* rows re-scored in exact fp32 per query (batch average) by the tensor-core scan */
 } oc_timing;
 #define OC_SCAN_EXACT 0          /* emb_scan_kernel: exact fp32 sweep (B < 8, limit > 32, tiny stores)          */
 #define OC_SCAN_TC_TF32 1        /* emb_gemm_kernel: kind::tf32 on the fp32 rows, one CTA per SM               */

@@ -124,7 +124,7 @@ static bool is_pinned_host(const void *p) {
     return a.type == cudaMemoryTypeHost;
 }
 
-enum { EV_START, EV_H2D, EV_DEV, EV_D2H, EV_SCAN0, EV_SCAN1, EV_BM0, EV_BM1, EV_FUSE0, EV_FUSE1, EV_COMM0, EV_COMM1, EV_SWEEP0, EV_SWEEP1, EV_N };
+enum { EV_START, EV_H2D, EV_DEV, EV_D2H, EV_SCAN0, EV_SCAN1, EV_BM0, EV_BM1, EV_FUSE0, EV_FUSE1, EV_COMM0, EV_COMM1, EV_SWEEP0, EV_SWEEP1, EV_RR0, EV_RR1, EV_N };
 
 struct oc_ctx {
     int device = 0;
@@ -132,6 +132,7 @@ struct oc_ctx {
     cudaStream_t side = nullptr;      // descriptor upload + BM25 plan/precompute while the main stream sweeps the matrix
     cudaEvent_t ev_side = nullptr;
     bool sweep_timed = false;         // EV_SWEEP0/1 recorded in this call (tensor-core path)
+    bool rerun_timed = false;         // EV_RR0/1 recorded: flagged queries were re-run through the exact sweep
     bool side_dirty = false;          // work was queued on the side stream and not yet joined (an error path returned early)
     cudaDeviceProp prop{};
     std::mutex mu;
@@ -144,7 +145,7 @@ struct oc_ctx {
     DevBuf seg, df_dev, row_ok, tau, cand_key, cand_ft, cand_cnt, tile_cnt, tile_max, tile_min, min_hint;
     DevBuf out_blob, shard_send, shard_recv;
     bool gemm_pending = false; const float *gemm_inv_norm = nullptr;
-    DevBuf q_bf16, pre_post, g_tau, g_cand, g_cnt, g_flag, g_max, r_qpad, r_qinv, r_map, r_doc, r_score, r_row, r_cnt, r_raw;
+    DevBuf q_bf16, q_rho, pre_post, g_thr, g_eps, g_ovf, g_ovfcnt, g_resc, g_cand, g_cnt, g_flag, g_max, r_qpad, r_qinv, r_map, r_doc, r_score, r_row, r_cnt, r_raw;
 
     HostBuf h_in, h_out, h_in0;   // h_in0 / in_blob0: query vectors + filter, uploaded before the descriptors
     OcComm comm;
@@ -187,7 +188,7 @@ extern "C" void oc_shutdown(oc_ctx *c) {
     DevBuf *bufs[] = {&c->in_blob, &c->q_pad, &c->q_inv, &c->eff_norm, &c->filter_dev, &c->scan_cand, &c->v_doc,
                       &c->v_score, &c->v_row, &c->v_cnt, &c->v_srow, &c->v_ft, &c->v_present, &c->v_raw, &c->seg, &c->df_dev,
                       &c->row_ok, &c->tau, &c->cand_key, &c->cand_ft, &c->cand_cnt, &c->tile_cnt, &c->tile_max,
-                      &c->tile_min, &c->min_hint, &c->out_blob, &c->shard_send, &c->shard_recv, &c->q_bf16, &c->pre_post, &c->g_tau, &c->g_cand, &c->g_cnt, &c->g_max,
+                      &c->tile_min, &c->min_hint, &c->out_blob, &c->shard_send, &c->shard_recv, &c->q_bf16, &c->q_rho, &c->pre_post, &c->g_thr, &c->g_eps, &c->g_ovf, &c->g_ovfcnt, &c->g_resc, &c->g_cand, &c->g_cnt, &c->g_max,
                       &c->g_flag, &c->r_qpad, &c->r_qinv, &c->r_map, &c->r_doc, &c->r_score, &c->r_row, &c->r_cnt, &c->r_raw};
     for (DevBuf *b : bufs) b->release();
     c->h_in.release(); c->h_out.release();
@@ -244,6 +245,7 @@ struct oc_emb {
     uint32_t esz = 4;            // element bytes
     float *inv_norm = nullptr;   // [cap] (NaN = tombstone)
     uint64_t *row_doc = nullptr; // [cap]
+    float *rho_x = nullptr;      // device scalar: max over rows of |x - bf16(x)| / |x| (fp32 stores; the sweep's error bound)
     uint64_t n_rows = 0, cap = 0, n_live = 0;
     std::unordered_multimap<uint64_t, uint64_t> doc_rows;  // doc -> rows (for delete)
 };
@@ -257,6 +259,13 @@ extern "C" int oc_emb_create(oc_ctx *c, uint32_t dim, int dtype, int rescale_e5,
     e->esz = dtype == OC_DTYPE_BF16 ? 2 : 4;
     e->stride = ((dim + 127) / 128) * 128;
     if (e->stride / 128 == 5 || e->stride / 128 == 7) e->stride += 128;  // instantiated widths: 1,2,3,4,6,8
+    {
+        std::lock_guard<std::mutex> g(c->mu);
+        if (cudaSetDevice(c->device) != cudaSuccess || cudaMalloc(&e->rho_x, 4) != cudaSuccess || cudaMemset(e->rho_x, 0, 4) != cudaSuccess) {
+            delete e;
+            return fail(OC_ERR_CUDA, "oc_emb_create: device allocation failed");
+        }
+    }
     *out = e;
     return OC_OK;
 }
@@ -265,7 +274,7 @@ extern "C" void oc_emb_destroy(oc_emb *e) {
     if (!e) return;
     cudaSetDevice(e->ctx->device);
     cudaStreamSynchronize(e->ctx->stream);
-    cudaFree(e->rows); cudaFree(e->inv_norm); cudaFree(e->row_doc);
+    cudaFree(e->rows); cudaFree(e->inv_norm); cudaFree(e->row_doc); cudaFree(e->rho_x);
     delete e;
 }
 
@@ -311,8 +320,9 @@ extern "C" int oc_emb_insert(oc_emb *e, const uint64_t *doc_ids, const void *row
     CU(cudaMemcpyAsync(e->row_doc + e->n_rows, doc_ids, n * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
     const uint64_t warps_per_block = 8;
     const uint64_t blocks = (n + warps_per_block - 1) / warps_per_block;
-    if (e->esz == 2) emb_inv_norm_kernel<bf16_t><<<(unsigned)blocks, 256, 0, c->stream>>>(e->rows, e->stride, e->n_rows, e->n_rows + n, e->inv_norm);
-    else emb_inv_norm_kernel<float><<<(unsigned)blocks, 256, 0, c->stream>>>(e->rows, e->stride, e->n_rows, e->n_rows + n, e->inv_norm);
+    if (e->esz == 2) emb_inv_norm_kernel<bf16_t><<<(unsigned)blocks, 256, 0, c->stream>>>(e->rows, e->stride, e->n_rows, e->n_rows + n, e->inv_norm, nullptr);
+    else emb_inv_norm_kernel<float><<<(unsigned)blocks, 256, 0, c->stream>>>(e->rows, e->stride, e->n_rows, e->n_rows + n, e->inv_norm,
+                                                                             reinterpret_cast<unsigned int *>(e->rho_x));
     launched(c);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(c->stream));
@@ -498,11 +508,16 @@ static int run_vector_stage(oc_ctx *c, oc_emb *e, const float *q_dev, uint32_t B
     const uint32_t n_qgroups = (B + GEMM_M - 1) / GEMM_M, Bpad = n_qgroups * GEMM_M;
     OCTRY(c->q_pad.ensure(size_t(Bpad) * e->stride * 4));
     OCTRY(c->q_inv.ensure(size_t(Bpad) * 4));
+    OCTRY(c->q_rho.ensure(size_t(Bpad) * 4));
     const char *env = getenv("OC_DISABLE_GEMM");
     g_disable_gemm = env && env[0] == '1';
-    const bool use_gemm = !g_disable_gemm && B >= 8 && limit <= 32 && e->n_rows >= 4096;
+    // tensor-core scan: a batch (the distance is a true GEMM), a store large enough that the threshold pass sees
+    // at least `limit` row groups of <= 256 rows with data (its seeds are the limit-th largest group maximum; with
+    // fewer live groups the threshold degenerates to "gather everything" and the query falls back to the exact sweep)
+    const bool use_gemm = !g_disable_gemm && B >= 8 && limit <= GEMM_MAX_LIMIT && e->n_rows >= std::max<uint64_t>(4096, uint64_t(limit) * 256);
     if (use_gemm) CU(cudaMemsetAsync(c->q_pad.p, 0, size_t(Bpad) * e->stride * 4, c->stream));
-    emb_prep_queries_kernel<<<(B + 7) / 8, 256, 0, c->stream>>>(q_dev, e->dim, e->stride, B, c->q_pad.as<float>(), c->q_inv.as<float>());
+    emb_prep_queries_kernel<<<(B + 7) / 8, 256, 0, c->stream>>>(q_dev, e->dim, e->stride, B, c->q_pad.as<float>(), c->q_inv.as<float>(),
+                                                                c->q_rho.as<float>());
     launched(c);
     const float *inv_norm = e->inv_norm;
     if (filter_dev) {
@@ -516,7 +531,7 @@ static int run_vector_stage(oc_ctx *c, oc_emb *e, const float *q_dev, uint32_t B
     CU(cudaEventRecord(c->ev[EV_SCAN0], c->stream));
     if (!use_gemm) return run_exact_sweeps(c, e, inv_norm, c->q_pad.as<float>(), c->q_inv.as<float>(), B, limit, similarity, out);
 
-    // ---------------- K2: tcgen05 tf32 batched scan ----------------
+    // ---------------- K2: tcgen05 batched scan ----------------
     const bool bf16 = e->esz == 2;
     // NG = 2: one CTA serves two query groups against each staged X tile (one copy of X per 256 queries)
     const int NG = n_qgroups >= 2 ? 2 : 1;
@@ -532,14 +547,11 @@ static int run_vector_stage(oc_ctx *c, oc_emb *e, const float *q_dev, uint32_t B
                               : std::max<uint32_t>(1, c->prop.multiProcessorCount / n_super);
     const uint32_t grid = pair ? 2 * cpg * n_super : cpg * n_super;
     const uint32_t lists = (NG == 1 || pair) ? cpg * 2 : cpg;
+    if (lists > 512) return fail(OC_ERR_UNSUPPORTED, "%u candidate lists per query (> 512)", lists);
     // fp32 store, pair path: convert the operands to bf16 inside the SM (kind::f16 at twice the tf32 rate)
     const char *cenv = getenv("OC_GEMM_CVT");
     const bool cvt = pair && !bf16 && !(cenv && cenv[0] == '0');
-    // K' candidates re-scored per query: the proof needs cos_limit - (K'-th approx) >= eps, so the wider
-    // eps of the bf16-rounded operands takes the deeper candidate list
-    // (bf16 arithmetic: eps is 2-4x the tf32 one, so the deeper list; on 1M x 768 random-like data the proof then
-    // fails for ~1e-5 of the queries at K' = 64 against 3e-3 at K' = 48 — tests/test_proof_bounds.py)
-    const uint32_t keep = (limit > 16 || cvt || bf16) ? 64 : 32, cap = 128;   // cap == warp sort scratch; compress when > 96
+    const uint32_t cap = GEMM_LIST_CAP;
     const uint32_t Bpad2 = n_super * NG * GEMM_M;   // query rows the kernel may address (TMA zero-fills beyond the tensor)
     CUtensorMap tm_q, tm_x;
     const void *q_operand = c->q_pad.p;
@@ -552,17 +564,22 @@ static int run_vector_stage(oc_ctx *c, oc_emb *e, const float *q_dev, uint32_t B
     }
     OCTRY(make_tmap_2d(&tm_q, q_operand, Bpad, e->stride, GEMM_M, bf16 || cvt, cvt));
     OCTRY(make_tmap_2d(&tm_x, e->rows, e->n_rows, e->stride, pair ? 128 : GEMM_N, bf16));
-    OCTRY(c->g_tau.ensure(size_t(Bpad2) * 4));
+    OCTRY(c->g_thr.ensure(size_t(B) * 4));
+    OCTRY(c->g_eps.ensure(size_t(B) * 4));
     OCTRY(c->g_cand.ensure(size_t(Bpad2) * lists * cap * 8));
     OCTRY(c->g_cnt.ensure(size_t(Bpad2) * lists * 4));
+    OCTRY(c->g_ovf.ensure(size_t(B) * GEMM_OVF_CAP * 8));
+    OCTRY(c->g_ovfcnt.ensure(size_t(B) * 4));
+    OCTRY(c->g_resc.ensure(size_t(B) * 4));
     OCTRY(c->g_flag.ensure(B));
-    CU(cudaMemsetAsync(c->g_tau.p, 0, size_t(Bpad2) * 4, c->stream));
     OCTRY(c->g_max.ensure(size_t(Bpad2) * lists * 4));
+    CU(cudaMemsetAsync(c->g_ovfcnt.p, 0, size_t(B) * 4, c->stream));
     GemmParams gp{};
     gp.n_rows = e->n_rows; gp.n_kblocks = e->stride / (bf16 ? 2 * GEMM_KB : GEMM_KB); gp.inv_norm = inv_norm; gp.n_queries = B;   // cvt: 32-element K-blocks too
-    gp.n_qgroups = n_qgroups; gp.ctas_per_group = cpg; gp.keep = keep; gp.cap = cap; gp.lists_per_query = lists;
-    gp.tau = c->g_tau.as<unsigned int>(); gp.cand = c->g_cand.as<uint64_t>(); gp.cand_cnt = c->g_cnt.as<uint32_t>();
+    gp.n_qgroups = n_qgroups; gp.ctas_per_group = cpg; gp.cap = cap; gp.lists_per_query = lists;
+    gp.thr = c->g_thr.as<float>(); gp.cand = c->g_cand.as<uint64_t>(); gp.cand_cnt = c->g_cnt.as<uint32_t>();
     gp.gmax = c->g_max.as<float>();
+    gp.ovf = c->g_ovf.as<uint64_t>(); gp.ovf_cnt = c->g_ovfcnt.as<uint32_t>(); gp.ovf_cap = GEMM_OVF_CAP;
     if (smem_cfg_needed(c->device, (const void *)emb_gemm_cvt_kernel, gemm_cvt_smem_bytes())) {   // all sweep variants at once
         CU(cudaFuncSetAttribute(emb_gemm_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes(1)));
         CU(cudaFuncSetAttribute(emb_gemm_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes(2)));
@@ -571,6 +588,7 @@ static int run_vector_stage(oc_ctx *c, oc_emb *e, const float *q_dev, uint32_t B
         CU(cudaFuncSetAttribute(emb_gemm_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_pair_smem_bytes()));
         CU(cudaFuncSetAttribute(emb_gemm_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_pair_smem_bytes()));
         CU(cudaFuncSetAttribute(emb_gemm_cvt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_cvt_smem_bytes()));
+        CU(cudaFuncSetAttribute(emb_gemm_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_merge_smem_bytes()));
     }
     auto launch_gemm = [&]() -> int {
         if (cvt) emb_gemm_cvt_kernel<<<grid, CVT_THREADS, gemm_cvt_smem_bytes(), c->stream>>>(tm_q, tm_x, gp);
@@ -584,10 +602,16 @@ static int run_vector_stage(oc_ctx *c, oc_emb *e, const float *q_dev, uint32_t B
         CU(cudaGetLastError());
         return OC_OK;
     };
-    // threshold pass: one row tile per CTA, record per-list maxima, derive each query's tau
+    // threshold pass: one row tile per CTA, record per-list maxima; thr = (limit-th largest maximum) - 2 eps
     gp.max_mode = 1; gp.tile_limit = 1;
     OCTRY(launch_gemm());
-    gemm_tau_from_max_kernel<<<B, 256, 0, c->stream>>>(c->g_max.as<float>(), lists, keep, c->g_tau.as<unsigned int>());
+    GemmThrParams tp{};
+    tp.gmax = c->g_max.as<float>(); tp.lists = lists; tp.limit = limit; tp.inv_qnorm = c->q_inv.as<float>();
+    tp.eps_const = (bf16 || cvt) ? GEMM_EPS_ACC : GEMM_EPS_TF32;
+    tp.rho_x = cvt ? e->rho_x : nullptr;                          // bf16 store: the rows are exact
+    tp.rho_q = (bf16 || cvt) ? c->q_rho.as<float>() : nullptr;
+    tp.thr = c->g_thr.as<float>(); tp.eps_v = c->g_eps.as<float>();
+    gemm_thr_kernel<<<B, 256, 0, c->stream>>>(tp);
     launched(c);
     // the sweep
     gp.max_mode = 0; gp.tile_limit = 0;
@@ -598,16 +622,16 @@ static int run_vector_stage(oc_ctx *c, oc_emb *e, const float *q_dev, uint32_t B
     c->timing.scan_bytes += e->n_rows * (uint64_t(e->stride) * e->esz + 4);
     CU(cudaEventRecord(c->ev[EV_SCAN1], c->stream));
     GemmMergeParams mp{};
-    mp.cand = gp.cand; mp.cand_cnt = gp.cand_cnt; mp.tau = gp.tau; mp.ctas_per_group = lists; mp.cap = cap; mp.keep = keep; mp.limit = limit;
+    mp.cand = gp.cand; mp.cand_cnt = gp.cand_cnt; mp.n_lists = lists; mp.cap = cap; mp.limit = limit;
+    mp.ovf = gp.ovf; mp.ovf_cnt = gp.ovf_cnt; mp.ovf_cap = gp.ovf_cap; mp.eps_v = tp.eps_v;
     mp.rows = e->rows; mp.rows_bf16 = bf16 ? 1 : 0; mp.stride = e->stride; mp.inv_norm = inv_norm; mp.queries = c->q_pad.as<float>();
     mp.inv_qnorm = c->q_inv.as<float>(); mp.row_doc_ids = e->row_doc; mp.rescale_e5 = e->e5; mp.similarity = similarity;
     mp.out_doc = out.doc; mp.out_score = out.score; mp.out_row = out.row; mp.out_count = out.cnt; mp.out_raw = out.raw;
-    mp.out_unproven = c->g_flag.as<uint8_t>();
-    mp.eps = cvt ? GEMM_EPS_BF16X2 : (bf16 ? GEMM_EPS_BF16_Q : GEMM_EPS_TF32);
-    emb_gemm_merge_kernel<<<B, 512, (GEMM_MERGE_BUF + 64) * 8, c->stream>>>(mp);
+    mp.out_unproven = c->g_flag.as<uint8_t>(); mp.out_rescored = c->g_resc.as<uint32_t>();
+    emb_gemm_merge_kernel<<<B, 512, gemm_merge_smem_bytes(), c->stream>>>(mp);
     launched(c);
     CU(cudaGetLastError());
-    // the proof flags travel back with the results; oc_*search re-runs flagged queries (fix_unproven)
+    // the overflow flags travel back with the results; oc_*search re-runs flagged queries (fix_unproven)
     c->gemm_pending = true; c->gemm_inv_norm = inv_norm;
     c->timing.scan_tensor_core = 1;
     c->timing.scan_variant = cvt ? OC_SCAN_TC_CVT_PAIR : bf16 ? (pair ? OC_SCAN_TC_BF16_PAIR : OC_SCAN_TC_BF16) : (pair ? OC_SCAN_TC_TF32_PAIR : OC_SCAN_TC_TF32);
@@ -651,13 +675,14 @@ static int fix_unproven(oc_ctx *c, oc_emb *e, const uint8_t *flags, uint32_t B, 
 }
 
 static void begin_call(oc_ctx *c) {
-    c->call_launches = 0; c->call_scan_launches = 0; c->gemm_pending = false; c->sweep_timed = false;
+    c->call_launches = 0; c->call_scan_launches = 0; c->gemm_pending = false; c->sweep_timed = false; c->rerun_timed = false;
     memset(&c->timing, 0, sizeof(c->timing));
 }
 static int finish_timing(oc_ctx *c, bool scan, bool bm, bool fuse, bool comm) {
     auto el = [&](int a, int b) { float ms = 0; cudaEventElapsedTime(&ms, c->ev[a], c->ev[b]); return ms; };
     c->timing.h2d_ms = el(EV_START, EV_H2D);
-    c->timing.device_ms = el(EV_H2D, EV_DEV);
+    c->timing.rerun_ms = c->rerun_timed ? el(EV_RR0, EV_RR1) : 0.f;
+    c->timing.device_ms = el(EV_H2D, EV_DEV) + c->timing.rerun_ms;   // a re-run is device work of this batch
     c->timing.d2h_ms = el(EV_DEV, EV_D2H);
     c->timing.scan_ms = scan ? el(EV_SCAN0, EV_SCAN1) : 0;
     c->timing.scan_sweep_ms = !scan ? 0 : (c->sweep_timed ? el(EV_SWEEP0, EV_SWEEP1) : c->timing.scan_ms);
@@ -694,22 +719,35 @@ extern "C" int oc_emb_search(oc_emb *e, const float *queries, uint32_t B, uint32
                            fwords ? c->filter_dev.as<uint64_t>() : nullptr, filter_nbits));
     CU(cudaEventRecord(c->ev[EV_DEV], c->stream));
     const size_t ob = size_t(B) * limit * 12 + size_t(B) * 4;
-    OCTRY(c->h_out.ensure(ob + B));
+    const size_t o_resc = ob + ((size_t(B) + 3) & ~size_t(3));
+    OCTRY(c->h_out.ensure(o_resc + size_t(B) * 4));
     uint8_t *h = c->h_out.as<uint8_t>();
     auto fetch = [&]() -> int {
         CU(cudaMemcpyAsync(h, c->v_doc.p, size_t(B) * limit * 8, cudaMemcpyDeviceToHost, c->stream));
         CU(cudaMemcpyAsync(h + size_t(B) * limit * 8, c->v_score.p, size_t(B) * limit * 4, cudaMemcpyDeviceToHost, c->stream));
         CU(cudaMemcpyAsync(h + size_t(B) * limit * 12, c->v_cnt.p, size_t(B) * 4, cudaMemcpyDeviceToHost, c->stream));
-        if (c->gemm_pending) CU(cudaMemcpyAsync(h + ob, c->g_flag.p, B, cudaMemcpyDeviceToHost, c->stream));
+        if (c->gemm_pending) {
+            CU(cudaMemcpyAsync(h + ob, c->g_flag.p, B, cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaMemcpyAsync(h + o_resc, c->g_resc.p, size_t(B) * 4, cudaMemcpyDeviceToHost, c->stream));
+        }
         return OC_OK;
     };
     OCTRY(fetch());
     CU(cudaEventRecord(c->ev[EV_D2H], c->stream));
     CU(cudaStreamSynchronize(c->stream));
     if (c->gemm_pending) {
+        uint64_t resc = 0;
+        for (uint32_t q = 0; q < B; q++) resc += reinterpret_cast<const uint32_t *>(h + o_resc)[q];
+        c->timing.scan_rescored = (uint32_t)(resc / B);
         uint32_t redone = 0;
+        CU(cudaEventRecord(c->ev[EV_RR0], c->stream));
         OCTRY(fix_unproven(c, e, h + ob, B, limit, similarity, &redone));
-        if (redone) { c->gemm_pending = false; OCTRY(fetch()); CU(cudaStreamSynchronize(c->stream)); }
+        if (redone) {
+            c->gemm_pending = false; OCTRY(fetch());
+            CU(cudaEventRecord(c->ev[EV_RR1], c->stream));
+            c->rerun_timed = true;
+            CU(cudaStreamSynchronize(c->stream));
+        }
     }
     c->timing.d2h_bytes = ob;
     memcpy(out_doc_ids, h, size_t(B) * limit * 8);
@@ -1401,8 +1439,9 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
     const size_t o_doc = 0, o_sc = size_t(B) * p->limit * 8, o_n = o_sc + size_t(B) * p->limit * 4;
     const size_t o_cnt = (o_n + size_t(B) * 4 + 7) & ~size_t(7), o_min = o_cnt + size_t(B) * 8;
     const size_t out_bytes = o_min + size_t(B) * 4;
+    const size_t o_resc = out_bytes + ((size_t(B) + 3) & ~size_t(3));
     OCTRY(c->out_blob.ensure(out_bytes));
-    OCTRY(c->h_out.ensure(out_bytes + B));
+    OCTRY(c->h_out.ensure(o_resc + size_t(B) * 4));
     uint8_t *dout = c->out_blob.as<uint8_t>();
     FuseParams fp{};
     size_t fuse_smem = 0;
@@ -1565,16 +1604,25 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
     CU(cudaEventRecord(c->ev[EV_DEV], c->stream));
     uint8_t *h = c->h_out.as<uint8_t>();
     CU(cudaMemcpyAsync(h, dout, out_bytes, cudaMemcpyDeviceToHost, c->stream));
-    if (c->gemm_pending) CU(cudaMemcpyAsync(h + out_bytes, c->g_flag.p, B, cudaMemcpyDeviceToHost, c->stream));
+    if (c->gemm_pending) {
+        CU(cudaMemcpyAsync(h + out_bytes, c->g_flag.p, B, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(h + o_resc, c->g_resc.p, size_t(B) * 4, cudaMemcpyDeviceToHost, c->stream));
+    }
     CU(cudaEventRecord(c->ev[EV_D2H], c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    if (c->gemm_pending) {   // tensor-core scan: re-run the (rare) queries that failed the exactness proof
+    if (c->gemm_pending) {   // tensor-core scan: re-run the (rare) queries whose candidate buffers overflowed
+        uint64_t resc = 0;
+        for (uint32_t q = 0; q < B; q++) resc += reinterpret_cast<const uint32_t *>(h + o_resc)[q];
+        c->timing.scan_rescored = (uint32_t)(resc / B);
         uint32_t redone = 0;
+        CU(cudaEventRecord(c->ev[EV_RR0], c->stream));
         OCTRY(fix_unproven(c, emb, h + out_bytes, B, vlimit, p->similarity, &redone));
         if (redone) {
             c->gemm_pending = false;
             OCTRY(device_tail());
             CU(cudaMemcpyAsync(h, dout, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaEventRecord(c->ev[EV_RR1], c->stream));
+            c->rerun_timed = true;
             CU(cudaStreamSynchronize(c->stream));
         }
     }

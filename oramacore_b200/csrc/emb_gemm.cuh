@@ -44,16 +44,26 @@ constexpr uint32_t GEMM_STAGES = 4;
 constexpr uint32_t GEMM_A_BYTES = GEMM_M * 128;   // 16 KB
 constexpr uint32_t GEMM_B_BYTES = GEMM_N * 128;   // 32 KB
 constexpr uint32_t GEMM_STAGE_BYTES = GEMM_A_BYTES + GEMM_B_BYTES;
-constexpr uint32_t GEMM_MAX_KEEP = 64;            // K' upper bound (candidate buffer = 2 K')
-constexpr uint32_t GEMM_MERGE_BUF = 4096;         // keys the merge kernel sorts in shared memory
-// Rigorous bounds on |approx - exact| of the COSINE for each sweep arithmetic (tests/test_proof_bounds.py):
-// sum_i |x_i q_i| (e_x + e_q + e_x e_q) <= (e_x + e_q + e_x e_q) |x||q| (Cauchy-Schwarz), plus fp32 accumulation
-// (<= 1024 adds x 2^-23, truncating) = 1.3e-4 on the cosine.
-//   tf32: the tensor core drops the low 13 mantissa bits of both fp32 operands: e = 2^-10 each -> 1.954e-3 (+acc)
-//   bf16 store: rows exact, query rounded to nearest bf16 (8 significant bits): e_q = 2^-8    -> 3.906e-3 (+acc)
-//   fp32 rows rounded to bf16 in the SM, query rounded too: e_x = e_q = 2^-8                 -> 7.828e-3 (+acc)
-constexpr float GEMM_EPS_TF32 = 2.1e-3f;
-constexpr float GEMM_EPS_BF16_Q = 4.1e-3f;
+constexpr uint32_t GEMM_LIST_CAP = 128;           // entries of one (query, list) candidate buffer
+constexpr uint32_t GEMM_OVF_CAP = 2048;           // per-query spill area shared by its lists (global atomics; rare)
+constexpr uint32_t GEMM_MERGE_BUF = 4096;         // keys the merge kernel holds in shared memory
+constexpr uint32_t GEMM_MAX_RESCORE = 2048;       // candidates re-scored exactly per query; more => exact sweep
+constexpr uint32_t GEMM_MAX_LIMIT = 128;          // largest `limit` the tensor-core scan serves (seeds need >= limit row groups)
+// Rigorous bounds on |approx - exact| of the COSINE for each sweep arithmetic (tests/test_proof_bounds.py).
+// With x~ = x + dx, q~ = q + dq the tensor core accumulates sum x~_i q~_i, so
+//   |approx - exact| <= (rho_x + rho_q + rho_x rho_q) |x||q| + acc,   rho = |d| / |.|   (Cauchy-Schwarz),
+// acc = the fp32 accumulation of the tensor core (<= 1024 adds x 2^-23, truncating: 1.3e-4 |x||q|) plus the
+// rounding of the exact fp32 re-score it is compared with (<= 1024 x 2^-24, twice): GEMM_EPS_ACC.
+//   tf32: the tensor core drops the low 13 mantissa bits of both operands: rho <= 2^-10 each, worst case taken
+//         -> GEMM_EPS_TF32 (constant);
+//   bf16 operands (round to nearest, unit roundoff 2^-8): the worst case 2^-8 per operand is ~2.4x the actual
+//         residual norm of a rounded vector (errors are ~uniform in +-half an ulp), so the MEASURED residuals
+//         are used: rho_q per query (emb_prep_queries_kernel), rho_x = max over the rows of the store (kept by
+//         emb_inv_norm_kernel at insert; 0 for a bf16 store, whose rows are exact).  Typical: rho ~ 1.6e-3 each
+//         -> eps ~ 3.5e-3 instead of the worst-case 8.0e-3.
+constexpr float GEMM_EPS_ACC = 2.5e-4f;
+constexpr float GEMM_EPS_TF32 = 2.25e-3f;
+constexpr float GEMM_RHO_BF16_WORST = 3.90625e-3f;   // 2^-8: cap of a measured rho (a sound upper bound by itself)
 
 struct GemmParams {
     uint64_t n_rows;
@@ -62,21 +72,22 @@ struct GemmParams {
     uint32_t n_queries;        // B (real queries)
     uint32_t n_qgroups;        // ceil(B / 128)
     uint32_t ctas_per_group;   // gridDim.x / n_qgroups
-    uint32_t keep;             // K'
-    uint32_t cap;              // 2 K'
-    unsigned int *tau;         // [n_qgroups*128] ordered-uint running thresholds (init 0)
+    uint32_t cap;              // GEMM_LIST_CAP
+    const float *thr;          // [n_queries] FIXED per-query gather thresholds (cos*|q| units), from gemm_thr_kernel
     uint32_t lists_per_query;  // candidate lists per query (NG=1: 2 per row partition, NG=2: 1)
-    int max_mode;              // 1 => threshold pass: record each list's best tf32 score, push nothing
+    int max_mode;              // 1 => threshold pass: record each list's best approximate score, push nothing
     uint32_t tile_limit;       // max row tiles per CTA (0 = all); the threshold pass looks at one
     float *gmax;               // [n_qgroups*128][lists_per_query] best score per list (max_mode)
     uint64_t *cand;            // [n_qgroups*128][lists_per_query][cap]
     uint32_t *cand_cnt;        // [n_qgroups*128][lists_per_query]
+    uint64_t *ovf;             // [n_queries][ovf_cap] spill area: a full private list is appended here
+    uint32_t *ovf_cnt;         // [n_queries] (may exceed ovf_cap: the merge then sends the query to the exact sweep)
+    uint32_t ovf_cap;
 };
 
 __host__ __device__ inline size_t gemm_smem_bytes(int ng) {
     const size_t ring = ng == 1 ? size_t(4) * (GEMM_A_BYTES + GEMM_B_BYTES) : size_t(3) * (2 * GEMM_A_BYTES + GEMM_B_BYTES);
-    return 1024 /*align slack*/ + ring + 2 * GEMM_N * 4 /*inv norms*/ +
-           GEMM_EPI_WARPS * 128 * 8 /*warp sort scratch*/ + 256 /*barriers, tmem ptr*/;
+    return 1024 /*align slack*/ + ring + 2 * GEMM_N * 4 /*inv norms*/ + 256 /*barriers, tmem ptr*/;
 }
 
 // ---- tcgen05 / TMA PTX wrappers ------------------------------------------------------
@@ -156,6 +167,54 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 constexpr uint64_t TMA_EVICT_FIRST = 0x12F0000000000000ull;
 constexpr uint64_t TMA_EVICT_LAST = 0x14F0000000000000ull;
 
+// ---- the epilogue all sweep variants share: thread = TMEM lane = ONE QUERY --------------------------------
+// Reads n_chunks x 32 accumulator columns (rows rbase ..) of this thread's lane, scales by the rows' inverse
+// norms (inr: shared memory, warp-wide broadcast LDS.128) and gathers every row whose approximate score
+// clears the query's FIXED threshold into the thread's private list; a full list is appended to the query's
+// spill area (one global atomic; rare).  max_mode: only the best score is tracked (threshold pass).
+struct GemmEpi {
+    uint32_t cnt = 0;
+    float thr = 0.f;
+    float best = 0.f;
+};
+__device__ __noinline__ void gemm_spill(const GemmParams &p, uint32_t q, const uint64_t *mybuf, uint32_t cnt) {
+    const uint32_t base = atomicAdd(p.ovf_cnt + q, cnt);
+    if (base + cnt <= p.ovf_cap)
+        for (uint32_t i = 0; i < cnt; i++) p.ovf[size_t(q) * p.ovf_cap + base + i] = mybuf[i];
+}
+__device__ __forceinline__ void gemm_epilogue_tile(const GemmParams &p, uint32_t taddr, const float *inr, uint32_t n_chunks,
+                                                   uint32_t rbase, uint32_t q, uint64_t *__restrict__ mybuf, GemmEpi &e) {
+    const float4 *inr4 = reinterpret_cast<const float4 *>(inr);
+    for (uint32_t ch = 0; ch < n_chunks; ch++) {
+        uint32_t d[32];
+        tmem_ld32(taddr + ch * 32, d);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (uint32_t j4 = 0; j4 < 8; j4++) {
+            const float4 w = inr4[ch * 8 + j4];          // LDS.128, warp-wide broadcast
+            v[4 * j4 + 0] = __uint_as_float(d[4 * j4 + 0]) * w.x;   // cos * |q|
+            v[4 * j4 + 1] = __uint_as_float(d[4 * j4 + 1]) * w.y;
+            v[4 * j4 + 2] = __uint_as_float(d[4 * j4 + 2]) * w.z;
+            v[4 * j4 + 3] = __uint_as_float(d[4 * j4 + 3]) * w.w;
+        }
+        if (p.max_mode) {
+#pragma unroll
+            for (uint32_t j = 0; j < 32; j++) e.best = fmaxf(e.best, v[j]);   // NaN (dead rows) ignored
+            continue;
+        }
+        uint32_t mask = 0;
+#pragma unroll
+        for (uint32_t j = 0; j < 32; j++) mask |= (v[j] > e.thr ? 1u : 0u) << j;   // NaN fails
+        if (mask) {   // rare: a few hundred rows per query and sweep clear the threshold
+#pragma unroll
+            for (uint32_t j = 0; j < 32; j++)
+                if ((mask >> j) & 1u) { mybuf[e.cnt] = make_key(v[j], rbase + ch * 32 + j); e.cnt++; }
+            if (e.cnt + 32 > p.cap) { gemm_spill(p, q, mybuf, e.cnt); e.cnt = 0; }
+        }
+    }
+}
+
 // NG = query groups (of 128) handled by ONE CTA against each streamed row tile:
 //   NG=1: accumulator double-buffered across tiles (2 x 256 TMEM columns), 4 smem stages of 48 KB;
 //         several CTAs (one per group) walk the same rows.
@@ -172,8 +231,7 @@ emb_gemm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     constexpr uint32_t STAGE_BYTES = NG * GEMM_A_BYTES + GEMM_B_BYTES;
     uint8_t *ring = smem_gemm;
     float *inr_s = reinterpret_cast<float *>(smem_gemm + STAGES * STAGE_BYTES);   // [2][256]
-    uint64_t *scratch = reinterpret_cast<uint64_t *>(inr_s + 2 * GEMM_N);          // [8 warps][128]
-    uint64_t *bars = scratch + GEMM_EPI_WARPS * 128;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(inr_s + 2 * GEMM_N);
     uint64_t *full = bars, *empty = bars + STAGES;
     uint64_t *tfull = bars + 2 * STAGES, *tempty = tfull + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
@@ -273,10 +331,9 @@ emb_gemm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const uint32_t lists = p.lists_per_query;
         const uint32_t my_list = NG == 1 ? c * 2 + sel : c;
         uint64_t *__restrict__ mybuf = p.cand + (size_t(q) * lists + my_list) * p.cap;
-        uint64_t *wscr = scratch + ew * 128;
-        uint32_t cnt = 0;
-        float tau = live ? -INFINITY : INFINITY;
-        float best = -INFINITY;                            // max_mode: best tf32 score seen by this list
+        GemmEpi e;
+        e.thr = live ? p.thr[q] : INFINITY;                // fixed for the whole sweep (gemm_thr_kernel)
+        e.best = -INFINITY;                                // max_mode: best approximate score seen by this list
         const uint32_t ncols = NG == 1 ? 128u : 256u, col0 = NG == 1 ? sel * 128u : 0u;
         for (uint64_t it = 0; it < my_tiles; it++) {
             const uint32_t slot = NG == 1 ? uint32_t(it & 1) : sel;
@@ -287,67 +344,16 @@ emb_gemm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 const uint64_t r = row0 + et;
                 inr[et] = r < p.n_rows ? __ldg(p.inv_norm + r) : __int_as_float(0x7fc00000);
             }
-            if (live) {   // the query's threshold as raised by every CTA so far
-                const unsigned int tg = *reinterpret_cast<volatile unsigned int *>(p.tau + q);
-                if (tg) tau = fmaxf(tau, f32_unordered(tg));
-            }
             named_bar_sync(1, GEMM_EPI_WARPS * 32);
             mbar_wait(&tfull[slot], ph);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((quad * 32u) << 16) + slot * GEMM_N + col0;
-            const float4 *inr4 = reinterpret_cast<const float4 *>(inr + col0);
-            for (uint32_t ch = 0; ch < ncols / 32; ch++) {
-                uint32_t d[32];
-                tmem_ld32(taddr + ch * 32, d);
-                tmem_ld_wait();
-                float v[32];
-                uint32_t mask = 0;
-#pragma unroll
-                for (uint32_t j4 = 0; j4 < 8; j4++) {
-                    const float4 w = inr4[ch * 8 + j4];          // LDS.128, warp-wide broadcast
-                    v[4 * j4 + 0] = __uint_as_float(d[4 * j4 + 0]) * w.x;   // cos * |q|
-                    v[4 * j4 + 1] = __uint_as_float(d[4 * j4 + 1]) * w.y;
-                    v[4 * j4 + 2] = __uint_as_float(d[4 * j4 + 2]) * w.z;
-                    v[4 * j4 + 3] = __uint_as_float(d[4 * j4 + 3]) * w.w;
-                }
-                if (p.max_mode) {
-#pragma unroll
-                    for (uint32_t j = 0; j < 32; j++) best = fmaxf(best, v[j]);   // NaN (dead rows) ignored
-                    continue;
-                }
-#pragma unroll
-                for (uint32_t j = 0; j < 32; j++) mask |= (v[j] > tau ? 1u : 0u) << j;
-                if (mask) {   // rare once the threshold has warmed up
-#pragma unroll
-                    for (uint32_t j = 0; j < 32; j++)
-                        if ((mask >> j) & 1u) { mybuf[cnt] = make_key(v[j], uint32_t(row0 + col0 + ch * 32 + j)); cnt++; }
-                }
-                // warp-cooperative compress of every lane whose buffer could overflow in the next chunk
-                uint32_t need = __ballot_sync(0xffffffffu, cnt + 32 > p.cap);
-                while (need) {
-                    const uint32_t l = __ffs(need) - 1;
-                    need &= need - 1;
-                    const uint32_t lq = grp * GEMM_M + quad * 32 + l;
-                    uint64_t *lbuf = p.cand + (size_t(lq) * lists + my_list) * p.cap;
-                    const uint32_t lcnt = __shfl_sync(0xffffffffu, cnt, l);
-                    __syncwarp();
-                    for (uint32_t i = lane; i < 128; i += 32) wscr[i] = i < lcnt ? lbuf[i] : KEY_NONE;
-                    warp_bitonic_desc(wscr, 128, lane);
-                    for (uint32_t i = lane; i < p.keep; i += 32) lbuf[i] = wscr[i];
-                    __syncwarp();
-                    if (lane == l) {
-                        cnt = p.keep;
-                        tau = fmaxf(tau, key_score(wscr[p.keep - 1]));
-                        atomicMax(p.tau + q, f32_ordered(tau));
-                    }
-                    __syncwarp();
-                }
-            }
+            gemm_epilogue_tile(p, tmem_base + ((quad * 32u) << 16) + slot * GEMM_N + col0, inr + col0, ncols / 32,
+                               uint32_t(row0) + col0, q, mybuf, e);
             tc_fence_before();
             mbar_arrive(&tempty[slot]);
         }
-        if (p.max_mode) p.gmax[size_t(q) * lists + my_list] = live ? best : -INFINITY;
-        else if (grp < p.n_qgroups) p.cand_cnt[size_t(q) * lists + my_list] = live ? cnt : 0;
+        if (p.max_mode) p.gmax[size_t(q) * lists + my_list] = live ? e.best : -INFINITY;
+        else if (grp < p.n_qgroups) p.cand_cnt[size_t(q) * lists + my_list] = live ? e.cnt : 0;
     }
     __syncthreads();
     if (warp == 1) {
@@ -370,7 +376,7 @@ constexpr uint32_t PAIR_STAGE_BYTES = GEMM_A_BYTES + 2 * PAIR_HALF_B;   // 48 KB
 constexpr uint32_t PAIR_TILE_ROWS = 512;
 
 __host__ __device__ inline size_t gemm_pair_smem_bytes() {
-    return 1024 + size_t(PAIR_STAGES) * PAIR_STAGE_BYTES + 2 * PAIR_TILE_ROWS * 4 + GEMM_EPI_WARPS * 128 * 8 + 256;
+    return 1024 + size_t(PAIR_STAGES) * PAIR_STAGE_BYTES + 2 * PAIR_TILE_ROWS * 4 + 256;
 }
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -443,8 +449,7 @@ emb_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     extern __shared__ __align__(1024) uint8_t smem_gemm[];
     uint8_t *ring = smem_gemm;
     float *inr_s = reinterpret_cast<float *>(smem_gemm + PAIR_STAGES * PAIR_STAGE_BYTES);   // [2][512]
-    uint64_t *scratch = reinterpret_cast<uint64_t *>(inr_s + 2 * PAIR_TILE_ROWS);            // [8 warps][128]
-    uint64_t *bars = scratch + GEMM_EPI_WARPS * 128;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(inr_s + 2 * PAIR_TILE_ROWS);
     uint64_t *full = bars, *empty = bars + PAIR_STAGES;       // full: used in the leader only
     uint64_t *tfull = bars + 2 * PAIR_STAGES, *tempty = tfull + 2;   // tempty: used in the leader only
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
@@ -537,11 +542,10 @@ emb_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         const uint32_t lists = p.lists_per_query;
         const uint32_t my_list = c * 2 + sel;
         uint64_t *__restrict__ mybuf = p.cand + (size_t(q) * lists + my_list) * p.cap;
-        uint64_t *wscr = scratch + ew * 128;
         const uint32_t tempty_remote = mapa_shared(smem_u32(&tempty[sel]), 0);
-        uint32_t cnt = 0;
-        float tau = live ? -INFINITY : INFINITY;
-        float best = -INFINITY;
+        GemmEpi e;
+        e.thr = live ? p.thr[q] : INFINITY;
+        e.best = -INFINITY;
         for (uint64_t it = 0; it < my_tiles; it++) {
             const uint32_t ph = uint32_t(it & 1);
             const uint64_t row0 = (c + it * p.ctas_per_group) * PAIR_TILE_ROWS;
@@ -551,68 +555,17 @@ emb_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                 const uint64_t r = row0 + et + h * 256;
                 inr[et + h * 256] = r < p.n_rows ? __ldg(p.inv_norm + r) : __int_as_float(0x7fc00000);
             }
-            if (live) {
-                const unsigned int tg = *reinterpret_cast<volatile unsigned int *>(p.tau + q);
-                if (tg) tau = fmaxf(tau, f32_unordered(tg));
-            }
             named_bar_sync(1, GEMM_EPI_WARPS * 32);
             mbar_wait(&tfull[sel], ph);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((quad * 32u) << 16) + sel * 256;
-            const float4 *inr4 = reinterpret_cast<const float4 *>(inr + sel * 256);
-            const uint32_t rbase = uint32_t(row0) + sel * 256;
-            for (uint32_t ch = 0; ch < 8; ch++) {
-                uint32_t d[32];
-                tmem_ld32(taddr + ch * 32, d);
-                tmem_ld_wait();
-                float v[32];
-                uint32_t mask = 0;
-#pragma unroll
-                for (uint32_t j4 = 0; j4 < 8; j4++) {
-                    const float4 w = inr4[ch * 8 + j4];
-                    v[4 * j4 + 0] = __uint_as_float(d[4 * j4 + 0]) * w.x;
-                    v[4 * j4 + 1] = __uint_as_float(d[4 * j4 + 1]) * w.y;
-                    v[4 * j4 + 2] = __uint_as_float(d[4 * j4 + 2]) * w.z;
-                    v[4 * j4 + 3] = __uint_as_float(d[4 * j4 + 3]) * w.w;
-                }
-                if (p.max_mode) {
-#pragma unroll
-                    for (uint32_t j = 0; j < 32; j++) best = fmaxf(best, v[j]);
-                    continue;
-                }
-#pragma unroll
-                for (uint32_t j = 0; j < 32; j++) mask |= (v[j] > tau ? 1u : 0u) << j;
-                if (mask) {
-#pragma unroll
-                    for (uint32_t j = 0; j < 32; j++)
-                        if ((mask >> j) & 1u) { mybuf[cnt] = make_key(v[j], rbase + ch * 32 + j); cnt++; }
-                }
-                uint32_t need = __ballot_sync(0xffffffffu, cnt + 32 > p.cap);
-                while (need) {
-                    const uint32_t l = __ffs(need) - 1;
-                    need &= need - 1;
-                    const uint32_t lq = grp * GEMM_M + quad * 32 + l;
-                    uint64_t *lbuf = p.cand + (size_t(lq) * lists + my_list) * p.cap;
-                    const uint32_t lcnt = __shfl_sync(0xffffffffu, cnt, l);
-                    __syncwarp();
-                    for (uint32_t i = lane; i < 128; i += 32) wscr[i] = i < lcnt ? lbuf[i] : KEY_NONE;
-                    warp_bitonic_desc(wscr, 128, lane);
-                    for (uint32_t i = lane; i < p.keep; i += 32) lbuf[i] = wscr[i];
-                    __syncwarp();
-                    if (lane == l) {
-                        cnt = p.keep;
-                        tau = fmaxf(tau, key_score(wscr[p.keep - 1]));
-                        atomicMax(p.tau + q, f32_ordered(tau));
-                    }
-                    __syncwarp();
-                }
-            }
+            gemm_epilogue_tile(p, tmem_base + ((quad * 32u) << 16) + sel * 256, inr + sel * 256, 8, uint32_t(row0) + sel * 256, q,
+                               mybuf, e);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(tempty_remote);   // one arrival per warp on the leader's barrier
         }
-        if (p.max_mode) p.gmax[size_t(q) * lists + my_list] = live ? best : -INFINITY;
-        else if (grp < p.n_qgroups) p.cand_cnt[size_t(q) * lists + my_list] = live ? cnt : 0;
+        if (p.max_mode) p.gmax[size_t(q) * lists + my_list] = live ? e.best : -INFINITY;
+        else if (grp < p.n_qgroups) p.cand_cnt[size_t(q) * lists + my_list] = live ? e.cnt : 0;
     }
     tc_fence_before();
     __syncthreads();
@@ -646,7 +599,7 @@ constexpr int CVT_THREADS = GEMM_THREADS + CVT_WARPS * 32;   // warps 10-13 conv
 constexpr float GEMM_EPS_BF16X2 = 8.0e-3f;                // both operands rounded to bf16: 2*2^-8 + 2^-16 + accumulation
 
 __host__ __device__ inline size_t gemm_cvt_smem_bytes() {
-    return 1024 + size_t(CVT_STAGES) * CVT_STAGE_BYTES + 2 * PAIR_TILE_ROWS * 4 + GEMM_EPI_WARPS * 128 * 8 + 256;
+    return 1024 + size_t(CVT_STAGES) * CVT_STAGE_BYTES + 2 * PAIR_TILE_ROWS * 4 + 256;
 }
 // K-major SWIZZLE_64B descriptor: 64-byte rows, 8-row groups 512 B apart
 __device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
@@ -667,8 +620,7 @@ emb_gemm_cvt_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     //        [0, 16 KB) bf16 X ([2 tiles][128 rows][64 B], SW64); [32 KB, 40 KB) bf16 Q ([128][64 B], SW64)
     uint8_t *ring = smem_gemm;
     float *inr_s = reinterpret_cast<float *>(ring + CVT_STAGES * CVT_STAGE_BYTES);
-    uint64_t *scratch = reinterpret_cast<uint64_t *>(inr_s + 2 * PAIR_TILE_ROWS);
-    uint64_t *bars = scratch + GEMM_EPI_WARPS * 128;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(inr_s + 2 * PAIR_TILE_ROWS);
     uint64_t *raw_full = bars;                         // X tile landed (this CTA)
     uint64_t *op_full = raw_full + CVT_STAGES;         // leader only: both CTAs converted + both Q tiles landed
     uint64_t *empty = op_full + CVT_STAGES;            // MMAs that read the stage retired (multicast to both CTAs)
@@ -805,11 +757,10 @@ emb_gemm_cvt_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         const uint32_t lists = p.lists_per_query;
         const uint32_t my_list = c * 2 + sel;
         uint64_t *__restrict__ mybuf = p.cand + (size_t(q) * lists + my_list) * p.cap;
-        uint64_t *wscr = scratch + ew * 128;
         const uint32_t tempty_remote = mapa_shared(smem_u32(&tempty[sel]), 0);
-        uint32_t cnt = 0;
-        float tau = live ? -INFINITY : INFINITY;
-        float best = -INFINITY;
+        GemmEpi e;
+        e.thr = live ? p.thr[q] : INFINITY;
+        e.best = -INFINITY;
         for (uint64_t it = 0; it < my_tiles; it++) {
             const uint32_t ph = uint32_t(it & 1);
             const uint64_t row0 = (c + it * p.ctas_per_group) * PAIR_TILE_ROWS;
@@ -819,68 +770,17 @@ emb_gemm_cvt_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                 const uint64_t r = row0 + et + h * 256;
                 inr[et + h * 256] = r < p.n_rows ? __ldg(p.inv_norm + r) : __int_as_float(0x7fc00000);
             }
-            if (live) {
-                const unsigned int tg = *reinterpret_cast<volatile unsigned int *>(p.tau + q);
-                if (tg) tau = fmaxf(tau, f32_unordered(tg));
-            }
             named_bar_sync(1, GEMM_EPI_WARPS * 32);
             mbar_wait(&tfull[sel], ph);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((quad * 32u) << 16) + sel * 256;
-            const float4 *inr4 = reinterpret_cast<const float4 *>(inr + sel * 256);
-            const uint32_t rbase = uint32_t(row0) + sel * 256;
-            for (uint32_t ch = 0; ch < 8; ch++) {
-                uint32_t d[32];
-                tmem_ld32(taddr + ch * 32, d);
-                tmem_ld_wait();
-                float v[32];
-                uint32_t mask = 0;
-#pragma unroll
-                for (uint32_t j4 = 0; j4 < 8; j4++) {
-                    const float4 w = inr4[ch * 8 + j4];
-                    v[4 * j4 + 0] = __uint_as_float(d[4 * j4 + 0]) * w.x;
-                    v[4 * j4 + 1] = __uint_as_float(d[4 * j4 + 1]) * w.y;
-                    v[4 * j4 + 2] = __uint_as_float(d[4 * j4 + 2]) * w.z;
-                    v[4 * j4 + 3] = __uint_as_float(d[4 * j4 + 3]) * w.w;
-                }
-                if (p.max_mode) {
-#pragma unroll
-                    for (uint32_t j = 0; j < 32; j++) best = fmaxf(best, v[j]);
-                    continue;
-                }
-#pragma unroll
-                for (uint32_t j = 0; j < 32; j++) mask |= (v[j] > tau ? 1u : 0u) << j;
-                if (mask) {
-#pragma unroll
-                    for (uint32_t j = 0; j < 32; j++)
-                        if ((mask >> j) & 1u) { mybuf[cnt] = make_key(v[j], rbase + ch * 32 + j); cnt++; }
-                }
-                uint32_t need = __ballot_sync(0xffffffffu, cnt + 32 > p.cap);
-                while (need) {
-                    const uint32_t l = __ffs(need) - 1;
-                    need &= need - 1;
-                    const uint32_t lq = grp * GEMM_M + quad * 32 + l;
-                    uint64_t *lbuf = p.cand + (size_t(lq) * lists + my_list) * p.cap;
-                    const uint32_t lcnt = __shfl_sync(0xffffffffu, cnt, l);
-                    __syncwarp();
-                    for (uint32_t i = lane; i < 128; i += 32) wscr[i] = i < lcnt ? lbuf[i] : KEY_NONE;
-                    warp_bitonic_desc(wscr, 128, lane);
-                    for (uint32_t i = lane; i < p.keep; i += 32) lbuf[i] = wscr[i];
-                    __syncwarp();
-                    if (lane == l) {
-                        cnt = p.keep;
-                        tau = fmaxf(tau, key_score(wscr[p.keep - 1]));
-                        atomicMax(p.tau + q, f32_ordered(tau));
-                    }
-                    __syncwarp();
-                }
-            }
+            gemm_epilogue_tile(p, tmem_base + ((quad * 32u) << 16) + sel * 256, inr + sel * 256, 8, uint32_t(row0) + sel * 256, q,
+                               mybuf, e);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(tempty_remote);
+            if (lane == 0) mbar_arrive_cluster(tempty_remote);   // one arrival per warp on the leader's barrier
         }
-        if (p.max_mode) p.gmax[size_t(q) * lists + my_list] = live ? best : -INFINITY;
-        else if (grp < p.n_qgroups) p.cand_cnt[size_t(q) * lists + my_list] = live ? cnt : 0;
+        if (p.max_mode) p.gmax[size_t(q) * lists + my_list] = live ? e.best : -INFINITY;
+        else if (grp < p.n_qgroups) p.cand_cnt[size_t(q) * lists + my_list] = live ? e.cnt : 0;
     }
     tc_fence_before();
     __syncthreads();
@@ -892,12 +792,27 @@ emb_gemm_cvt_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 }
 
 // ---------------------------------------------------------------------------------------
-// Merge: best K' candidates by tf32 score -> exact fp32 re-score (K1 arithmetic) -> proof.
+// Merge: gathered candidates -> the ones that can still be in the exact top-`limit` -> exact fp32
+// re-score (K1 arithmetic) -> top-`limit`.
+//
+// Exactness argument (eps = bound on |approx - exact| of this query, in cos*|q| units):
+//   * the sweep gathered EVERY row with approx > thr, thr = LB - 2 eps, LB <= a_lim := the limit-th best
+//     approximate score of the whole store (LB is attained by `limit` distinct rows: gemm_thr_kernel), so the
+//     gathered set holds the global top-`limit` by approximate score and a_lim is known exactly;
+//   * the `limit` rows with the best approximate scores have exact >= a_lim - eps, hence the limit-th best
+//     EXACT score s* >= a_lim - eps, and a row can only belong to the exact top-`limit` if
+//     approx >= s* - eps >= a_lim - 2 eps: those rows (all gathered, since a_lim - 2 eps >= thr) are re-scored
+//     exactly and ranked.  Nothing is assumed about the distribution of the scores: near-duplicate clusters
+//     only make the re-scored set larger (the whole cluster instead of a few dozen rows).
+// The host re-runs a query through the exact sweep only if a buffer overflowed (out_unproven): more than
+// GEMM_OVF_CAP spilled candidates or more than GEMM_MAX_RESCORE rows within 2 eps of the limit-th best.
 // ---------------------------------------------------------------------------------------
 struct GemmMergeParams {
     const uint64_t *cand; const uint32_t *cand_cnt;
-    const unsigned int *tau;     // final per-query thresholds (ordered uint, 0 = never set)
-    uint32_t ctas_per_group, cap, keep, limit;
+    uint32_t n_lists, cap;
+    const uint64_t *ovf; const uint32_t *ovf_cnt; uint32_t ovf_cap;
+    const float *eps_v;          // [B] per-query eps in cos*|q| units (gemm_thr_kernel)
+    uint32_t limit;
     const void *rows; int rows_bf16; uint32_t stride; const float *inv_norm;
     const float *queries;        // [B][stride] padded fp32 (exact re-score always uses the fp32 query)
     const float *inv_qnorm;      // [B]
@@ -905,73 +820,91 @@ struct GemmMergeParams {
     int rescale_e5; float similarity;
     uint64_t *out_doc; float *out_score; uint32_t *out_row; uint32_t *out_count; float *out_raw;
     uint8_t *out_unproven;       // [B] 1 => host must re-run this query through the exact sweep
-    float eps;                   // rigorous |approx - exact| bound on the cosine for the sweep's arithmetic
+    uint32_t *out_rescored;      // [B] rows re-scored exactly (diagnostics), may be NULL
 };
+__host__ __device__ inline size_t gemm_merge_smem_bytes() { return size_t(GEMM_MERGE_BUF + GEMM_MAX_RESCORE + GEMM_MAX_LIMIT) * 8; }
 
 __global__ void __launch_bounds__(512, 2) emb_gemm_merge_kernel(const GemmMergeParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
-    uint64_t *buf = reinterpret_cast<uint64_t *>(smem);          // [GEMM_MERGE_BUF]
-    uint64_t *exact = buf + GEMM_MERGE_BUF;                       // [64]
-    __shared__ uint32_t s_cnt;
+    uint64_t *buf = reinterpret_cast<uint64_t *>(smem);          // [GEMM_MERGE_BUF] gathered approximate keys
+    uint64_t *exact = buf + GEMM_MERGE_BUF;                       // [GEMM_MAX_RESCORE] filtered keys, then exact keys
+    uint64_t *sel = exact + GEMM_MAX_RESCORE;                     // [GEMM_MAX_LIMIT]
+    __shared__ uint32_t s_cnt, s_m, s_off[512];
+    __shared__ unsigned int s_alim;
     const uint32_t q = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint64_t total = uint64_t(p.ctas_per_group) * p.cap;
-    const uint64_t *src = p.cand + size_t(q) * total;
-    const uint32_t *cnts = p.cand_cnt + size_t(q) * p.ctas_per_group;
-    // the lists are mostly empty once the thresholds have warmed up: gather the valid keys into a
-    // dense array (exclusive scan of the counts) and sort just that; stream only if it overflows
-    __shared__ uint32_t s_off[512];
-    __shared__ uint32_t s_valid;
-    uint32_t got;
-    {   // exclusive scan of the list lengths (one list per thread; blockDim.x == 512)
-        const uint32_t mine = (tid < p.ctas_per_group) ? min(cnts[tid], p.cap) : 0u;
+    const uint64_t *src = p.cand + size_t(q) * p.n_lists * p.cap;
+    const uint32_t *cnts = p.cand_cnt + size_t(q) * p.n_lists;
+    const uint64_t *osrc = p.ovf + size_t(q) * p.ovf_cap;
+    const uint32_t n_ovf_raw = p.ovf_cnt[q];
+    bool lost = n_ovf_raw > p.ovf_cap;                            // a spill did not fit: candidates are missing
+    const uint32_t n_ovf = min(n_ovf_raw, p.ovf_cap);
+    // ---- gather: exclusive scan of the list lengths (host guarantees n_lists <= 512), then the spill area
+    uint32_t nv;
+    {
+        const uint32_t mine = (tid < p.n_lists) ? min(cnts[tid], p.cap) : 0u;
         uint32_t tot;
         const uint32_t off = block_exclusive_scan(mine, &tot);
-        if (tid < 512) s_off[tid] = off;
-        if (tid == 0) s_valid = p.ctas_per_group <= 512 ? tot : 0xffffffffu;
+        s_off[tid] = off;
+        nv = tot + n_ovf;
     }
+    if (tid == 0) { s_cnt = 0; s_m = 0; s_alim = 0; }
     __syncthreads();
-    if (s_valid <= GEMM_MERGE_BUF) {
-        const uint32_t nv = s_valid;
-        const uint32_t np2 = max(64u, next_pow2(nv));
-        for (uint32_t l = tid; l < p.ctas_per_group; l += blockDim.x) {
+    const bool in_smem = nv <= GEMM_MERGE_BUF;
+    const float eps_v = p.eps_v[q];
+    float a_lim = -INFINITY;                                      // limit-th best approximate score (if there are that many)
+    if (in_smem) {
+        for (uint32_t l = tid; l < p.n_lists; l += blockDim.x) {
             const uint32_t c = min(cnts[l], p.cap), o = s_off[l];
             for (uint32_t k = 0; k < c; k++) buf[o + k] = src[size_t(l) * p.cap + k];
         }
-        if (nv <= 256u) {   // few candidates (warm thresholds): sort them all
-            for (uint32_t i = nv + tid; i < np2; i += blockDim.x) buf[i] = KEY_NONE;
-            group_bitonic_desc(buf, np2, tid, blockDim.x, 0);
-        } else {
-            // radix select of the keep largest keys, then a one-warp sort of those
-            uint64_t *sel = exact;   // [64] scratch, re-initialised below
-            for (uint32_t i = tid; i < 64; i += blockDim.x) sel[i] = KEY_NONE;
+        for (uint32_t i = tid; i < n_ovf; i += blockDim.x) buf[nv - n_ovf + i] = osrc[i];
+        __syncthreads();
+        if (nv >= p.limit) {
+            const uint32_t got = block_select_largest(buf, nv, p.limit, sel);   // unsorted
+            uint64_t mn = ~0ull;
+            for (uint32_t i = tid; i < got; i += blockDim.x) mn = min(mn, sel[i]);
+            for (int o = 16; o > 0; o >>= 1) mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            if (lane == 0 && mn != ~0ull) atomicMax(&s_alim, ~uint32_t(mn >> 32));   // min of keys == max of complemented score bits
             __syncthreads();
-            block_select_largest(buf, nv, p.keep, sel);
-            if (warp == 0) warp_bitonic_desc(sel, 64, lane);
-            __syncthreads();
-            for (uint32_t i = tid; i < 64; i += blockDim.x) buf[i] = sel[i];
-            __syncthreads();
+            a_lim = f32_unordered(~s_alim);
         }
-        got = min(nv, p.keep);
     } else {
-        got = block_topn_stream(buf, GEMM_MERGE_BUF, p.keep, total, [&](uint64_t i) -> uint64_t {
-            const uint32_t cta = uint32_t(i / p.cap), k = uint32_t(i % p.cap);
-            return k < cnts[cta] ? src[i] : KEY_NONE;
+        // too many candidates for shared memory (degenerate thresholds): stream them
+        const uint64_t total = uint64_t(p.n_lists) * p.cap + n_ovf;
+        const uint32_t got = block_topn_stream(buf, GEMM_MERGE_BUF, p.limit, total, [&](uint64_t i) -> uint64_t {
+            if (i >= uint64_t(p.n_lists) * p.cap) return osrc[i - uint64_t(p.n_lists) * p.cap];
+            const uint32_t l = uint32_t(i / p.cap), k = uint32_t(i % p.cap);
+            return k < min(cnts[l], p.cap) ? src[i] : KEY_NONE;
         });
+        if (got == p.limit) a_lim = key_score(buf[p.limit - 1]);
+        __syncthreads();
     }
-    const float iqn = p.inv_qnorm[q];
-    // bound on the tf32 score (cos*|q| units) of every row OUTSIDE the selected candidates:
-    // rows never pushed were <= the query's threshold at that time <= its final value; rows
-    // dropped by a compress or by the top-K' selection above are <= the K'-th selected score.
-    const unsigned int tq = p.tau[q];
-    float bound_v = tq ? f32_unordered(tq) : -INFINITY;
-    if (got == p.keep) bound_v = fmaxf(bound_v, key_score(buf[p.keep - 1]));
-    // exact fp32 re-score, one warp per candidate, K1's lane layout and FMA order
-    for (uint32_t i = tid; i < 64; i += blockDim.x) exact[i] = KEY_NONE;
-    if (tid == 0) s_cnt = 0;
+    // ---- filter: only rows with approx >= a_lim - 2 eps can reach the exact top-`limit`
+    const float cut = (a_lim == -INFINITY) ? -INFINITY : a_lim - 2.0f * eps_v;   // eps_v = inf (zero query) -> -inf
+    auto stage = [&](uint64_t k) {
+        if (k != KEY_NONE && key_score(k) >= cut) {
+            const uint32_t s = atomicAdd(&s_m, 1u);
+            if (s < GEMM_MAX_RESCORE) exact[s] = k;
+        }
+    };
+    if (in_smem) {
+        for (uint32_t i = tid; i < nv; i += blockDim.x) stage(buf[i]);
+    } else {
+        for (uint32_t l = warp; l < p.n_lists; l += blockDim.x / 32) {
+            const uint32_t c = min(cnts[l], p.cap);
+            for (uint32_t k = lane; k < c; k += 32) stage(src[size_t(l) * p.cap + k]);
+        }
+        for (uint32_t i = tid; i < n_ovf; i += blockDim.x) stage(osrc[i]);
+    }
     __syncthreads();
+    const uint32_t m_raw = s_m;
+    if (m_raw > GEMM_MAX_RESCORE) lost = true;
+    const uint32_t M = min(m_raw, GEMM_MAX_RESCORE);
+    // ---- exact fp32 re-score, one warp per candidate, K1's lane layout and FMA order
+    const float iqn = p.inv_qnorm[q];
     const float4 *qp = reinterpret_cast<const float4 *>(p.queries + size_t(q) * p.stride);
-    for (uint32_t i = warp; i < got; i += blockDim.x / 32) {   // one warp per candidate (32 warps)
-        const uint32_t row = key_idx(buf[i]);
+    for (uint32_t i = warp; i < M; i += blockDim.x / 32) {
+        const uint32_t row = key_idx(exact[i]);
         const void *rp = static_cast<const uint8_t *>(p.rows) + size_t(row) * p.stride * (p.rows_bf16 ? 2 : 4);
         // all row loads are issued before the first use (the rows were streamed evict-first: DRAM latency)
         float4 xr[8];
@@ -989,18 +922,23 @@ __global__ void __launch_bounds__(512, 2) emb_gemm_merge_kernel(const GemmMergeP
         const float dot = warp_sum(acc);
         const float cosv = dot * p.inv_norm[row] * iqn;
         const float kf = -(1.0f - cosv);
+        __syncwarp();
         if (lane == 0) exact[i] = make_key(kf, row);
     }
     __syncthreads();
-    if (warp == 0) warp_bitonic_desc(exact, 64, lane);
-    __syncthreads();
-    const uint32_t n_top = min(got, p.limit);
-    // proof: every outside row has exact cos <= bound_v*iqn + eps; the answer is exact when the
-    // limit-th exact cosine clears that (or when nothing was ever excluded)
-    bool proven = bound_v == -INFINITY;
-    if (!proven && n_top == p.limit) {
-        const float c_lim = 1.0f + key_score(exact[p.limit - 1]);   // cos = 1 - distance
-        proven = c_lim >= bound_v * iqn + p.eps;
+    // ---- rank the exact keys: sort all when few, else select the best `limit` and sort those
+    const uint32_t n_top = min(M, p.limit);
+    if (M <= 256) {
+        const uint32_t np2 = max(32u, next_pow2(M));
+        for (uint32_t i = M + tid; i < np2; i += blockDim.x) exact[i] = KEY_NONE;
+        group_bitonic_desc(exact, np2, tid, blockDim.x, 0);
+    } else {
+        for (uint32_t i = tid; i < GEMM_MAX_LIMIT; i += blockDim.x) sel[i] = KEY_NONE;
+        __syncthreads();
+        block_select_largest(exact, M, p.limit, sel);
+        group_bitonic_desc(sel, GEMM_MAX_LIMIT, tid, blockDim.x, 0);
+        for (uint32_t i = tid; i < GEMM_MAX_LIMIT; i += blockDim.x) exact[i] = sel[i];
+        __syncthreads();
     }
     for (uint32_t i = tid; i < p.limit; i += blockDim.x) {
         uint64_t doc = 0; float score = 0.f, raw = 0.f; uint32_t row = 0xffffffffu;
@@ -1022,24 +960,46 @@ __global__ void __launch_bounds__(512, 2) emb_gemm_merge_kernel(const GemmMergeP
         if (p.out_raw) p.out_raw[size_t(q) * p.limit + i] = raw;
     }
     __syncthreads();
-    if (tid == 0) { p.out_count[q] = s_cnt; p.out_unproven[q] = proven ? 0 : 1; }
+    if (tid == 0) {
+        p.out_count[q] = s_cnt;
+        p.out_unproven[q] = lost ? 1 : 0;
+        if (p.out_rescored) p.out_rescored[q] = M;
+    }
 }
 
-// Threshold pass, step 2: every list of the threshold pass reported the best tf32 score of a
-// disjoint group of rows; the keep-th largest of those group maxima is attained by `keep`
-// distinct rows, hence a valid lower bound of the query's global keep-th best tf32 score —
-// in the same arithmetic the sweep compares with (no error margin needed).
-__global__ void __launch_bounds__(256) gemm_tau_from_max_kernel(const float *gmax, uint32_t lists, uint32_t keep,
-                                                                unsigned int *tau) {
+// Threshold pass, step 2.  Every list of the threshold pass reported the best approximate score of a
+// disjoint group of rows; the limit-th largest of those group maxima is attained by `limit` distinct rows,
+// hence a valid lower bound LB of the query's global limit-th best approximate score — in the same
+// arithmetic the sweep compares with.  The sweep gathers every row above thr = LB - 2 eps (see the merge).
+// eps (cosine) = eps_const + rho_x + rho_q + rho_x rho_q, scaled to the sweep's cos*|q| units.
+struct GemmThrParams {
+    const float *gmax; uint32_t lists, limit;
+    const float *inv_qnorm;
+    float eps_const;
+    const float *rho_x;       // device scalar: max relative bf16 residual norm over the store's rows, or NULL
+    const float *rho_q;       // [B] relative bf16 residual norm of each query, or NULL
+    float *thr, *eps_v;       // [B] outputs
+};
+__global__ void __launch_bounds__(256) gemm_thr_kernel(const GemmThrParams p) {
     __shared__ uint64_t keys[512];
     const uint32_t q = blockIdx.x, tid = threadIdx.x;
-    const uint32_t n = min(lists, 512u), np2 = max(64u, next_pow2(n));
+    const uint32_t n = min(p.lists, 512u), np2 = max(64u, next_pow2(n));
     for (uint32_t i = tid; i < np2; i += blockDim.x) {
-        const float v = i < n ? gmax[size_t(q) * lists + i] : -INFINITY;
+        const float v = i < n ? p.gmax[size_t(q) * p.lists + i] : -INFINITY;
         keys[i] = (v == v && v > -INFINITY) ? make_key(v, i) : KEY_NONE;
     }
     group_bitonic_desc(keys, np2, tid, blockDim.x, 0);
-    if (tid == 0 && n >= keep && keys[keep - 1] != KEY_NONE) tau[q] = f32_ordered(key_score(keys[keep - 1]));
+    if (tid == 0) {
+        const float rx = p.rho_x ? fminf(*p.rho_x, GEMM_RHO_BF16_WORST) : 0.f;
+        const float rq = p.rho_q ? fminf(p.rho_q[q], GEMM_RHO_BF16_WORST) : 0.f;
+        const float eps_cos = p.eps_const + rx + rq + rx * rq;
+        const float iqn = p.inv_qnorm[q];
+        const float ev = iqn > 0.f ? __fdiv_ru(eps_cos, iqn) : INFINITY;
+        float thr = -INFINITY;
+        if (n >= p.limit && keys[p.limit - 1] != KEY_NONE && ev < INFINITY) thr = key_score(keys[p.limit - 1]) - 2.0f * ev;
+        p.thr[q] = thr;
+        p.eps_v[q] = ev;
+    }
 }
 
 // fp32 -> bf16 (round to nearest even) of the padded queries: the B operand of the bf16 sweep

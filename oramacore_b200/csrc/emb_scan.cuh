@@ -207,36 +207,60 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) emb_scan_kernel(const ScanPar
 // ---------------------------------------------------------------------------------------
 // Row preparation: inverse L2 norms of newly inserted rows (one warp per row).
 // ---------------------------------------------------------------------------------------
+// round-to-nearest-even bf16 of an fp32 value, as the fp32 it denotes (what cvt.rn.bf16x2.f32 produces)
+__device__ __forceinline__ float bf16_round_f32(float x) {
+    const uint32_t u = __float_as_uint(x);
+    const uint32_t r = ((u & 0x7fffffffu) > 0x7f800000u) ? (u | 0x00400000u) : (u + 0x7fffu + ((u >> 16) & 1u));
+    return __uint_as_float(r & 0xffff0000u);
+}
+// rho_max (optional, fp32 stores): running max over the rows of |x - bf16(x)| / |x|, the relative residual norm
+// of rounding the row to bf16 — the store-side term of the tensor-core sweep's error bound (emb_gemm.cuh).
+// Kept as the bits of a non-negative float (ordered like unsigned ints); padded 0.1 % for the fp32 sums.
 template <typename T>
 __global__ void emb_inv_norm_kernel(const void *rows, uint32_t stride, uint64_t row_begin, uint64_t row_end,
-                                    float *inv_norm) {
+                                    float *inv_norm, unsigned int *rho_max) {
     const uint64_t r = row_begin + (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) / 32;
     const uint32_t lane = threadIdx.x & 31;
     if (r >= row_end) return;
     const void *rp = static_cast<const uint8_t *>(rows) + r * stride * RowLoad<T>::ESZ;
-    float s = 0.f;
+    float s = 0.f, sd = 0.f;
     for (uint32_t j = lane; j < stride / 4; j += 32) {
         const float4 x = RowLoad<T>::ld(rp, j);
         s = fmaf(x.x, x.x, s); s = fmaf(x.y, x.y, s); s = fmaf(x.z, x.z, s); s = fmaf(x.w, x.w, s);
+        if (rho_max) {
+            const float a = x.x - bf16_round_f32(x.x), b = x.y - bf16_round_f32(x.y);
+            const float c = x.z - bf16_round_f32(x.z), d = x.w - bf16_round_f32(x.w);
+            sd = fmaf(a, a, sd); sd = fmaf(b, b, sd); sd = fmaf(c, c, sd); sd = fmaf(d, d, sd);
+        }
     }
     s = warp_sum(s);
-    if (lane == 0) inv_norm[r] = s > 0.f ? 1.0f / sqrtf(s) : 0.f;
+    if (rho_max) sd = warp_sum(sd);
+    if (lane == 0) {
+        inv_norm[r] = s > 0.f ? 1.0f / sqrtf(s) : 0.f;
+        if (rho_max && s > 0.f) atomicMax(rho_max, __float_as_uint(sqrtf(sd / s) * 1.001f));
+    }
 }
 
-// Query preparation: zero-pad to stride and compute 1/|q| (one warp per query).
+// Query preparation: zero-pad to stride, 1/|q| and (optional) rho_q = |q - bf16(q)| / |q| (one warp per query).
 __global__ void emb_prep_queries_kernel(const float *q_in, uint32_t dim, uint32_t stride, uint32_t nq,
-                                        float *q_out, float *inv_qnorm) {
+                                        float *q_out, float *inv_qnorm, float *rho_q) {
     const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x & 31;
     if (q >= nq) return;
-    float s = 0.f;
+    float s = 0.f, sd = 0.f;
 #pragma unroll 8
     for (uint32_t j = lane; j < stride; j += 32) {
         const float v = j < dim ? __ldg(q_in + size_t(q) * dim + j) : 0.f;
         q_out[size_t(q) * stride + j] = v;
         s = fmaf(v, v, s);
+        const float d = v - bf16_round_f32(v);
+        sd = fmaf(d, d, sd);
     }
     s = warp_sum(s);
-    if (lane == 0) inv_qnorm[q] = s > 0.f ? 1.0f / sqrtf(s) : 0.f;
+    sd = warp_sum(sd);
+    if (lane == 0) {
+        inv_qnorm[q] = s > 0.f ? 1.0f / sqrtf(s) : 0.f;
+        if (rho_q) rho_q[q] = s > 0.f ? sqrtf(sd / s) * 1.001f : 0.f;
+    }
 }
 
 // Effective inverse norms under a DocumentId filter bitmap (FilterResult::contains,

@@ -1,6 +1,8 @@
-"""K2 (tcgen05 tf32 batched scan + exact re-score + proof) against K1 (exact sweep) and the oracle.
-The tensor-core path must return bit-identical hits to the exact path: tf32 only selects
-candidates; every returned score is re-computed with K1's fp32 arithmetic."""
+"""K2 (tcgen05 batched scan: gather every row within 2*eps of the limit-th best approximate score, exact
+re-score of those) against K1 (exact sweep) and the oracle.  The tensor-core path must return bit-identical
+hits to the exact path: the low-precision sweep only selects candidates; every returned score is
+re-computed with K1's fp32 arithmetic.  Includes the adversarial inputs for a selection scheme:
+near-duplicate clusters, exact duplicates, large limits."""
 import os
 
 import numpy as np
@@ -119,4 +121,77 @@ def test_bf16_store_parity(gpu_ctx, orc, monkeypatch, n, dim, model, B, pair):
         finally:
             os.environ.pop("OC_DISABLE_GEMM", None)
         assert np.array_equal(docs, d2) and np.array_equal(scores, s2)
+    emb.close()
+
+
+@pytest.mark.parametrize("n,B,cents,sigma", [(60000, 64, 100, 0.1), (150000, 300, 300, 0.1), (150000, 256, 50, 0.02)])
+def test_gemm_on_near_duplicate_clusters(gpu_ctx, orc, n, B, cents, sigma):
+    """Hundreds of rows within ~1e-3 (sigma 0.02: ~1e-4) of every query's best hit: the 10th and the 64th best
+    are closer than the sweep's rounding error, so a fixed candidate depth cannot certify the answer.  The
+    scan must stay on the tensor cores (no exact re-run) and equal the exact sweep bit for bit."""
+    dim = 768
+    rows = synth.make_clustered_vectors(n, dim, n_centroids=cents, sigma=sigma, seed=n)
+    qv, _ = synth.make_vector_queries(rows, B, seed=n + 1)
+    emb = ob.EmbeddingFieldStorage(gpu_ctx, "BGEBase")
+    emb.insert_batch(np.arange(n, dtype=np.uint64), rows)
+    d1, s1, c1 = emb.search_batch(qv, 10, 0.0)
+    t = gpu_ctx.last_timing()
+    assert t["scan_tensor_core"] == 1
+    per_cluster = n // cents
+    assert t["scan_unproven"] == 0 or per_cluster > 2000, t     # the whole cluster fits the re-score budget
+    assert t["scan_rescored"] >= min(per_cluster, 2000) // 4, t   # ... and it is the cluster that gets re-scored
+    os.environ["OC_DISABLE_GEMM"] = "1"
+    try:
+        d2, s2, c2 = emb.search_batch(qv, 10, 0.0)
+    finally:
+        os.environ.pop("OC_DISABLE_GEMM", None)
+    assert np.array_equal(d1, d2) and np.array_equal(s1, s2) and np.array_equal(c1, c2)
+    st = orc.EmbStore(rows)
+    for i in range(0, B, max(1, B // 8)):
+        ed, es = orc.vector(st, qv[i], 10, 0.0)
+        order = np.argsort(-es, kind="stable")
+        assert_topk_equal(d1[i, :c1[i]], s1[i, :c1[i]], ed[order], es[order], atol=1e-5)
+    emb.close()
+
+
+def test_gemm_exact_duplicates_overflow_to_the_exact_sweep(gpu_ctx, orc):
+    """5000 copies of one vector tie exactly: more rows within 2*eps of the 10th best than the re-score budget
+    -> those queries are flagged and served by the exact sweep (ties resolve to the lowest doc ids)."""
+    n, dim, B = 40000, 384, 16
+    rows = synth.make_vectors(n, dim, seed=77)
+    rows[10000:15000] = rows[123]
+    qv, _ = synth.make_vector_queries(rows, B, seed=78)
+    qv[3] = rows[123] * 1.5
+    emb = ob.EmbeddingFieldStorage(gpu_ctx, "BGESmall")
+    emb.insert_batch(np.arange(n, dtype=np.uint64), rows)
+    docs, scores, counts = emb.search_batch(qv, 10, -1.0)
+    t = gpu_ctx.last_timing()
+    assert t["scan_tensor_core"] == 1 and t["scan_unproven"] >= 1
+    assert docs[3, :10].tolist() == [123] + list(range(10000, 10009))
+    assert np.all(np.abs(scores[3, :10] - 1.0) < 1e-5)
+    st = orc.EmbStore(rows)
+    for i in range(B):
+        ed, es = orc.vector(st, qv[i], 10, -1.0)
+        order = np.argsort(-es, kind="stable")
+        assert_topk_equal(docs[i, :counts[i]], scores[i, :counts[i]], ed[order], es[order], atol=1e-5)
+    emb.close()
+
+
+@pytest.mark.parametrize("limit", [33, 100, 128])
+def test_gemm_serves_large_limits(gpu_ctx, limit):
+    """limit in (32, 128] used to fall off the tensor-core path (64 exact sweeps per 256-query batch)."""
+    n, dim, B = 90000, 384, 48
+    rows = synth.make_vectors(n, dim, seed=5)
+    qv, _ = synth.make_vector_queries(rows, B, seed=6)
+    emb = ob.EmbeddingFieldStorage(gpu_ctx, "BGESmall")
+    emb.insert_batch(np.arange(n, dtype=np.uint64), rows)
+    d1, s1, c1 = emb.search_batch(qv, limit, -1.0)
+    t = gpu_ctx.last_timing()
+    assert t["scan_tensor_core"] == 1 and t["scan_unproven"] == 0, t
+    os.environ["OC_DISABLE_GEMM"] = "1"
+    try:
+        d2, s2, c2 = emb.search_batch(qv, limit, -1.0)
+    finally:
+        os.environ.pop("OC_DISABLE_GEMM", None)
+    assert np.array_equal(d1, d2) and np.array_equal(s1, s2) and np.array_equal(c1, c2)
     emb.close()
