@@ -189,6 +189,43 @@ typedef struct {
 int oc_search(oc_ctx *ctx, oc_emb *emb, oc_str *str, const oc_search_params *p,
               uint64_t *out_doc_ids, float *out_scores, uint32_t *out_n, uint64_t *out_count);
 
+/* ---- term dictionary and query-term resolution (host only; no device needed) ------------------------
+ * The step the reference performs before the posting walk: TextParser::tokenize_and_stem(term) —
+ * originals, plus stems unless `exact`, [""] when nothing is left (token_score.rs:196-209) — and the
+ * expansion of every token to index terms inside StringStorage's FST (string_field.rs:208-225): the exact
+ * term when `exact` (tolerance Some(0), token_score.rs:240), terms within Levenshtein distance t for
+ * tolerance = Some(t) (tests/fulltext_search.rs:956-1018), prefix expansion otherwise (:633-644); an
+ * exactly matching term carries exact_match_boost (tests/boost_integration.rs:449-490; the reference's
+ * constant lives in oramacore_fields 0.2.0 and is not visible: 2.0 is this library's default).
+ * Term ids are stable: the id a term gets from oc_dict_add_terms is the id oc_str_insert / the loaded
+ * posting lists use for it.  Output = the CSR arrays of oc_search_params. */
+typedef struct oc_dict oc_dict;
+typedef struct oc_resolved oc_resolved;
+/* writes the stem of tok[0..len) into out (cap bytes) and returns its length; 0 = no stem */
+typedef size_t (*oc_stem_fn)(const char *tok, size_t len, char *out, size_t cap, void *user);
+typedef struct {
+    const char *const *texts;   /* n_queries NUL-terminated query strings ("term" of SearchParams)        */
+    uint32_t n_queries;
+    int exact;                  /* exact match (types.rs "exact")                                          */
+    int tolerance;              /* < 0: None => prefix expansion; t >= 0: Levenshtein <= t (bytes)         */
+    const float *field_boost;   /* n_fields, NULL = 1.0 (boost: field -> f32, token_score.rs:138-147)      */
+    const uint8_t *field_mask;  /* n_fields, NULL = all string fields (properties, token_score.rs:159-178) */
+    float exact_match_boost;    /* <= 0: default 2.0                                                       */
+} oc_resolve_params;
+int oc_dict_create(uint32_t n_fields, oc_dict **out);
+void oc_dict_destroy(oc_dict *d);
+int oc_dict_add_terms(oc_dict *d, uint32_t field, const char *const *terms, uint32_t n, uint32_t *out_ids);
+int oc_dict_lookup(oc_dict *d, uint32_t field, const char *term, uint32_t *out_id);   /* 0xffffffff = absent */
+uint32_t oc_dict_size(oc_dict *d, uint32_t field);
+int oc_dict_set_stemmer(oc_dict *d, oc_stem_fn fn, void *user);
+int oc_dict_resolve(oc_dict *d, const oc_resolve_params *p, oc_resolved **out);
+void oc_resolved_arrays(const oc_resolved *r, const uint32_t **q_token_offsets, const uint32_t **token_term_offsets,
+                        const uint32_t **term_field, const uint32_t **term_id, const float **term_weight,
+                        uint32_t *n_tokens, uint32_t *n_terms);
+/* points p's query arrays (and n_queries) at r; r must outlive the oc_search call */
+void oc_resolved_fill(const oc_resolved *r, oc_search_params *p);
+void oc_resolved_free(oc_resolved *r);
+
 /* ---- micro-batching front --------------------------------------------------------------
  * The reference runs one search per request task, many at a time (bin/oramacore.rs:76-79,
  * SURVEY.md §8b "Threading"); the GPU path earns its throughput on batches.  A batcher coalesces

@@ -24,6 +24,8 @@ EXPORTED_SYMBOLS = [
     "oc_emb_info", "oc_emb_search", "oc_str_create", "oc_str_destroy", "oc_str_set_rows", "oc_str_load_field",
     "oc_str_insert", "oc_str_commit", "oc_str_delete", "oc_str_info", "oc_str_set_global", "oc_search", "oc_pinned_alloc", "oc_pinned_free", "oc_last_timing", "oc_launch_count",
     "oc_batcher_create", "oc_batcher_destroy", "oc_batcher_search", "oc_batcher_stats",
+    "oc_dict_create", "oc_dict_destroy", "oc_dict_add_terms", "oc_dict_lookup", "oc_dict_size", "oc_dict_set_stemmer",
+    "oc_dict_resolve", "oc_resolved_arrays", "oc_resolved_fill", "oc_resolved_free",
 ]
 
 
@@ -52,6 +54,14 @@ class SearchParams(C.Structure):
                 ("filter_bits", C.c_void_p), ("filter_nbits", C.c_uint64),
                 ("omc_doc_ids", C.c_void_p), ("omc_mult", C.c_void_p), ("n_omc", C.c_uint64),
                 ("sharded", C.c_int)]
+
+
+class ResolveParams(C.Structure):
+    _fields_ = [("texts", C.POINTER(C.c_char_p)), ("n_queries", C.c_uint32), ("exact", C.c_int), ("tolerance", C.c_int),
+                ("field_boost", C.c_void_p), ("field_mask", C.c_void_p), ("exact_match_boost", C.c_float)]
+
+
+STEM_FN = C.CFUNCTYPE(C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p)
 
 
 class Timing(C.Structure):
@@ -126,6 +136,21 @@ def lib():
     L.oc_batcher_destroy.restype = None
     L.oc_batcher_search.argtypes = [vp, C.POINTER(SearchParams), vp, vp, vp, vp]
     L.oc_batcher_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
+    L.oc_dict_create.argtypes = [u32, C.POINTER(vp)]
+    L.oc_dict_destroy.argtypes = [vp]
+    L.oc_dict_destroy.restype = None
+    L.oc_dict_add_terms.argtypes = [vp, u32, C.POINTER(C.c_char_p), u32, vp]
+    L.oc_dict_lookup.argtypes = [vp, u32, C.c_char_p, C.POINTER(u32)]
+    L.oc_dict_size.argtypes = [vp, u32]
+    L.oc_dict_size.restype = u32
+    L.oc_dict_set_stemmer.argtypes = [vp, STEM_FN, vp]
+    L.oc_dict_resolve.argtypes = [vp, C.POINTER(ResolveParams), C.POINTER(vp)]
+    L.oc_resolved_arrays.argtypes = [vp] + [C.POINTER(vp)] * 5 + [C.POINTER(u32)] * 2
+    L.oc_resolved_arrays.restype = None
+    L.oc_resolved_fill.argtypes = [vp, C.POINTER(SearchParams)]
+    L.oc_resolved_fill.restype = None
+    L.oc_resolved_free.argtypes = [vp]
+    L.oc_resolved_free.restype = None
     L.oc_pinned_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
     L.oc_pinned_free.argtypes = [vp]
     L.oc_pinned_free.restype = None

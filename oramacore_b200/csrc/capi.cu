@@ -18,6 +18,7 @@
 
 #include "bm25.cuh"
 #include "comm.h"
+#include "dict.h"
 #include "emb_gemm.cuh"
 #include "emb_scan.cuh"
 #include "fuse.cuh"
@@ -1685,3 +1686,64 @@ extern "C" int oc_batcher_stats(oc_batcher *b, uint64_t *n_queries, uint64_t *n_
     b->q.stats(n_queries, n_batches, n_direct);
     return OC_OK;
 }
+
+// ------------------------------------------------------------------------------------ term dictionary / query resolution
+// Host only (no device): the step the reference performs before the posting walk — tokenize_and_stem
+// (token_score.rs:196-209) and the FST term expansion inside StringStorage (string_field.rs:208-225).
+struct oc_dict { ocd::Dict d; explicit oc_dict(uint32_t n) : d(n) {} };
+struct oc_resolved { ocd::Resolved r; };
+
+extern "C" int oc_dict_create(uint32_t n_fields, oc_dict **out) {
+    if (!out || n_fields == 0) return fail(OC_ERR_INVALID, "bad arguments");
+    *out = new oc_dict(n_fields);
+    return OC_OK;
+}
+extern "C" void oc_dict_destroy(oc_dict *d) { delete d; }
+extern "C" int oc_dict_add_terms(oc_dict *d, uint32_t field, const char *const *terms, uint32_t n, uint32_t *out_ids) {
+    if (!d || field >= d->d.n_fields() || (n && !terms)) return fail(OC_ERR_INVALID, "bad arguments");
+    for (uint32_t i = 0; i < n; i++) if (!terms[i]) return fail(OC_ERR_INVALID, "term %u is NULL", i);
+    d->d.add_terms(field, terms, n, out_ids);
+    return OC_OK;
+}
+extern "C" int oc_dict_lookup(oc_dict *d, uint32_t field, const char *term, uint32_t *out_id) {
+    if (!d || field >= d->d.n_fields() || !term || !out_id) return fail(OC_ERR_INVALID, "bad arguments");
+    if (!d->d.lookup(field, term, out_id)) *out_id = 0xffffffffu;
+    return OC_OK;
+}
+extern "C" uint32_t oc_dict_size(oc_dict *d, uint32_t field) { return (d && field < d->d.n_fields()) ? d->d.size(field) : 0; }
+extern "C" int oc_dict_set_stemmer(oc_dict *d, oc_stem_fn fn, void *user) {
+    if (!d) return fail(OC_ERR_INVALID, "dict is NULL");
+    d->d.set_stemmer(fn, user);
+    return OC_OK;
+}
+extern "C" int oc_dict_resolve(oc_dict *d, const oc_resolve_params *p, oc_resolved **out) {
+    if (!d || !p || !out || (p->n_queries && !p->texts)) return fail(OC_ERR_INVALID, "bad arguments");
+    for (uint32_t i = 0; i < p->n_queries; i++) if (!p->texts[i]) return fail(OC_ERR_INVALID, "text %u is NULL", i);
+    if (p->tolerance > 8) return fail(OC_ERR_UNSUPPORTED, "tolerance %d > 8", p->tolerance);
+    ocd::ResolveOpts o;
+    o.exact = p->exact != 0; o.tolerance = p->tolerance; o.field_boost = p->field_boost; o.field_mask = p->field_mask;
+    o.exact_match_boost = p->exact_match_boost > 0.f ? p->exact_match_boost : 2.0f;
+    oc_resolved *r = new oc_resolved();
+    d->d.resolve(p->texts, p->n_queries, o, &r->r);
+    *out = r;
+    return OC_OK;
+}
+extern "C" void oc_resolved_arrays(const oc_resolved *r, const uint32_t **q_token_offsets, const uint32_t **token_term_offsets,
+                                   const uint32_t **term_field, const uint32_t **term_id, const float **term_weight,
+                                   uint32_t *n_tokens, uint32_t *n_terms) {
+    if (!r) return;
+    static const uint32_t zero_u = 0; static const float one_f = 1.0f;   // empty arrays still get valid pointers
+    if (q_token_offsets) *q_token_offsets = r->r.q_token_offsets.data();
+    if (token_term_offsets) *token_term_offsets = r->r.token_term_offsets.data();
+    if (term_field) *term_field = r->r.term_field.empty() ? &zero_u : r->r.term_field.data();
+    if (term_id) *term_id = r->r.term_id.empty() ? &zero_u : r->r.term_id.data();
+    if (term_weight) *term_weight = r->r.term_weight.empty() ? &one_f : r->r.term_weight.data();
+    if (n_tokens) *n_tokens = (uint32_t)r->r.token_term_offsets.size() - 1;
+    if (n_terms) *n_terms = (uint32_t)r->r.term_id.size();
+}
+extern "C" void oc_resolved_fill(const oc_resolved *r, oc_search_params *p) {
+    if (!r || !p) return;
+    oc_resolved_arrays(r, &p->q_token_offsets, &p->token_term_offsets, &p->term_field, &p->term_id, &p->term_weight, nullptr, nullptr);
+    p->n_queries = (uint32_t)r->r.q_token_offsets.size() - 1;
+}
+extern "C" void oc_resolved_free(oc_resolved *r) { delete r; }

@@ -245,8 +245,98 @@ class StringFieldStorage:
         check(lib().oc_str_set_global(self._h, int(document_count), _p(a)))
 
 
+class TermDictionary:
+    """Native term dictionaries of the string fields of one Index + batch query resolution (oc_dict_*,
+    csrc/dict.h): tokenize (+ stem hook), then per field exact / prefix / Levenshtein expansion — what
+    TextParser::tokenize_and_stem and the FST inside StringStorage do in the reference
+    (token_score.rs:196-209, string_field.rs:208-225).  Host only: works without a GPU."""
+
+    def __init__(self, n_fields: int = 1):
+        self.n_fields = n_fields
+        self._h = C.c_void_p()
+        check(lib().oc_dict_create(n_fields, C.byref(self._h)))
+        self._stem_cb = None
+
+    def close(self):
+        if self._h:
+            lib().oc_dict_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def add_terms(self, field: int, terms: Sequence[str]) -> np.ndarray:
+        """Returns the (stable) ids of the terms; known terms keep their id, new ones get the next."""
+        arr = (C.c_char_p * len(terms))(*[t.encode("utf-8") for t in terms])
+        ids = np.zeros(len(terms), np.uint32)
+        check(lib().oc_dict_add_terms(self._h, field, arr, len(terms), _p(ids)))
+        return ids
+
+    def lookup(self, field: int, term: str) -> Optional[int]:
+        out = C.c_uint32()
+        check(lib().oc_dict_lookup(self._h, field, term.encode("utf-8"), C.byref(out)))
+        return None if out.value == 0xffffffff else int(out.value)
+
+    def size(self, field: int) -> int:
+        return int(lib().oc_dict_size(self._h, field))
+
+    def set_stemmer(self, fn):
+        """fn(token: str) -> Optional[str]; None / "" = no stem (test hook: a production binding passes a C function)."""
+        def cb(tok, n, out, cap, _user):
+            s = fn(C.string_at(tok, n).decode("utf-8"))
+            if not s:
+                return 0
+            b = s.encode("utf-8")
+            if len(b) > cap:
+                return 0
+            C.memmove(out, b, len(b))
+            return len(b)
+        self._stem_cb = _lib.STEM_FN(cb) if fn is not None else _lib.STEM_FN()
+        check(lib().oc_dict_set_stemmer(self._h, self._stem_cb, None))
+
+    def resolve_batch(self, texts: Sequence[str], exact: bool = False, tolerance: Optional[int] = None,
+                      boost: Optional[Sequence[float]] = None, properties: Optional[Sequence[int]] = None,
+                      exact_match_boost: float = 0.0) -> "TextQueryBatch":
+        """SearchParams{tokens, exact_match, boost, tolerance} for B queries at once (token_score.rs:235-242)
+        -> the packed CSR arrays oc_search takes."""
+        rp = _lib.ResolveParams()
+        arr = (C.c_char_p * len(texts))(*[t.encode("utf-8") for t in texts])
+        rp.texts, rp.n_queries = arr, len(texts)
+        rp.exact, rp.tolerance = int(bool(exact)), -1 if tolerance is None else int(tolerance)
+        fb = None if boost is None else np.ascontiguousarray(boost, np.float32)
+        fm = None
+        if properties is not None:
+            fm = np.zeros(self.n_fields, np.uint8)
+            fm[list(properties)] = 1
+        rp.field_boost, rp.field_mask, rp.exact_match_boost = _p(fb), _p(fm), float(exact_match_boost)
+        res = C.c_void_p()
+        check(lib().oc_dict_resolve(self._h, C.byref(rp), C.byref(res)))
+        try:
+            ptrs = [C.c_void_p() for _ in range(5)]
+            nt, ne = C.c_uint32(), C.c_uint32()
+            lib().oc_resolved_arrays(res, *[C.byref(x) for x in ptrs], C.byref(nt), C.byref(ne))
+            B = len(texts)
+
+            def arr_of(ptr, n, ct, dt):
+                return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ct)), shape=(max(n, 1),))[:n].astype(dt, copy=True)
+            out = TextQueryBatch.__new__(TextQueryBatch)
+            out.n_queries = B
+            out.q_token_offsets = arr_of(ptrs[0], B + 1, C.c_uint32, np.uint32)
+            out.token_term_offsets = arr_of(ptrs[1], nt.value + 1, C.c_uint32, np.uint32)
+            out.term_field = arr_of(ptrs[2], ne.value, C.c_uint32, np.uint32)
+            out.term_id = arr_of(ptrs[3], ne.value, C.c_uint32, np.uint32)
+            out.term_weight = arr_of(ptrs[4], ne.value, C.c_float, np.float32)
+            return out
+        finally:
+            lib().oc_resolved_free(res)
+
+
 class TextQueryBatch:
     """B resolved queries packed as the CSR arrays oc_search takes (q -> tokens -> expanded terms)."""
+
+    def query(self, i: int) -> TextQuery:
+        """The i-th query as a TextQuery (tests: compare with a host-side resolution)."""
+        t0, t1 = int(self.q_token_offsets[i]), int(self.q_token_offsets[i + 1])
+        e0, e1 = int(self.token_term_offsets[t0]), int(self.token_term_offsets[t1])
+        return TextQuery((self.token_term_offsets[t0:t1 + 1] - np.uint32(e0)).astype(np.uint32), self.term_field[e0:e1].copy(),
+                         self.term_id[e0:e1].copy(), self.term_weight[e0:e1].copy())
 
     def __init__(self, texts: Sequence[TextQuery]):
         B = len(texts)
