@@ -556,4 +556,345 @@ __global__ void __launch_bounds__(BM25_THREADS) bm25_tile_kernel(const Bm25Param
     }
 }
 
+
+// =======================================================================================
+// K3b — the scorer for the common query shape: every token resolves to (at most) ONE index term.
+//
+// Same contract and outputs as bm25_tile_kernel<false, THRESH, OMC> (bit-identical scores: contributions are
+// added in token order with explicit round-to-nearest ops), restructured around the POSTINGS instead of the
+// row slots:
+//   * persistent CTAs pull (tile, query) items from a global counter, tile-major, so the queries that share a
+//     tile's hot posting ranges run back to back (L2) and the per-CTA setup is paid once;
+//   * the shared-memory accumulators are zeroed once per CTA; every item leaves them clean: a SPARSE item
+//     (few postings in the tile) is finished by walking its postings again (L1/L2-hot) and exchanging each
+//     slot with 0 — the first visitor owns the document, later visitors see 0 — so neither a zeroing pass nor
+//     a scan of the 8192 slots is paid; a DENSE item scans the slots (as K3 did) and zeroes them on the way out;
+//   * lanes map to postings one-to-one for short ranges (4-way unrolled only when a range fills the block).
+// The hybrid lookup of the vector hits' fulltext scores is not done here (bm25_point_kernel), so this kernel
+// does not depend on the vector stage and can overlap the matrix sweep on another stream.
+// =======================================================================================
+constexpr uint32_t BM25_SPARSE_MAX = 2048;     // postings of one (query, tile) item up to which the sparse finish is used
+constexpr uint32_t BM25_MAX_TOK = 32;          // tokens per query (u32 bitmask, token_score.rs:293)
+
+__host__ __device__ inline size_t bm25_tile2_smem_bytes(bool threshold, bool omc, uint32_t cap) {
+    size_t b = size_t(BM25_TILE) * 4;                 // score
+    if (omc) b += size_t(BM25_TILE) * 4;              // omc multipliers
+    if (threshold) b += size_t(BM25_TILE) * 4;        // token masks
+    b += size_t(BM25_TILE) / 8;                       // row_ok bits
+    b += size_t(cap) * 8;                             // top buffer keys
+    return b + 64;
+}
+
+template <bool THRESH, bool OMC>
+__global__ void __launch_bounds__(BM25_THREADS, 4) bm25_tile2_kernel(const Bm25Params p, unsigned int *work_counter) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    float *score = reinterpret_cast<float *>(smem);
+    float *aux = score + BM25_TILE;                                    // OMC multipliers
+    uint32_t *mask = reinterpret_cast<uint32_t *>(score + BM25_TILE * (OMC ? 2 : 1));
+    uint32_t *okb = mask + (THRESH ? BM25_TILE : 0);
+    uint64_t *tbuf = reinterpret_cast<uint64_t *>(okb + BM25_TILE / 32);
+    __shared__ uint32_t s_cnt, s_matched, s_item, s_ovf;
+    __shared__ unsigned int s_maxo, s_mino;
+    __shared__ const uint2 *t_ptr[BM25_MAX_TOK];
+    __shared__ uint32_t t_n[BM25_MAX_TOK], t_bit[BM25_MAX_TOK], t_pre[BM25_MAX_TOK];
+    __shared__ float t_w[BM25_MAX_TOK], t_idf[BM25_MAX_TOK];
+
+    const uint32_t tid = threadIdx.x;
+    const float kp1 = __fadd_rn(p.k, 1.0f);
+    const bool use_ok = p.row_ok_bits != nullptr;
+    const uint32_t n_items = p.n_tiles * p.n_queries;
+
+    for (uint32_t i = tid; i < BM25_TILE / 4; i += BM25_THREADS) {
+        reinterpret_cast<float4 *>(score)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (THRESH) reinterpret_cast<uint4 *>(mask)[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    for (;;) {
+        __syncthreads();                                   // previous item fully retired (tables, buffers, accumulators clean)
+        if (tid == 0) {
+            s_item = atomicAdd(work_counter, 1u);
+            s_cnt = 0; s_matched = 0; s_ovf = 0; s_maxo = f32_ordered(0.f); s_mino = f32_ordered(0.f);
+        }
+        __syncthreads();
+        const uint32_t item = s_item;
+        if (item >= n_items) break;
+        const uint32_t tile = item / p.n_queries, q = item % p.n_queries;
+        const uint32_t row0 = tile * BM25_TILE;
+        const QueryDesc qd = p.queries[q];
+        const uint32_t ntok = min(qd.token_end - qd.token_begin, BM25_MAX_TOK);
+        if (tid < ntok) {
+            const TokenDesc tk = p.tokens[qd.token_begin + tid];
+            uint32_t n = 0;
+            if (tk.term_end > tk.term_begin) {
+                const uint32_t e = tk.term_begin;
+                const TermDesc td = p.terms[e];
+                const uint32_t *sg = p.seg + size_t(e) * (p.n_tiles + 1);
+                const uint32_t lo = sg[tile], hi = sg[tile + 1];
+                t_ptr[tid] = reinterpret_cast<const uint2 *>(td.ptr) + lo;
+                n = hi - lo;
+                t_w[tid] = td.weight; t_pre[tid] = td.flags & 1u;
+            }
+            t_n[tid] = n; t_idf[tid] = tk.idf; t_bit[tid] = tk.bit;
+        }
+        if (use_ok)
+            for (uint32_t i = tid; i < BM25_TILE / 32; i += BM25_THREADS) okb[i] = p.row_ok_bits[row0 / 32 + i];
+        __syncthreads();
+
+        // ---------------------------------------- accumulate, token by token (the reference's summation order)
+        uint32_t total = 0;
+        for (uint32_t j = 0; j < ntok; j++) {
+            const uint32_t n = t_n[j];
+            if (n == 0) continue;                          // block-uniform
+            total += n;
+            const uint2 *pp = t_ptr[j];
+            const bool pre = t_pre[j] != 0;
+            const float w = t_w[j], idf = t_idf[j];
+            const uint32_t bit = t_bit[j];
+            auto apply = [&](const uint2 rec) {
+                const uint32_t l = rec.x - row0;
+                if (use_ok && !((okb[l >> 5] >> (l & 31)) & 1u)) return;
+                float c;
+                if (pre) c = __uint_as_float(rec.y);       // contribution precomputed once per batch (NaN = skip)
+                else {
+                    const float ntf = __fmul_rn(w, __uint_as_float(rec.y));
+                    c = f32_is_normal(ntf) ? bm25_sat(ntf, p.k, kp1, idf) : __int_as_float(0x7fc00000);   // bm25.rs:387,501
+                }
+                if (c == c) {
+                    score[l] = __fadd_rn(score[l], c);
+                    if (THRESH) mask[l] |= bit;
+                }
+            };
+            uint32_t base = 0;
+            for (; base + BM25_THREADS * 4 <= n; base += BM25_THREADS * 4) {   // full batches: 4 loads in flight per lane
+                uint2 r[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) r[u] = __ldg(pp + base + tid + u * BM25_THREADS);
+#pragma unroll
+                for (int u = 0; u < 4; u++) apply(r[u]);
+            }
+            for (uint32_t pi = base + tid; pi < n; pi += BM25_THREADS) apply(__ldg(pp + pi));
+            __syncthreads();                               // the next token may touch the same rows
+        }
+
+        if (OMC) {   // multipliers of this tile's rows (search.rs:39-48), rare
+            for (uint32_t i = tid; i < BM25_TILE; i += BM25_THREADS) aux[i] = 1.0f;
+            uint32_t lo = 0, hi = p.n_omc;
+            while (lo < hi) { uint32_t m = (lo + hi) >> 1; if (p.omc_row[m] < row0) lo = m + 1; else hi = m; }
+            const uint32_t omc_lo = lo;
+            hi = p.n_omc;
+            const uint64_t rend = uint64_t(row0) + BM25_TILE;
+            while (lo < hi) { uint32_t m = (lo + hi) >> 1; if (uint64_t(p.omc_row[m]) < rend) lo = m + 1; else hi = m; }
+            __syncthreads();
+            for (uint32_t i = omc_lo + tid; i < lo; i += BM25_THREADS) aux[p.omc_row[i] - row0] = p.omc_mult[i];
+            __syncthreads();
+        }
+
+        // ---------------------------------------- finish: count, extrema, gated top-n; leave the accumulators clean
+        const float mh = p.min_hint ? p.min_hint[q] : 0.f;
+        unsigned long long tau = p.tau[q];
+        float tau_f = tau ? key_score(tau) : -INFINITY;
+        uint32_t matched = 0;
+        float lmax = 0.f, lmin = 0.f;
+        const uint64_t rows_here = min(uint64_t(BM25_TILE), p.n_rows - row0);
+        auto visit = [&](float s, uint32_t l) -> bool {   // one matched row; returns true when it pushed a candidate
+            matched++;
+            lmax = fmaxf(lmax, s);
+            lmin = fminf(lmin, s);
+            float proxy = __fsub_rn(s, mh);
+            if (OMC) proxy = __fmul_rn(proxy, aux[l]);
+            if (!(proxy >= tau_f)) return false;                            // NaN fails; ties re-checked on the key
+            const unsigned long long key = make_key(proxy, row0 + l);
+            if (key <= tau) return false;
+            const uint32_t slot = atomicAdd(&s_cnt, 1u);
+            if (slot < p.cap) tbuf[slot] = key; else s_ovf = 1u;
+            return true;
+        };
+        // the sparse finish re-derives a candidate's raw score from its key (proxy == score): only without OMC / min hint
+        const bool sparse = total != 0 && total <= BM25_SPARSE_MAX && p.cap >= BM25_SPARSE_MAX && !OMC && mh == 0.f;
+        if (sparse) {
+            // walk the postings again; the first visitor of a row takes its sum and clears the slot
+            for (uint32_t j = 0; j < ntok; j++) {
+                const uint32_t n = t_n[j];
+                const uint2 *pp = t_ptr[j];
+                for (uint32_t pi = tid; pi < n; pi += BM25_THREADS) {
+                    const uint32_t l = __ldg(&pp[pi].x) - row0;
+                    float s = __uint_as_float(atomicExch(reinterpret_cast<unsigned int *>(&score[l]), 0u));
+                    if (s != 0.f) {
+                        if (THRESH) {   // the masks are stable during this walk (cleared below)
+                            const uint32_t m = mask[l];
+                            if (!(m != 0u && uint32_t(__popc(m)) >= qd.required)) continue;   // bm25.rs:416-428
+                        }
+                        visit(s, l);
+                    }
+                }
+            }
+            __syncthreads();
+            if (THRESH) {
+                for (uint32_t j = 0; j < ntok; j++) {
+                    const uint32_t n = t_n[j];
+                    const uint2 *pp = t_ptr[j];
+                    for (uint32_t pi = tid; pi < n; pi += BM25_THREADS) mask[__ldg(&pp[pi].x) - row0] = 0u;
+                }
+            }
+        } else if (total != 0) {
+            // DENSE: scan the slots (4 per thread per step: one LDS.128); overflow of the candidate buffer (cold
+            // threshold) -> redo chunk by chunk with a compress between chunks, as K3 does
+            auto scan_pass = [&](const bool chunked) {
+                matched = 0; lmax = 0.f; lmin = 0.f;
+                for (uint32_t base = 0; base < rows_here; base += BM25_CHUNK) {
+                    const uint32_t l0 = base + tid * 4;
+                    bool pushed = false;
+                    const float4 s4 = *reinterpret_cast<const float4 *>(score + l0);
+                    float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+                    if (THRESH) {
+                        const uint4 m4 = *reinterpret_cast<const uint4 *>(mask + l0);
+                        const uint32_t mv[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+                        for (int u = 0; u < 4; u++)
+                            sv[u] = (mv[u] != 0u && uint32_t(__popc(mv[u])) >= qd.required) ? sv[u] : 0.f;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+                        if (sv[u] != 0.f) pushed |= visit(sv[u], l0 + u);
+                    if (!chunked) continue;
+                    if (!__syncthreads_or(pushed)) continue;
+                    const uint32_t c = s_cnt;
+                    __syncthreads();
+                    if (c + BM25_CHUNK > p.cap && base + BM25_CHUNK < rows_here) {
+                        block_keep_top(tbuf, c, p.cap, p.n_keep, tid);
+                        const uint32_t kept = min(c, p.n_keep);
+                        if (tid == 0) s_cnt = kept;
+                        if (kept == p.n_keep) { tau = max(tau, (unsigned long long)tbuf[p.n_keep - 1]); tau_f = key_score(tau); }
+                        __syncthreads();
+                    }
+                }
+            };
+            scan_pass(false);
+            __syncthreads();
+            if (s_ovf) {
+                __syncthreads();
+                if (tid == 0) { s_cnt = 0u; s_ovf = 0u; }
+                __syncthreads();
+                scan_pass(true);
+                __syncthreads();
+            }
+        }
+        // ---- block reductions of count / extrema
+        matched = __reduce_add_sync(0xffffffffu, matched);
+        for (int o = 16; o > 0; o >>= 1) {
+            lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+            lmin = fminf(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+        }
+        if ((tid & 31) == 0 && matched) {
+            atomicAdd(&s_matched, matched);
+            atomicMax(&s_maxo, f32_ordered(lmax));
+            atomicMin(&s_mino, f32_ordered(lmin));
+        }
+        __syncthreads();
+        // ---- emit: best <= n_keep of the buffer
+        const size_t slot_base = (size_t(q) * p.n_tiles + tile);
+        uint32_t c = min(s_cnt, p.cap);
+        if (c >= p.n_keep && c > 0) {
+            block_keep_top(tbuf, c, p.cap, p.n_keep, tid);
+            c = p.n_keep;
+            if (tid == 0) atomicMax(p.tau + q, (unsigned long long)tbuf[p.n_keep - 1]);
+        }
+        for (uint32_t i = tid; i < c; i += BM25_THREADS) {
+            const uint64_t key = tbuf[i];
+            p.cand_key[slot_base * p.n_keep + i] = key;
+            p.cand_ft[slot_base * p.n_keep + i] = sparse ? key_score(key) : score[key_idx(key) - row0];
+        }
+        if (tid == 0) {
+            p.cand_cnt[slot_base] = c;
+            p.tile_count[slot_base] = s_matched;
+            p.tile_max[slot_base] = f32_unordered(s_maxo);
+            p.tile_min[slot_base] = f32_unordered(s_mino);
+        }
+        if (!sparse && total != 0) {
+            __syncthreads();                               // emit read the scores
+            for (uint32_t i = tid; i < BM25_TILE / 4; i += BM25_THREADS) {   // leave the accumulators clean
+                reinterpret_cast<float4 *>(score)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (THRESH) reinterpret_cast<uint4 *>(mask)[i] = make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Hybrid: the fulltext score of each vector hit's document (token_score.rs:416-419 needs it for the <= limit
+// documents of the vector map), by POINT lookups instead of a pass inside the tile scorer: one warp per
+// (query, hit), lane i evaluates token i — binary search of the row in each of the token's posting lists, the
+// same rounded ops and the same term / token order as the tile kernels — and lane 0 adds the token
+// contributions in order, so the value is bit-identical to what the tile accumulators held.
+// ---------------------------------------------------------------------------------------
+struct PointParams {
+    const TermDesc *terms; const TokenDesc *tokens; const QueryDesc *queries;
+    uint32_t n_queries, v_stride;
+    const uint32_t *v_row;        // [q][v_stride] string row of each vector hit, 0xffffffff = none
+    const uint32_t *row_ok_bits;  // NULL or bitmap over rows
+    float k;
+    int threshold;
+    float *v_ft; uint8_t *v_present;
+};
+__device__ __forceinline__ bool posting_find(const TermDesc &td, uint32_t row, uint32_t *payload) {
+    const uint2 *pp = reinterpret_cast<const uint2 *>(td.ptr);
+    uint32_t lo = 0, hi = td.len;
+    while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if (__ldg(&pp[m].x) < row) lo = m + 1; else hi = m; }
+    if (lo < td.len) { const uint2 r = __ldg(pp + lo); if (r.x == row) { *payload = r.y; return true; } }
+    return false;
+}
+__global__ void __launch_bounds__(256) bm25_point_kernel(const PointParams p) {
+    const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x & 31;
+    if (wid >= p.n_queries * p.v_stride) return;
+    const uint32_t q = wid / p.v_stride;
+    const uint32_t r = p.v_row[wid];
+    const QueryDesc qd = p.queries[q];
+    const float kp1 = __fadd_rn(p.k, 1.0f);
+    float score = 0.f;
+    uint32_t mask = 0;
+    bool ok = r != 0xffffffffu;
+    if (ok && p.row_ok_bits) ok = (p.row_ok_bits[r >> 5] >> (r & 31)) & 1u;
+    if (ok) {
+        for (uint32_t t0 = qd.token_begin; t0 < qd.token_end; t0 += 32) {
+            const uint32_t ti = t0 + lane;
+            float c = __int_as_float(0x7fc00000);
+            uint32_t bit = 0;
+            if (ti < qd.token_end) {
+                const TokenDesc tk = p.tokens[ti];
+                bit = tk.bit;
+                const uint32_t nt = tk.term_end - tk.term_begin;
+                if (nt == 1) {
+                    const TermDesc td = p.terms[tk.term_begin];
+                    uint32_t pay;
+                    if (posting_find(td, r, &pay)) {
+                        if (td.flags & 1u) c = __uint_as_float(pay);
+                        else {
+                            const float ntf = __fmul_rn(td.weight, __uint_as_float(pay));
+                            if (f32_is_normal(ntf)) c = bm25_sat(ntf, p.k, kp1, tk.idf);
+                        }
+                    }
+                } else if (nt > 1) {
+                    float S = 0.f;   // S += weight(1.0) * ntf in term order (token_score.rs:266-271)
+                    for (uint32_t e = tk.term_begin; e < tk.term_end; e++) {
+                        const TermDesc td = p.terms[e];
+                        uint32_t pay;
+                        if (posting_find(td, r, &pay)) S = __fadd_rn(S, __fmul_rn(td.weight, __uint_as_float(pay)));
+                    }
+                    if (f32_is_normal(S)) c = bm25_sat(S, p.k, kp1, tk.idf);
+                }
+            }
+            const uint32_t nhere = min(32u, qd.token_end - t0);
+            for (uint32_t i = 0; i < nhere; i++) {      // token order
+                const float ci = __shfl_sync(0xffffffffu, c, i);
+                const uint32_t bi = __shfl_sync(0xffffffffu, bit, i);
+                if (ci == ci) { score = __fadd_rn(score, ci); mask |= bi; }
+            }
+        }
+    }
+    if (lane == 0) {
+        const bool present = ok && (p.threshold ? (mask != 0u && uint32_t(__popc(mask)) >= qd.required) : score != 0.f);
+        p.v_ft[wid] = present ? score : 0.f;
+        p.v_present[wid] = present ? 1 : 0;
+    }
+}
+
 }  // namespace oc

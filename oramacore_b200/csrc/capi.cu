@@ -133,6 +133,7 @@ struct oc_ctx {
     cudaStream_t side = nullptr;      // descriptor upload + BM25 plan/precompute while the main stream sweeps the matrix
     cudaEvent_t ev_side = nullptr;
     bool sweep_timed = false;         // EV_SWEEP0/1 recorded in this call (tensor-core path)
+    uint32_t cvt_stages_default = 5;  // run_vector_stage: ring depth of the converting sweep when the caller has no preference
     bool rerun_timed = false;         // EV_RR0/1 recorded: flagged queries were re-run through the exact sweep
     bool side_dirty = false;          // work was queued on the side stream and not yet joined (an error path returned early)
     cudaDeviceProp prop{};
@@ -144,7 +145,7 @@ struct oc_ctx {
     // workspaces
     DevBuf in_blob, in_blob0, q_pad, q_inv, eff_norm, filter_dev, scan_cand, v_doc, v_score, v_row, v_cnt, v_srow, v_ft, v_present, v_raw;
     DevBuf seg, df_dev, row_ok, tau, cand_key, cand_ft, cand_cnt, tile_cnt, tile_max, tile_min, min_hint;
-    DevBuf out_blob, shard_send, shard_recv;
+    DevBuf out_blob, shard_send, shard_recv, work_ctr;
     bool gemm_pending = false; const float *gemm_inv_norm = nullptr;
     DevBuf q_bf16, q_rho, pre_post, g_thr, g_eps, g_ovf, g_ovfcnt, g_resc, g_cand, g_cnt, g_flag, g_max, r_qpad, r_qinv, r_map, r_doc, r_score, r_row, r_cnt, r_raw;
 
@@ -189,7 +190,7 @@ extern "C" void oc_shutdown(oc_ctx *c) {
     DevBuf *bufs[] = {&c->in_blob, &c->q_pad, &c->q_inv, &c->eff_norm, &c->filter_dev, &c->scan_cand, &c->v_doc,
                       &c->v_score, &c->v_row, &c->v_cnt, &c->v_srow, &c->v_ft, &c->v_present, &c->v_raw, &c->seg, &c->df_dev,
                       &c->row_ok, &c->tau, &c->cand_key, &c->cand_ft, &c->cand_cnt, &c->tile_cnt, &c->tile_max,
-                      &c->tile_min, &c->min_hint, &c->out_blob, &c->shard_send, &c->shard_recv, &c->q_bf16, &c->q_rho, &c->pre_post, &c->g_thr, &c->g_eps, &c->g_ovf, &c->g_ovfcnt, &c->g_resc, &c->g_cand, &c->g_cnt, &c->g_max,
+                      &c->tile_min, &c->min_hint, &c->out_blob, &c->shard_send, &c->shard_recv, &c->work_ctr, &c->q_bf16, &c->q_rho, &c->pre_post, &c->g_thr, &c->g_eps, &c->g_ovf, &c->g_ovfcnt, &c->g_resc, &c->g_cand, &c->g_cnt, &c->g_max,
                       &c->g_flag, &c->r_qpad, &c->r_qinv, &c->r_map, &c->r_doc, &c->r_score, &c->r_row, &c->r_cnt, &c->r_raw};
     for (DevBuf *b : bufs) b->release();
     c->h_in.release(); c->h_out.release();
@@ -581,18 +582,24 @@ static int run_vector_stage(oc_ctx *c, oc_emb *e, const float *q_dev, uint32_t B
     gp.thr = c->g_thr.as<float>(); gp.cand = c->g_cand.as<uint64_t>(); gp.cand_cnt = c->g_cnt.as<uint32_t>();
     gp.gmax = c->g_max.as<float>();
     gp.ovf = c->g_ovf.as<uint64_t>(); gp.ovf_cnt = c->g_ovfcnt.as<uint32_t>(); gp.ovf_cap = GEMM_OVF_CAP;
-    if (smem_cfg_needed(c->device, (const void *)emb_gemm_cvt_kernel, gemm_cvt_smem_bytes())) {   // all sweep variants at once
+    // ring depth of the converting sweep: 5 stages alone on the SM; 4 stages (OC_CVT_STAGES=4) leave ~60 KB of shared
+    // memory so one CTA of the BM25 tile scorer (side stream) can co-reside and use the issue slots the HBM-bound sweep leaves idle
+    const char *stenv = getenv("OC_CVT_STAGES");
+    const uint32_t cvt_stages = (stenv && stenv[0] == '4') ? 4 : (stenv && stenv[0] == '5') ? 5 : c->cvt_stages_default;
+    if (smem_cfg_needed(c->device, (const void *)emb_gemm_cvt_kernel<5>, gemm_cvt_smem_bytes(5))) {   // all sweep variants at once
         CU(cudaFuncSetAttribute(emb_gemm_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes(1)));
         CU(cudaFuncSetAttribute(emb_gemm_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes(2)));
         CU(cudaFuncSetAttribute(emb_gemm_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes(1)));
         CU(cudaFuncSetAttribute(emb_gemm_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes(2)));
         CU(cudaFuncSetAttribute(emb_gemm_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_pair_smem_bytes()));
         CU(cudaFuncSetAttribute(emb_gemm_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_pair_smem_bytes()));
-        CU(cudaFuncSetAttribute(emb_gemm_cvt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_cvt_smem_bytes()));
+        CU(cudaFuncSetAttribute(emb_gemm_cvt_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_cvt_smem_bytes(5)));
+        CU(cudaFuncSetAttribute(emb_gemm_cvt_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_cvt_smem_bytes(4)));
         CU(cudaFuncSetAttribute(emb_gemm_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_merge_smem_bytes()));
     }
     auto launch_gemm = [&]() -> int {
-        if (cvt) emb_gemm_cvt_kernel<<<grid, CVT_THREADS, gemm_cvt_smem_bytes(), c->stream>>>(tm_q, tm_x, gp);
+        if (cvt && cvt_stages == 4) emb_gemm_cvt_kernel<4><<<grid, CVT_THREADS, gemm_cvt_smem_bytes(4), c->stream>>>(tm_q, tm_x, gp);
+        else if (cvt) emb_gemm_cvt_kernel<5><<<grid, CVT_THREADS, gemm_cvt_smem_bytes(5), c->stream>>>(tm_q, tm_x, gp);
         else if (pair && !bf16) emb_gemm_pair_kernel<false><<<grid, GEMM_THREADS, gemm_pair_smem_bytes(), c->stream>>>(tm_q, tm_x, gp);
         else if (pair) emb_gemm_pair_kernel<true><<<grid, GEMM_THREADS, gemm_pair_smem_bytes(), c->stream>>>(tm_q, tm_x, gp);
         else if (NG == 1 && !bf16) emb_gemm_kernel<1, false><<<grid, GEMM_THREADS, gemm_smem_bytes(1), c->stream>>>(tm_q, tm_x, gp);
@@ -1151,27 +1158,54 @@ static inline float host_idf(float total_documents, uint64_t corpus_df) {
 }
 
 template <bool MULTI, bool THRESH, bool OMC>
-static int launch_tile_t(oc_ctx *c, const Bm25Params &bp, uint32_t grid, size_t smem) {
+static int launch_tile_t(oc_ctx *c, const Bm25Params &bp, uint32_t grid, size_t smem, cudaStream_t st) {
     // (static smem counts against the 227 KB cap)
     if (smem_cfg_needed(c->device, (const void *)bm25_tile_kernel<MULTI, THRESH, OMC>, smem))
         CU(cudaFuncSetAttribute(bm25_tile_kernel<MULTI, THRESH, OMC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    bm25_tile_kernel<MULTI, THRESH, OMC><<<grid, BM25_THREADS, smem, c->stream>>>(bp);
+    bm25_tile_kernel<MULTI, THRESH, OMC><<<grid, BM25_THREADS, smem, st>>>(bp);
     launched(c);
     CU(cudaGetLastError());
     return OC_OK;
 }
-static int launch_tile(oc_ctx *c, const Bm25Params &bp, uint32_t grid, bool multi, bool thr, bool omc) {
+template <bool THRESH, bool OMC>
+static int launch_tile2_t(oc_ctx *c, const Bm25Params &bp, size_t smem, cudaStream_t st) {
+    if (smem_cfg_needed(c->device, (const void *)bm25_tile2_kernel<THRESH, OMC>, smem))
+        CU(cudaFuncSetAttribute(bm25_tile2_kernel<THRESH, OMC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bm25_tile2_kernel<THRESH, OMC>, BM25_THREADS, smem));
+    const uint64_t items = uint64_t(bp.n_tiles) * bp.n_queries;
+    const uint32_t grid = (uint32_t)std::min<uint64_t>(items, uint64_t(std::max(per_sm, 1)) * c->prop.multiProcessorCount);
+    OCTRY(c->work_ctr.ensure(4));
+    CU(cudaMemsetAsync(c->work_ctr.p, 0, 4, st));
+    bm25_tile2_kernel<THRESH, OMC><<<grid, BM25_THREADS, smem, st>>>(bp, c->work_ctr.as<unsigned int>());
+    launched(c);
+    CU(cudaGetLastError());
+    return OC_OK;
+}
+// multi == false (every token resolves to <= 1 term): the posting-centred persistent kernel; else the slot-scan kernel
+static int launch_tile(oc_ctx *c, const Bm25Params &bp, uint32_t grid, bool multi, bool thr, bool omc, cudaStream_t st) {
+    const char *env = getenv("OC_BM25_TILE2");
+    if (!multi && !(env && env[0] == '0')) {
+        const size_t smem = bm25_tile2_smem_bytes(thr, omc, bp.cap);
+        const int sel = (thr ? 2 : 0) | (omc ? 1 : 0);
+        switch (sel) {
+            case 0: return launch_tile2_t<false, false>(c, bp, smem, st);
+            case 1: return launch_tile2_t<false, true>(c, bp, smem, st);
+            case 2: return launch_tile2_t<true, false>(c, bp, smem, st);
+            default: return launch_tile2_t<true, true>(c, bp, smem, st);
+        }
+    }
     const size_t smem = bm25_smem_bytes(multi, thr, omc, bp.cap);
     const int sel = (multi ? 4 : 0) | (thr ? 2 : 0) | (omc ? 1 : 0);
     switch (sel) {
-        case 0: return launch_tile_t<false, false, false>(c, bp, grid, smem);
-        case 1: return launch_tile_t<false, false, true>(c, bp, grid, smem);
-        case 2: return launch_tile_t<false, true, false>(c, bp, grid, smem);
-        case 3: return launch_tile_t<false, true, true>(c, bp, grid, smem);
-        case 4: return launch_tile_t<true, false, false>(c, bp, grid, smem);
-        case 5: return launch_tile_t<true, false, true>(c, bp, grid, smem);
-        case 6: return launch_tile_t<true, true, false>(c, bp, grid, smem);
-        default: return launch_tile_t<true, true, true>(c, bp, grid, smem);
+        case 0: return launch_tile_t<false, false, false>(c, bp, grid, smem, st);
+        case 1: return launch_tile_t<false, false, true>(c, bp, grid, smem, st);
+        case 2: return launch_tile_t<false, true, false>(c, bp, grid, smem, st);
+        case 3: return launch_tile_t<false, true, true>(c, bp, grid, smem, st);
+        case 4: return launch_tile_t<true, false, false>(c, bp, grid, smem, st);
+        case 5: return launch_tile_t<true, false, true>(c, bp, grid, smem, st);
+        case 6: return launch_tile_t<true, true, false>(c, bp, grid, smem, st);
+        default: return launch_tile_t<true, true, true>(c, bp, grid, smem, st);
     }
 }
 
@@ -1411,7 +1445,7 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
     // (OC_SIDE_STREAM=0 disables it: the step gets ~2.5 % longer, the sweep itself ~4 % shorter — A/B switch)
     const char *senv = getenv("OC_SIDE_STREAM");
     // (single-GPU only for now: the sharded path was measured and validated without it)
-    const bool side = !(senv && senv[0] == '0') && has_v && has_ft && !need_df && !derived_now && !multi_rank;
+    const bool side = !(senv && senv[0] == '0') && has_v && has_ft && !need_df && !derived_now;
     if (!has_v) CU(cudaEventRecord(c->ev[EV_START], c->stream));
     if (c->side_dirty) { CU(cudaStreamSynchronize(c->side)); c->side_dirty = false; }   // leftover of a failed call
     if (side) { CU(cudaStreamWaitEvent(c->side, c->ev[EV_H2D], 0)); c->side_dirty = true; }   // the filter bitmap went up with the query vectors
@@ -1421,25 +1455,16 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
     uint8_t *din = c->in_blob.as<uint8_t>();
     if (filter && !has_v) filter_dev = reinterpret_cast<const uint64_t *>(din + o_flt);
 
-    if (has_v && c->gemm_pending && p->sharded && c->comm.world > 1) {
-        // sharded: every rank must enter the collective exactly once per batch, so the local
-        // proof flags are resolved here, before the exchange (one extra stream sync per batch)
-        OCTRY(c->h_out.ensure(B));
-        CU(cudaMemcpyAsync(c->h_out.p, c->g_flag.p, B, cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
-        uint32_t redone = 0;
-        OCTRY(fix_unproven(c, emb, c->h_out.as<uint8_t>(), B, vlimit, p->similarity, &redone));
-        c->gemm_pending = false;
-    }
-
     // ------------------------------------------------------------ fulltext stage + fusion (re-runnable)
     // arg-max selection (n_keep <= 32) needs no power-of-two buffer; the bitonic fallback does
-    const uint32_t cap = n_keep <= 32 ? n_keep + BM25_CHUNK : next_pow2(n_keep + BM25_CHUNK);
+    // (also >= BM25_SPARSE_MAX: the sparse finish of the posting-centred kernel pushes at most that many candidates)
+    const uint32_t cap = n_keep <= 32 ? std::max<uint32_t>(n_keep + BM25_CHUNK, BM25_SPARSE_MAX) : next_pow2(std::max<uint32_t>(n_keep + BM25_CHUNK, BM25_SPARSE_MAX));
     Bm25Params bp{};
     float *min_hint_dev = nullptr;
     const size_t o_doc = 0, o_sc = size_t(B) * p->limit * 8, o_n = o_sc + size_t(B) * p->limit * 4;
     const size_t o_cnt = (o_n + size_t(B) * 4 + 7) & ~size_t(7), o_min = o_cnt + size_t(B) * 8;
-    const size_t out_bytes = o_min + size_t(B) * 4;
+    const size_t o_gflag = o_min + size_t(B) * 4;                       // sharded: OR over the ranks of the per-query overflow flags
+    const size_t out_bytes = o_gflag + ((size_t(B) + 3) & ~size_t(3));
     const size_t o_resc = out_bytes + ((size_t(B) + 3) & ~size_t(3));
     OCTRY(c->out_blob.ensure(out_bytes));
     OCTRY(c->h_out.ensure(o_resc + size_t(B) * 4));
@@ -1447,13 +1472,13 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
     FuseParams fp{};
     size_t fuse_smem = 0;
     bool did_comm = false;
-    bool side_pending = side;   // first pass only: a re-run (unproven vector hits) stays on the main stream
-    auto device_tail = [&]() -> int {
-    if (has_ft) {
-        const bool on_side = side_pending;
-        side_pending = false;
-        cudaStream_t ps = on_side ? c->side : c->stream;   // stream of the vector-independent prologue
-        if (!on_side) CU(cudaEventRecord(c->ev[EV_BM0], c->stream));
+    // The fulltext stage does not depend on the vector stage (the vector hits' fulltext scores are point lookups
+    // afterwards): in hybrid mode it runs on the side stream, concurrently with the matrix sweep, and is joined
+    // before the lookups and the fusion.  It runs ONCE per call; device_tail (lookups + fusion) is re-runnable.
+    const uint32_t *row_ok = nullptr;
+    auto bm25_stage = [&]() -> int {
+        cudaStream_t ps = side ? c->side : c->stream;
+        CU(cudaEventRecord(c->ev[EV_BM0], ps));
         if (!pre_items.empty()) {
             bm25_precompute_kernel<<<(unsigned)pre_items.size(), 256, 0, ps>>>(
                 reinterpret_cast<const PreDesc *>(din + o_pre), reinterpret_cast<const uint2 *>(din + o_pitems), p->bm25_k);
@@ -1461,7 +1486,6 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
             CU(cudaGetLastError());
         }
         const uint64_t ok_words = uint64_t(n_tiles) * (BM25_TILE / 32);
-        const uint32_t *row_ok = nullptr;
         if (filter || tombs) {
             OCTRY(c->row_ok.ensure(ok_words * 4));
             rows_ok_kernel<<<(unsigned)((ok_words + 255) / 256), 256, 0, ps>>>(
@@ -1478,13 +1502,7 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
                 reinterpret_cast<const TermDesc *>(din + o_terms), (uint32_t)n_td, n_tiles, c->seg.as<uint32_t>());
             launched(c);
         }
-        if (on_side) {   // join: everything below needs the vector hits (main stream) and the plan (side stream)
-            CU(cudaEventRecord(c->ev_side, c->side));
-            CU(cudaStreamWaitEvent(c->stream, c->ev_side, 0));
-            c->side_dirty = false;
-            CU(cudaEventRecord(c->ev[EV_BM0], c->stream));
-        }
-        if (need_df) {
+        if (need_df) {   // (never on the side stream)
             // corpus_df by counting (token_score.rs:262-275), then idf on the host
             const size_t ntok = tokens.size();
             OCTRY(c->df_dev.ensure(ntok * 4));
@@ -1510,17 +1528,6 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
                 if (tok_need_df[t]) tokens[t].idf = host_idf(N, std::max<uint32_t>(1u, dfh[t]));
             CU(cudaMemcpyAsync(din + o_tokens, tokens.data(), ntok * sizeof(TokenDesc), cudaMemcpyHostToDevice, c->stream));
         }
-        // hybrid: vector hits -> string rows
-        if (has_v) {
-            OCTRY(c->v_srow.ensure(size_t(B) * vlimit * 4));
-            OCTRY(c->v_ft.ensure(size_t(B) * vlimit * 4));
-            OCTRY(c->v_present.ensure(size_t(B) * vlimit));
-            map_docs_to_rows_kernel<<<(B * vlimit + 255) / 256, 256, 0, c->stream>>>(
-                c->v_doc.as<uint64_t>(), c->v_cnt.as<uint32_t>(), vlimit, B, S->row_doc, S->n_rows, c->v_srow.as<uint32_t>());
-            launched(c);
-            CU(cudaMemsetAsync(c->v_ft.p, 0, size_t(B) * vlimit * 4, c->stream));
-            CU(cudaMemsetAsync(c->v_present.p, 0, size_t(B) * vlimit, c->stream));
-        }
         const size_t slots = size_t(B) * std::max<uint32_t>(n_tiles, 1);
         OCTRY(c->tau.ensure(size_t(B) * 8));
         OCTRY(c->cand_key.ensure(slots * n_keep * 8));
@@ -1531,7 +1538,7 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
         OCTRY(c->tile_min.ensure(slots * 4));
         OCTRY(c->min_hint.ensure(size_t(B) * 8));
         min_hint_dev = c->min_hint.as<float>();
-        CU(cudaMemsetAsync(c->min_hint.p, 0, size_t(B) * 8, c->stream));
+        CU(cudaMemsetAsync(c->min_hint.p, 0, size_t(B) * 8, ps));
         bp.terms = reinterpret_cast<const TermDesc *>(din + o_terms);
         bp.tokens = reinterpret_cast<const TokenDesc *>(din + o_tokens);
         bp.queries = reinterpret_cast<const QueryDesc *>(din + o_queries);
@@ -1543,9 +1550,9 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
         bp.omc_row = omc_tile ? reinterpret_cast<const uint32_t *>(din + o_omcr) : nullptr;
         bp.omc_mult = omc_tile ? reinterpret_cast<const float *>(din + o_omcrm) : nullptr;
         bp.n_omc = (uint32_t)omc_rows.size();
-        bp.v_row = has_v ? c->v_srow.as<uint32_t>() : nullptr;
+        bp.v_row = nullptr;            // the hybrid lookups are point lookups (bm25_point_kernel)
         bp.v_stride = vlimit;
-        bp.v_ft = c->v_ft.as<float>(); bp.v_present = c->v_present.as<uint8_t>();
+        bp.v_ft = nullptr; bp.v_present = nullptr;
         bp.min_hint = min_hint_dev;
         bp.n_keep = n_keep; bp.cap = cap;
         bp.tau = c->tau.as<unsigned long long>();
@@ -1553,10 +1560,36 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
         bp.cand_cnt = c->cand_cnt.as<uint32_t>(); bp.tile_count = c->tile_cnt.as<uint32_t>();
         bp.tile_max = c->tile_max.as<float>(); bp.tile_min = c->tile_min.as<float>();
         bp.tile_first = 0;
-        CU(cudaMemsetAsync(c->tau.p, 0, size_t(B) * 8, c->stream));
-        if (n_tiles) OCTRY(launch_tile(c, bp, n_tiles * B, any_multi, thr, omc_tile));
-        CU(cudaEventRecord(c->ev[EV_BM1], c->stream));
+        CU(cudaMemsetAsync(c->tau.p, 0, size_t(B) * 8, ps));
+        if (n_tiles) OCTRY(launch_tile(c, bp, n_tiles * B, any_multi, thr, omc_tile, ps));
+        CU(cudaEventRecord(c->ev[EV_BM1], ps));
         c->timing.bm25_postings = postings_walked;
+        if (side) {   // join: the lookups and the fusion need the vector hits (main stream) and the tiles (side stream)
+            CU(cudaEventRecord(c->ev_side, c->side));
+            CU(cudaStreamWaitEvent(c->stream, c->ev_side, 0));
+            c->side_dirty = false;
+        }
+        return OC_OK;
+    };
+    if (has_ft) OCTRY(bm25_stage());
+
+    auto device_tail = [&]() -> int {
+    if (has_ft && has_v) {
+        // hybrid: vector hits -> string rows -> their fulltext scores (point lookups)
+        OCTRY(c->v_srow.ensure(size_t(B) * vlimit * 4));
+        OCTRY(c->v_ft.ensure(size_t(B) * vlimit * 4));
+        OCTRY(c->v_present.ensure(size_t(B) * vlimit));
+        map_docs_to_rows_kernel<<<(B * vlimit + 255) / 256, 256, 0, c->stream>>>(
+            c->v_doc.as<uint64_t>(), c->v_cnt.as<uint32_t>(), vlimit, B, S->row_doc, S->n_rows, c->v_srow.as<uint32_t>());
+        launched(c);
+        PointParams pp{};
+        pp.terms = bp.terms; pp.tokens = bp.tokens; pp.queries = bp.queries;
+        pp.n_queries = B; pp.v_stride = vlimit; pp.v_row = c->v_srow.as<uint32_t>(); pp.row_ok_bits = row_ok;
+        pp.k = p->bm25_k; pp.threshold = thr ? 1 : 0;
+        pp.v_ft = c->v_ft.as<float>(); pp.v_present = c->v_present.as<uint8_t>();
+        bm25_point_kernel<<<(B * vlimit * 32 + 255) / 256, 256, 0, c->stream>>>(pp);
+        launched(c);
+        CU(cudaGetLastError());
     }
 
     // ------------------------------------------------------------ fusion + top-n (+ shard exchange)
@@ -1589,7 +1622,8 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
 
     if (p->sharded && c->comm.world > 1) {
         CU(cudaEventRecord(c->ev[EV_FUSE0], c->stream));
-        OCTRY(run_sharded_merge(c, p, fp, has_ft ? (uint32_t)S->n_rows : 0, has_v ? (uint32_t)emb->n_rows : 0, B));
+        OCTRY(run_sharded_merge(c, p, fp, has_ft ? (uint32_t)S->n_rows : 0, has_v ? (uint32_t)emb->n_rows : 0, B,
+                                (has_v && c->gemm_pending) ? c->g_flag.as<uint8_t>() : nullptr, dout + o_gflag));
         CU(cudaEventRecord(c->ev[EV_FUSE1], c->stream));
         did_comm = true;
     } else {
@@ -1611,14 +1645,21 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
     }
     CU(cudaEventRecord(c->ev[EV_D2H], c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    if (c->gemm_pending) {   // tensor-core scan: re-run the (rare) queries whose candidate buffers overflowed
-        uint64_t resc = 0;
-        for (uint32_t q = 0; q < B; q++) resc += reinterpret_cast<const uint32_t *>(h + o_resc)[q];
-        c->timing.scan_rescored = (uint32_t)(resc / B);
+    {   // tensor-core scan: re-run the (rare) queries whose candidate buffers overflowed
+        // sharded: every rank must enter the collective the same number of times, so the decision to re-run is
+        // taken on the flags all ranks exchanged inside the shard records (no host sync before the collective),
+        // by every rank — also one whose own shard was served by the exact sweep
+        bool rerun = false;
+        if (did_comm && has_v) for (uint32_t q = 0; q < B; q++) rerun = rerun || h[o_gflag + q] != 0;
         uint32_t redone = 0;
-        CU(cudaEventRecord(c->ev[EV_RR0], c->stream));
-        OCTRY(fix_unproven(c, emb, h + out_bytes, B, vlimit, p->similarity, &redone));
-        if (redone) {
+        if (c->gemm_pending || rerun) CU(cudaEventRecord(c->ev[EV_RR0], c->stream));
+        if (c->gemm_pending) {
+            uint64_t resc = 0;
+            for (uint32_t q = 0; q < B; q++) resc += reinterpret_cast<const uint32_t *>(h + o_resc)[q];
+            c->timing.scan_rescored = (uint32_t)(resc / B);
+            OCTRY(fix_unproven(c, emb, h + out_bytes, B, vlimit, p->similarity, &redone));
+        }
+        if (redone || rerun) {
             c->gemm_pending = false;
             OCTRY(device_tail());
             CU(cudaMemcpyAsync(h, dout, out_bytes, cudaMemcpyDeviceToHost, c->stream));
@@ -1637,7 +1678,7 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
         if (redo) {
             CU(cudaMemcpyAsync(min_hint_dev, mins, size_t(B) * 4, cudaMemcpyHostToDevice, c->stream));
             CU(cudaMemsetAsync(c->tau.p, 0, size_t(B) * 8, c->stream));
-            OCTRY(launch_tile(c, bp, n_tiles * B, any_multi, thr, omc_tile));
+            OCTRY(launch_tile(c, bp, n_tiles * B, any_multi, thr, omc_tile, c->stream));
             fuse_topk_kernel<<<B, 256, fuse_smem, c->stream>>>(fp);
             launched(c);
             CU(cudaMemcpyAsync(c->h_out.p, dout, out_bytes, cudaMemcpyDeviceToHost, c->stream));

@@ -588,7 +588,7 @@ emb_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 //   per CTA: 5 stages x (32 KB fp32 X tile, converted IN PLACE into its first 16 KB, + 8 KB bf16 Q):
 //   a stage cycles TMA -> convert -> MMA -> free, so ~3 stages (96 KB) are in flight from HBM per SM.
 // ---------------------------------------------------------------------------------------
-constexpr uint32_t CVT_STAGES = 5;
+constexpr uint32_t CVT_STAGES_DEFAULT = 5;               // ring depth: template parameter of the kernel (4 leaves room for a co-resident BM25 CTA)
 constexpr uint32_t CVT_PREFETCH = 0;                     // K-blocks (32 KB per CTA each) prefetched into L2 ahead of the ring
 constexpr uint32_t CVT_RAW_BYTES = 256 * 128;             // 256 rows x 32 fp32
 constexpr uint32_t CVT_XOP_BYTES = 256 * 64;              // 256 rows x 32 bf16 (two 128-row B tiles of 8 KB)
@@ -598,8 +598,8 @@ constexpr uint32_t CVT_WARPS = 4;
 constexpr int CVT_THREADS = GEMM_THREADS + CVT_WARPS * 32;   // warps 10-13 convert
 constexpr float GEMM_EPS_BF16X2 = 8.0e-3f;                // both operands rounded to bf16: 2*2^-8 + 2^-16 + accumulation
 
-__host__ __device__ inline size_t gemm_cvt_smem_bytes() {
-    return 1024 + size_t(CVT_STAGES) * CVT_STAGE_BYTES + 2 * PAIR_TILE_ROWS * 4 + 256;
+__host__ __device__ inline size_t gemm_cvt_smem_bytes(uint32_t stages = CVT_STAGES_DEFAULT) {
+    return 1024 + size_t(stages) * CVT_STAGE_BYTES + 2 * PAIR_TILE_ROWS * 4 + 256;
 }
 // K-major SWIZZLE_64B descriptor: 64-byte rows, 8-row groups 512 B apart
 __device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
@@ -613,6 +613,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2_rn(float lo, float hi) {
     return r;
 }
 
+template <uint32_t CVT_STAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CVT_THREADS, 1)
 emb_gemm_cvt_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_x, const GemmParams p) {
     extern __shared__ __align__(1024) uint8_t smem_gemm[];

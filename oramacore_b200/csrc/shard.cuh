@@ -13,16 +13,17 @@
 // after which every rank runs the same merge kernel: global vector top-`limit` by distance,
 // global max/min, fused scores (token_score.rs:393-422), OMC (search.rs:39-48), global
 // top-n, count = sum(local counts) + |V \ FT| — bit-identical to the single-GPU kernel.
-// Payload at B=256, limit=10: 256 * (32 + 10*16 + 10*32) B = 131 KB per rank: latency-bound.
+// Payload at B=256, limit=10: 256 * (40 + 10*16 + 10*32) B = 133 KB per rank: latency-bound.
 #pragma once
 
 namespace oc {
 
-struct ShardHdr {          // 32 B
+struct ShardHdr {          // 40 B
     unsigned long long count_ft;
     float max_ft, min_ft;
     uint32_t n_ft, n_v;
     uint32_t n_rows_str, n_rows_emb;
+    uint32_t unproven, pad;   // this rank's tensor-core scan overflowed for the query: every rank re-runs the batch tail
 };
 struct ShardFt {           // 16 B
     uint64_t doc;
@@ -43,6 +44,7 @@ struct ShardPackParams {
     const float *v_raw;        // [q][v_stride] -distance of each local vector hit
     const uint32_t *v_erow;    // [q][v_stride] embedding row of each hit
     uint32_t n_rows_str, n_rows_emb;
+    const uint8_t *unproven;   // [q] local overflow flags of the tensor-core scan, or NULL
     uint8_t *out;              // [q] records
 };
 
@@ -150,6 +152,7 @@ __global__ void __launch_bounds__(256) shard_pack_kernel(const ShardPackParams p
     if (tid == 0) {
         hdr->count_ft = s_count; hdr->max_ft = f32_unordered(s_maxo); hdr->min_ft = f32_unordered(s_mino);
         hdr->n_ft = got; hdr->n_v = vc; hdr->n_rows_str = pp.n_rows_str; hdr->n_rows_emb = pp.n_rows_emb;
+        hdr->unproven = pp.unproven ? pp.unproven[q] : 0u; hdr->pad = 0u;
     }
 }
 
@@ -160,6 +163,7 @@ struct ShardFuseParams {
     uint32_t n_keep, limit, offset, v_stride, capb;
     const uint64_t *omc_doc; const float *omc_mult; uint32_t n_omc;
     uint64_t *out_doc; float *out_score; uint32_t *out_n; unsigned long long *out_count; float *out_min;
+    uint8_t *out_flag;        // [q] 1 if any rank flagged the query (identical on every rank)
 };
 
 constexpr uint32_t SHARD_MAX_WORLD = 16;
@@ -327,13 +331,16 @@ __global__ void __launch_bounds__(256) shard_fuse_kernel(const ShardFuseParams p
         p.out_n[q] = n_out;
         p.out_count[q] = s_count;
         if (p.out_min) p.out_min[q] = gmin;
+        uint32_t fl = 0;
+        for (uint32_t s = 0; s < W; s++) fl |= hdr_of(s)->unproven;
+        if (p.out_flag) p.out_flag[q] = fl ? 1 : 0;
     }
 }
 
 }  // namespace oc
 
 static int run_sharded_merge(oc_ctx *c, const oc_search_params *p, const oc::FuseParams &fp, uint32_t n_rows_str,
-                             uint32_t n_rows_emb, uint32_t B) {
+                             uint32_t n_rows_emb, uint32_t B, const uint8_t *unproven_dev, uint8_t *out_flag_dev) {
     using namespace oc;
     const uint32_t W = (uint32_t)c->comm.world;
     if (W > SHARD_MAX_WORLD) return fail(OC_ERR_UNSUPPORTED, "world size %u > %u", W, SHARD_MAX_WORLD);
@@ -345,6 +352,7 @@ static int run_sharded_merge(oc_ctx *c, const oc_search_params *p, const oc::Fus
     pp.v_raw = c->v_raw.as<float>();
     pp.v_erow = c->v_row.as<uint32_t>();
     pp.n_rows_str = n_rows_str; pp.n_rows_emb = n_rows_emb;
+    pp.unproven = unproven_dev;
     pp.out = c->shard_send.as<uint8_t>();
     const size_t pack_smem = size_t(fp.capb) * 8 + size_t(std::max<uint32_t>(32, next_pow2(fp.n_keep))) * 8 + 64;
     if (smem_cfg_needed(c->device, (const void *)shard_pack_kernel, pack_smem))
@@ -362,6 +370,7 @@ static int run_sharded_merge(oc_ctx *c, const oc_search_params *p, const oc::Fus
     sp.capb = std::max<uint32_t>(sp.capb, next_pow2(2 * std::max(fp.n_keep, fp.v_stride)));
     sp.omc_doc = fp.omc_doc; sp.omc_mult = fp.omc_mult; sp.n_omc = fp.n_omc;
     sp.out_doc = fp.out_doc; sp.out_score = fp.out_score; sp.out_n = fp.out_n; sp.out_count = fp.out_count; sp.out_min = fp.out_min;
+    sp.out_flag = out_flag_dev;
     const size_t fsmem = size_t(sp.capb) * 8 + size_t(fp.v_stride) * 36 + 64;
     if (smem_cfg_needed(c->device, (const void *)shard_fuse_kernel, fsmem))
         CU(cudaFuncSetAttribute(shard_fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
