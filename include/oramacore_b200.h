@@ -43,6 +43,7 @@ extern "C" {
 typedef struct oc_ctx oc_ctx;   /* one device + stream + workspace (one per process/GPU)  */
 typedef struct oc_emb oc_emb;   /* == one EmbeddingFieldStorage (embedding_field.rs:29-34) */
 typedef struct oc_str oc_str;   /* == the StringFieldStorage set of one Index (string_field.rs:32-36) */
+typedef struct oc_filter oc_filter; /* == a FilterResult<DocumentId> evaluated to a bitmap on the device (filter.rs:344-392) */
 
 const char *oc_last_error(void);
 int oc_version(void);
@@ -181,13 +182,73 @@ typedef struct {
     const uint64_t *omc_doc_ids;       /* OMC multipliers sorted by doc id (index/mod.rs:1720-1739) */
     const float *omc_mult;
     uint64_t n_omc;
-    int sharded;                       /* OC_SHARDED [| OC_SHARD_TOMBSTONES] => merge across oc_comm ranks */
+    int sharded;                       /* OC_SHARDED [| OC_SHARD_TOMBSTONES | OC_SHARD_COUNT_DF] => merge across oc_comm ranks */
+    uint32_t vector_limit;             /* 0 => limit.  Candidate depth of the vector stage = limit_hint, which the
+                                          reference keeps at `limit` while top_n takes limit+offset (search.rs:330-336):
+                                          a caller that needs the rows [0, limit+offset) of one index (multi-index
+                                          union, oc_merge_results) asks for limit' = limit+offset, vector_limit = limit */
+    const struct oc_filter *filter;    /* NULL, or a device-resident DocumentId bitmap (oc_filter_*): takes precedence
+                                          over filter_bits and is not re-uploaded per call                           */
 } oc_search_params;
 
 /* out_doc_ids/out_scores: B x limit (best first, after offset); out_n[b] hits written;
  * out_count[b] = all matching documents. emb may be NULL for fulltext, str NULL for vector. */
 int oc_search(oc_ctx *ctx, oc_emb *emb, oc_str *str, const oc_search_params *p,
               uint64_t *out_doc_ids, float *out_scores, uint32_t *out_n, uint64_t *out_count);
+
+/* ---- filters on the device -------------------------------------------------------------------------
+ * FilterContext::execute_filter (read/index/filter.rs:344-392) yields a FilterResult tree: And / Or / Not over
+ * plain DocumentId sets (:351-362, 378-389), consulted by the scorers through contains(doc)
+ * (embedding_field.rs:54-61, string_field.rs:66-69).  Here a FilterResult is a bitmap over DocumentId
+ * [0, nbits) that lives on the device: build the leaves from id lists, combine with And / Or / Not (word-wise
+ * kernels), hand the handle to any number of oc_search / oc_search_facets calls (no per-call upload).
+ * execute_filter's own rule — AND the where-filter with NOT(uncommitted deletes) — is oc_filter_and +
+ * oc_filter_not over an id leaf of the deleted documents. */
+int oc_filter_from_ids(oc_ctx *ctx, const uint64_t *doc_ids, uint64_t n, uint64_t nbits, oc_filter **out);  /* PlainFilterResult::from_iter; ids >= nbits ignored */
+int oc_filter_from_bits(oc_ctx *ctx, const uint64_t *bits, uint64_t nbits, oc_filter **out);
+int oc_filter_and(const oc_filter *a, const oc_filter *b, oc_filter **out);   /* FilterResult::And */
+int oc_filter_or(const oc_filter *a, const oc_filter *b, oc_filter **out);    /* FilterResult::Or  */
+int oc_filter_not(const oc_filter *a, oc_filter **out);                       /* FilterResult::Not (within [0, nbits)) */
+int oc_filter_count(const oc_filter *f, uint64_t *out);                       /* documents that pass */
+int oc_filter_read(const oc_filter *f, uint64_t *out_bits /* (nbits+63)/64 words */);
+void oc_filter_destroy(oc_filter *f);
+
+/* ---- facets over the score set ------------------------------------------------------------------
+ * FacetContext::execute (read/index/facet.rs:147-209): for each requested variant of a filter field — bool
+ * true / false (bool_field.rs:182-208), a number range [from, to], both ends inclusive (number_field.rs:368-387,
+ * NumberFilter::Between), a string_filter key (string_filter_field.rs:175-193) — the number of the variant's
+ * documents that are keys of the score map.  The store keeps, per field, the variants' document lists on the
+ * device (number fields: documents sorted by value, so a range is a slice); a search in facet mode makes the tile
+ * scorer emit the bitmap of matched documents (+ the vector hits) and one kernel counts every (query, variant).
+ * As in the reference (search.rs:361-396) the score map is computed WITHOUT the where-filter (uncommitted deletes
+ * stay excluded), so p->filter_bits / p->filter are ignored here: hits come from oc_search, facets from this call.
+ * A document may be listed under several variants (array values).  nbits: DocumentId space [0, nbits). */
+typedef struct oc_facets oc_facets;
+typedef struct {
+    uint32_t field;     /* id returned by oc_facets_add_*                                     */
+    uint32_t variant;   /* bool / string fields: variant index                                */
+    double from, to;    /* number fields: inclusive range                                     */
+} oc_facet_req;
+int oc_facets_create(oc_ctx *ctx, uint64_t nbits, oc_facets **out);
+void oc_facets_destroy(oc_facets *f);
+int oc_facets_add_field(oc_facets *f, uint32_t n_variants, const uint64_t *variant_offsets /* n+1 */, const uint64_t *doc_ids,
+                        uint32_t *out_field);
+int oc_facets_add_number_field(oc_facets *f, uint64_t n, const double *values_sorted, const uint64_t *doc_ids, uint32_t *out_field);
+/* out_counts: n_queries x n_reqs.  emb / str as for oc_search (the mode decides which are needed). */
+int oc_search_facets(oc_ctx *ctx, oc_emb *emb, oc_str *str, oc_facets *facets, const oc_search_params *p,
+                     const oc_facet_req *reqs, uint32_t n_reqs, uint64_t *out_counts);
+
+/* ---- multi-index collections ---------------------------------------------------------------------
+ * search_on_indexes runs every index of a collection into ONE score map (read/search.rs:304-338,
+ * token_score.rs:472-499): document ids are unique per collection, so the per-index maps are disjoint; hybrid
+ * normalisation is per index; count = sum of the per-index counts; then one top_n(limit+offset) and
+ * skip(offset).take(limit) (search.rs:482-498).  The caller runs oc_search once per index with
+ * limit' = limit+offset, offset' = 0, vector_limit = limit and merges here (host; k sorted lists of <= limit'
+ * entries).  in_stride = limit' (row stride of the per-index arrays).  Ties: ascending document id. */
+int oc_merge_results(uint32_t n_indexes, uint32_t n_queries, uint32_t limit, uint32_t offset, uint32_t in_stride,
+                     const uint64_t *const *doc_ids, const float *const *scores, const uint32_t *const *n,
+                     const uint64_t *const *counts, uint64_t *out_doc_ids /* B x limit */, float *out_scores,
+                     uint32_t *out_n, uint64_t *out_count);
 
 /* ---- term dictionary and query-term resolution (host only; no device needed) ------------------------
  * The step the reference performs before the posting walk: TextParser::tokenize_and_stem(term) —

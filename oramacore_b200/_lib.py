@@ -24,6 +24,9 @@ EXPORTED_SYMBOLS = [
     "oc_emb_info", "oc_emb_search", "oc_str_create", "oc_str_destroy", "oc_str_set_rows", "oc_str_load_field",
     "oc_str_insert", "oc_str_commit", "oc_str_delete", "oc_str_info", "oc_str_set_global", "oc_search", "oc_pinned_alloc", "oc_pinned_free", "oc_last_timing", "oc_launch_count",
     "oc_batcher_create", "oc_batcher_destroy", "oc_batcher_search", "oc_batcher_stats",
+    "oc_filter_from_ids", "oc_filter_from_bits", "oc_filter_and", "oc_filter_or", "oc_filter_not", "oc_filter_count",
+    "oc_filter_read", "oc_filter_destroy", "oc_merge_results",
+    "oc_facets_create", "oc_facets_destroy", "oc_facets_add_field", "oc_facets_add_number_field", "oc_search_facets",
     "oc_dict_create", "oc_dict_destroy", "oc_dict_add_terms", "oc_dict_lookup", "oc_dict_size", "oc_dict_set_stemmer",
     "oc_dict_resolve", "oc_resolved_arrays", "oc_resolved_fill", "oc_resolved_free",
 ]
@@ -53,7 +56,11 @@ class SearchParams(C.Structure):
                 ("term_field", C.c_void_p), ("term_id", C.c_void_p), ("term_weight", C.c_void_p),
                 ("filter_bits", C.c_void_p), ("filter_nbits", C.c_uint64),
                 ("omc_doc_ids", C.c_void_p), ("omc_mult", C.c_void_p), ("n_omc", C.c_uint64),
-                ("sharded", C.c_int)]
+                ("sharded", C.c_int), ("vector_limit", C.c_uint32), ("filter", C.c_void_p)]
+
+
+class FacetReq(C.Structure):
+    _fields_ = [("field", C.c_uint32), ("variant", C.c_uint32), ("from_", C.c_double), ("to", C.c_double)]
 
 
 class ResolveParams(C.Structure):
@@ -136,6 +143,22 @@ def lib():
     L.oc_batcher_destroy.restype = None
     L.oc_batcher_search.argtypes = [vp, C.POINTER(SearchParams), vp, vp, vp, vp]
     L.oc_batcher_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
+    L.oc_filter_from_ids.argtypes = [vp, vp, u64, u64, C.POINTER(vp)]
+    L.oc_filter_from_bits.argtypes = [vp, vp, u64, C.POINTER(vp)]
+    L.oc_filter_and.argtypes = [vp, vp, C.POINTER(vp)]
+    L.oc_filter_or.argtypes = [vp, vp, C.POINTER(vp)]
+    L.oc_filter_not.argtypes = [vp, C.POINTER(vp)]
+    L.oc_filter_count.argtypes = [vp, C.POINTER(u64)]
+    L.oc_filter_read.argtypes = [vp, vp]
+    L.oc_filter_destroy.argtypes = [vp]
+    L.oc_filter_destroy.restype = None
+    L.oc_facets_create.argtypes = [vp, u64, C.POINTER(vp)]
+    L.oc_facets_destroy.argtypes = [vp]
+    L.oc_facets_destroy.restype = None
+    L.oc_facets_add_field.argtypes = [vp, u32, vp, vp, C.POINTER(u32)]
+    L.oc_facets_add_number_field.argtypes = [vp, u64, vp, vp, C.POINTER(u32)]
+    L.oc_search_facets.argtypes = [vp, vp, vp, vp, C.POINTER(SearchParams), C.POINTER(FacetReq), u32, vp]
+    L.oc_merge_results.argtypes = [u32, u32, u32, u32, u32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), vp, vp, vp, vp]
     L.oc_dict_create.argtypes = [u32, C.POINTER(vp)]
     L.oc_dict_destroy.argtypes = [vp]
     L.oc_dict_destroy.restype = None

@@ -21,20 +21,20 @@
 namespace ocb {
 
 struct BatchKey {
-    int mode; uint32_t limit, offset; float similarity, threshold, k, b;
+    int mode; uint32_t limit, offset; float similarity, threshold, k, b; uint32_t vector_limit;
     bool operator==(const BatchKey &o) const {
-        return mode == o.mode && limit == o.limit && offset == o.offset && memcmp(&similarity, &o.similarity, 4) == 0 &&
+        return mode == o.mode && limit == o.limit && offset == o.offset && vector_limit == o.vector_limit && memcmp(&similarity, &o.similarity, 4) == 0 &&
                memcmp(&threshold, &o.threshold, 4) == 0 && memcmp(&k, &o.k, 4) == 0 && memcmp(&b, &o.b, 4) == 0;
     }
 };
 inline BatchKey key_of(const oc_search_params *p) {
-    return BatchKey{p->mode, p->limit, p->offset, p->similarity, p->threshold, p->bm25_k, p->bm25_b};
+    return BatchKey{p->mode, p->limit, p->offset, p->similarity, p->threshold, p->bm25_k, p->bm25_b, p->vector_limit};
 }
 // has_emb / has_str: the stores the batcher was created with.  A call that oc_search would reject
 // (unknown mode, missing store, NULL query arrays) is NOT batchable: it goes straight to the
 // executor so the caller gets oc_search's normal error instead of a merge that dereferences NULL.
 inline bool batchable(const oc_search_params *p, bool has_emb = true, bool has_str = true) {
-    if (p->n_queries != 1 || p->filter_bits || p->n_omc != 0 || p->sharded) return false;
+    if (p->n_queries != 1 || p->filter_bits || p->filter || p->n_omc != 0 || p->sharded) return false;
     if (p->mode != OC_MODE_FULLTEXT && p->mode != OC_MODE_VECTOR && p->mode != OC_MODE_HYBRID) return false;
     const bool need_v = p->mode != OC_MODE_FULLTEXT, need_ft = p->mode != OC_MODE_VECTOR;
     if (need_v && (!has_emb || !p->q_vecs)) return false;

@@ -146,6 +146,8 @@ struct Bm25Params {
     uint32_t *tile_count;         // matched docs
     float *tile_max, *tile_min;   // pre-OMC extrema (fold start 0.0, token_score.rs:398-401)
     uint32_t tile_first;          // first tile handled by this launch (sharding of launches)
+    uint32_t *matched_bits;       // NULL, or out: [n_queries][n_tiles * TILE/32] bitmap of the matched rows (the keys of the
+                                  // score map) — what the facet counts run over (read/index/facet.rs:147-209)
 };
 
 __host__ __device__ inline size_t bm25_smem_bytes(bool multi, bool threshold, bool omc, uint32_t cap) {
@@ -269,6 +271,7 @@ __global__ void __launch_bounds__(BM25_THREADS) bm25_tile_kernel(const Bm25Param
     __shared__ uint32_t s_cnt, s_matched;
     __shared__ unsigned int s_maxo, s_mino;   // extrema in order-preserving uint space
     __shared__ unsigned long long s_tau;
+    __shared__ uint32_t s_mbits[BM25_TILE / 32];
 
     const uint32_t q = blockIdx.x % p.n_queries;
     const uint32_t tile = p.tile_first + blockIdx.x / p.n_queries;
@@ -286,6 +289,7 @@ __global__ void __launch_bounds__(BM25_THREADS) bm25_tile_kernel(const Bm25Param
     if (use_ok)
         for (uint32_t i = tid; i < BM25_TILE / 32; i += BM25_THREADS) okb[i] = p.row_ok_bits[row0 / 32 + i];
     if (tid == 0) { s_cnt = 0; s_matched = 0; s_maxo = f32_ordered(0.f); s_mino = f32_ordered(0.f); s_tau = p.tau[q]; }
+    if (p.matched_bits) s_mbits[tid] = 0u;
     __syncthreads();
 
     // ------------------------------------------------ accumulate, token by token, term by term.
@@ -477,6 +481,7 @@ __global__ void __launch_bounds__(BM25_THREADS) bm25_tile_kernel(const Bm25Param
                     const float s = sv[u];
                     const bool present = s != 0.f;
                     matched += present ? 1u : 0u;
+                    if (p.matched_bits && present) atomicOr(&s_mbits[(l0 + u) >> 5], 1u << ((l0 + u) & 31));
                     lmax = fmaxf(lmax, s);
                     lmin = fminf(lmin, s);
                     float proxy = __fsub_rn(s, mh);
@@ -554,6 +559,7 @@ __global__ void __launch_bounds__(BM25_THREADS) bm25_tile_kernel(const Bm25Param
         p.tile_max[slot_base] = f32_unordered(s_maxo);
         p.tile_min[slot_base] = f32_unordered(s_mino);
     }
+    if (p.matched_bits) p.matched_bits[slot_base * (BM25_TILE / 32) + tid] = s_mbits[tid];
 }
 
 
@@ -598,10 +604,12 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_tile2_kernel(const Bm25P
     __shared__ const uint2 *t_ptr[BM25_MAX_TOK];
     __shared__ uint32_t t_n[BM25_MAX_TOK], t_bit[BM25_MAX_TOK], t_pre[BM25_MAX_TOK];
     __shared__ float t_w[BM25_MAX_TOK], t_idf[BM25_MAX_TOK];
+    __shared__ uint32_t s_mbits[BM25_TILE / 32];
 
     const uint32_t tid = threadIdx.x;
     const float kp1 = __fadd_rn(p.k, 1.0f);
     const bool use_ok = p.row_ok_bits != nullptr;
+    const bool want_bits = p.matched_bits != nullptr;
     const uint32_t n_items = p.n_tiles * p.n_queries;
 
     for (uint32_t i = tid; i < BM25_TILE / 4; i += BM25_THREADS) {
@@ -614,6 +622,7 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_tile2_kernel(const Bm25P
             s_item = atomicAdd(work_counter, 1u);
             s_cnt = 0; s_matched = 0; s_ovf = 0; s_maxo = f32_ordered(0.f); s_mino = f32_ordered(0.f);
         }
+        if (want_bits) s_mbits[tid] = 0u;
         __syncthreads();
         const uint32_t item = s_item;
         if (item >= n_items) break;
@@ -697,6 +706,7 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_tile2_kernel(const Bm25P
         const uint64_t rows_here = min(uint64_t(BM25_TILE), p.n_rows - row0);
         auto visit = [&](float s, uint32_t l) -> bool {   // one matched row; returns true when it pushed a candidate
             matched++;
+            if (want_bits) atomicOr(&s_mbits[l >> 5], 1u << (l & 31));
             lmax = fmaxf(lmax, s);
             lmin = fminf(lmin, s);
             float proxy = __fsub_rn(s, mh);
@@ -809,6 +819,7 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_tile2_kernel(const Bm25P
             p.tile_max[slot_base] = f32_unordered(s_maxo);
             p.tile_min[slot_base] = f32_unordered(s_mino);
         }
+        if (want_bits) p.matched_bits[slot_base * (BM25_TILE / 32) + tid] = s_mbits[tid];
         if (!sparse && total != 0) {
             __syncthreads();                               // emit read the scores
             for (uint32_t i = tid; i < BM25_TILE / 4; i += BM25_THREADS) {   // leave the accumulators clean

@@ -145,7 +145,7 @@ struct oc_ctx {
     // workspaces
     DevBuf in_blob, in_blob0, q_pad, q_inv, eff_norm, filter_dev, scan_cand, v_doc, v_score, v_row, v_cnt, v_srow, v_ft, v_present, v_raw;
     DevBuf seg, df_dev, row_ok, tau, cand_key, cand_ft, cand_cnt, tile_cnt, tile_max, tile_min, min_hint;
-    DevBuf out_blob, shard_send, shard_recv, work_ctr;
+    DevBuf out_blob, shard_send, shard_recv, work_ctr, mbits, dbits, facet_req, facet_out;
     bool gemm_pending = false; const float *gemm_inv_norm = nullptr;
     DevBuf q_bf16, q_rho, pre_post, g_thr, g_eps, g_ovf, g_ovfcnt, g_resc, g_cand, g_cnt, g_flag, g_max, r_qpad, r_qinv, r_map, r_doc, r_score, r_row, r_cnt, r_raw;
 
@@ -190,7 +190,7 @@ extern "C" void oc_shutdown(oc_ctx *c) {
     DevBuf *bufs[] = {&c->in_blob, &c->q_pad, &c->q_inv, &c->eff_norm, &c->filter_dev, &c->scan_cand, &c->v_doc,
                       &c->v_score, &c->v_row, &c->v_cnt, &c->v_srow, &c->v_ft, &c->v_present, &c->v_raw, &c->seg, &c->df_dev,
                       &c->row_ok, &c->tau, &c->cand_key, &c->cand_ft, &c->cand_cnt, &c->tile_cnt, &c->tile_max,
-                      &c->tile_min, &c->min_hint, &c->out_blob, &c->shard_send, &c->shard_recv, &c->work_ctr, &c->q_bf16, &c->q_rho, &c->pre_post, &c->g_thr, &c->g_eps, &c->g_ovf, &c->g_ovfcnt, &c->g_resc, &c->g_cand, &c->g_cnt, &c->g_max,
+                      &c->tile_min, &c->min_hint, &c->out_blob, &c->shard_send, &c->shard_recv, &c->work_ctr, &c->mbits, &c->dbits, &c->facet_req, &c->facet_out, &c->q_bf16, &c->q_rho, &c->pre_post, &c->g_thr, &c->g_eps, &c->g_ovf, &c->g_ovfcnt, &c->g_resc, &c->g_cand, &c->g_cnt, &c->g_max,
                       &c->g_flag, &c->r_qpad, &c->r_qinv, &c->r_map, &c->r_doc, &c->r_score, &c->r_row, &c->r_cnt, &c->r_raw};
     for (DevBuf *b : bufs) b->release();
     c->h_in.release(); c->h_out.release();
@@ -1149,6 +1149,165 @@ extern "C" int oc_str_info(oc_str *s, oc_str_info_t *out) {
     return OC_OK;
 }
 
+// ------------------------------------------------------------------------------------ device-resident filters
+struct oc_facets;
+struct oc_filter {
+    oc_ctx *ctx;
+    uint64_t nbits, words;
+    uint64_t *bits = nullptr;   // device
+};
+__global__ void filter_scatter_ids_kernel(const uint64_t *ids, uint64_t n, uint64_t nbits, unsigned long long *bits) {
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t d = ids[i];
+    if (d < nbits) atomicOr(bits + (d >> 6), 1ull << (d & 63));
+}
+// op: 0 and, 1 or, 2 not(a); the padding bits of the last word stay clear
+__global__ void filter_combine_kernel(const uint64_t *a, const uint64_t *b, uint64_t words, uint64_t nbits, int op, uint64_t *out) {
+    const uint64_t w = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (w >= words) return;
+    uint64_t v = op == 0 ? (a[w] & b[w]) : op == 1 ? (a[w] | b[w]) : ~a[w];
+    if (w == words - 1 && (nbits & 63)) v &= (1ull << (nbits & 63)) - 1;
+    out[w] = v;
+}
+__global__ void filter_popcount_kernel(const uint64_t *a, uint64_t words, unsigned long long *out) {
+    uint64_t c = 0;
+    for (uint64_t w = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; w < words; w += uint64_t(gridDim.x) * blockDim.x) c += __popcll(a[w]);
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, (unsigned long long)c);
+}
+static int filter_alloc(oc_ctx *c, uint64_t nbits, oc_filter **out) {
+    oc_filter *f = new oc_filter();
+    f->ctx = c; f->nbits = nbits; f->words = (nbits + 63) / 64;
+    cudaError_t e = cudaMalloc(&f->bits, std::max<uint64_t>(f->words, 1) * 8);
+    if (e != cudaSuccess) { delete f; return fail(OC_ERR_OOM, "cudaMalloc(filter): %s", cudaGetErrorString(e)); }
+    *out = f;
+    return OC_OK;
+}
+extern "C" void oc_filter_destroy(oc_filter *f) {
+    if (!f) return;
+    std::lock_guard<std::mutex> g(f->ctx->mu);
+    cudaSetDevice(f->ctx->device);
+    cudaStreamSynchronize(f->ctx->stream);
+    cudaFree(f->bits);
+    delete f;
+}
+extern "C" int oc_filter_from_ids(oc_ctx *c, const uint64_t *doc_ids, uint64_t n, uint64_t nbits, oc_filter **out) {
+    if (!c || !out || (n && !doc_ids)) return fail(OC_ERR_INVALID, "bad arguments");
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    oc_filter *f = nullptr;
+    OCTRY(filter_alloc(c, nbits, &f));
+    CU(cudaMemsetAsync(f->bits, 0, std::max<uint64_t>(f->words, 1) * 8, c->stream));
+    if (n) {
+        OCTRY(c->in_blob.ensure(n * 8));
+        CU(cudaMemcpyAsync(c->in_blob.p, doc_ids, n * 8, cudaMemcpyHostToDevice, c->stream));
+        filter_scatter_ids_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->in_blob.as<uint64_t>(), n, nbits,
+                                                                                    reinterpret_cast<unsigned long long *>(f->bits));
+        launched(c);
+        CU(cudaGetLastError());
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    *out = f;
+    return OC_OK;
+}
+extern "C" int oc_filter_from_bits(oc_ctx *c, const uint64_t *bits, uint64_t nbits, oc_filter **out) {
+    if (!c || !out || (nbits && !bits)) return fail(OC_ERR_INVALID, "bad arguments");
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    oc_filter *f = nullptr;
+    OCTRY(filter_alloc(c, nbits, &f));
+    if (f->words) CU(cudaMemcpy(f->bits, bits, f->words * 8, cudaMemcpyHostToDevice));
+    *out = f;
+    return OC_OK;
+}
+static int filter_combine(const oc_filter *a, const oc_filter *b, int op, oc_filter **out) {
+    if (!a || !out || (op != 2 && !b)) return fail(OC_ERR_INVALID, "NULL argument");
+    if (b && (b->ctx != a->ctx || b->nbits != a->nbits)) return fail(OC_ERR_INVALID, "filters of different contexts / sizes");
+    oc_ctx *c = a->ctx;
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    oc_filter *f = nullptr;
+    OCTRY(filter_alloc(c, a->nbits, &f));
+    if (f->words) {
+        filter_combine_kernel<<<(unsigned)((f->words + 255) / 256), 256, 0, c->stream>>>(a->bits, b ? b->bits : nullptr, f->words, f->nbits, op, f->bits);
+        launched(c);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    *out = f;
+    return OC_OK;
+}
+extern "C" int oc_filter_and(const oc_filter *a, const oc_filter *b, oc_filter **out) { return filter_combine(a, b, 0, out); }
+extern "C" int oc_filter_or(const oc_filter *a, const oc_filter *b, oc_filter **out) { return filter_combine(a, b, 1, out); }
+extern "C" int oc_filter_not(const oc_filter *a, oc_filter **out) { return filter_combine(a, nullptr, 2, out); }
+extern "C" int oc_filter_count(const oc_filter *f, uint64_t *out) {
+    if (!f || !out) return fail(OC_ERR_INVALID, "NULL argument");
+    oc_ctx *c = f->ctx;
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    OCTRY(c->work_ctr.ensure(8));
+    CU(cudaMemsetAsync(c->work_ctr.p, 0, 8, c->stream));
+    if (f->words) {
+        filter_popcount_kernel<<<(unsigned)std::min<uint64_t>((f->words + 255) / 256, 1184), 256, 0, c->stream>>>(
+            f->bits, f->words, c->work_ctr.as<unsigned long long>());
+        launched(c);
+    }
+    unsigned long long v = 0;
+    CU(cudaMemcpyAsync(&v, c->work_ctr.p, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    *out = v;
+    return OC_OK;
+}
+extern "C" int oc_filter_read(const oc_filter *f, uint64_t *out_bits) {
+    if (!f || !out_bits) return fail(OC_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> g(f->ctx->mu);
+    CU(cudaSetDevice(f->ctx->device));
+    CU(cudaStreamSynchronize(f->ctx->stream));
+    if (f->words) CU(cudaMemcpy(out_bits, f->bits, f->words * 8, cudaMemcpyDeviceToHost));
+    return OC_OK;
+}
+
+// ------------------------------------------------------------------------------------ multi-index union (host)
+extern "C" int oc_merge_results(uint32_t n_indexes, uint32_t B, uint32_t limit, uint32_t offset, uint32_t in_stride,
+                                const uint64_t *const *doc_ids, const float *const *scores, const uint32_t *const *n,
+                                const uint64_t *const *counts, uint64_t *out_doc_ids, float *out_scores, uint32_t *out_n,
+                                uint64_t *out_count) {
+    if (!doc_ids || !scores || !n || !counts || !out_doc_ids || !out_scores || !out_n || !out_count) return fail(OC_ERR_INVALID, "NULL argument");
+    if (limit == 0) return fail(OC_ERR_INVALID, "limit must be >= 1");
+    std::vector<uint32_t> head(n_indexes);
+    for (uint32_t q = 0; q < B; q++) {
+        std::fill(head.begin(), head.end(), 0u);
+        uint64_t cnt = 0;
+        for (uint32_t i = 0; i < n_indexes; i++) {
+            if (n[i][q] > in_stride) return fail(OC_ERR_INVALID, "index %u query %u: n > in_stride", i, q);
+            cnt += counts[i][q];
+        }
+        uint32_t taken = 0, written = 0;
+        while (written < limit) {   // k-way merge of lists already sorted by (score desc, doc asc); NaN never reaches a list
+            int best = -1;
+            for (uint32_t i = 0; i < n_indexes; i++) {
+                if (head[i] >= n[i][q]) continue;
+                if (best < 0) { best = (int)i; continue; }
+                const float sa = scores[i][size_t(q) * in_stride + head[i]], sb = scores[best][size_t(q) * in_stride + head[best]];
+                const uint64_t da = doc_ids[i][size_t(q) * in_stride + head[i]], db = doc_ids[best][size_t(q) * in_stride + head[best]];
+                if (sa > sb || (sa == sb && da < db)) best = (int)i;
+            }
+            if (best < 0) break;
+            if (taken >= offset) {
+                out_doc_ids[size_t(q) * limit + written] = doc_ids[best][size_t(q) * in_stride + head[best]];
+                out_scores[size_t(q) * limit + written] = scores[best][size_t(q) * in_stride + head[best]];
+                written++;
+            }
+            taken++; head[best]++;
+        }
+        for (uint32_t k = written; k < limit; k++) { out_doc_ids[size_t(q) * limit + k] = 0; out_scores[size_t(q) * limit + k] = 0.f; }
+        out_n[q] = written;
+        out_count[q] = cnt;
+    }
+    return OC_OK;
+}
+
 // ------------------------------------------------------------------------------------ search()
 // bm25.rs:78-82, evaluated on the host with libm (the same log1pf the oracle uses)
 static inline float host_idf(float total_documents, uint64_t corpus_df) {
@@ -1212,8 +1371,17 @@ static int launch_tile(oc_ctx *c, const Bm25Params &bp, uint32_t grid, bool mult
 #include "shard.cuh"
 #include "batcher.h"
 
-extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_params *p, uint64_t *out_doc_ids,
-                         float *out_scores, uint32_t *out_n, uint64_t *out_count) {
+struct FacetJob {   // oc_search_facets: count, per query, the matched documents of each requested variant
+    oc_facets *fc;
+    const oc_facet_req *reqs;
+    uint32_t n_reqs;
+    uint64_t *out_counts;   // [B][n_reqs]
+};
+static int run_facets(oc_ctx *c, const FacetJob &fj, uint32_t B, bool has_ft, bool has_v, const StrSnap *S, uint32_t n_tiles,
+                      uint32_t vlimit);
+
+static int search_impl(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_params *p, uint64_t *out_doc_ids,
+                       float *out_scores, uint32_t *out_n, uint64_t *out_count, const FacetJob *fj) {
     if (!c || !p || !out_doc_ids || !out_scores || !out_n || !out_count) return fail(OC_ERR_INVALID, "NULL argument");
     const uint32_t B = p->n_queries;
     if (B == 0) return OC_OK;
@@ -1228,7 +1396,9 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
     const uint64_t n_keep64 = uint64_t(p->limit) + p->offset;
     if (n_keep64 > OC_MAX_TOPK) return fail(OC_ERR_UNSUPPORTED, "limit+offset %llu > %u", (unsigned long long)n_keep64, OC_MAX_TOPK);
     const uint32_t n_keep = (uint32_t)n_keep64;
-    const uint32_t vlimit = p->limit;  // limit_hint = limit, NOT limit+offset (search.rs:330-336)
+    // limit_hint = limit, NOT limit+offset (search.rs:330-336); vector_limit lets a multi-index caller keep that depth
+    const uint32_t vlimit = p->vector_limit ? p->vector_limit : p->limit;
+    if (vlimit > OC_MAX_TOPK) return fail(OC_ERR_UNSUPPORTED, "vector_limit %u > %u", vlimit, OC_MAX_TOPK);
     if (p->sharded && !c->comm.ready()) return fail(OC_ERR_COMM, "sharded search without oc_comm_init");
 
     // the published snapshot of the string store: grabbed once, immutable for the whole call (a commit may
@@ -1260,21 +1430,24 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
     };
     // ------------------------------------------------------------ vector stage first: the query vectors
     // (+ filter) go up alone and the matrix sweep starts; the host-side descriptor work below overlaps it
-    const bool filter = p->filter_bits != nullptr;
-    const size_t fwords = filter ? (p->filter_nbits + 63) / 64 : 0;
-    const uint64_t *filter_dev = nullptr;
+    if (p->filter && p->filter->ctx != c) return fail(OC_ERR_INVALID, "filter belongs to another ctx");
+    const bool filter_h = !p->filter && p->filter_bits != nullptr;        // host bitmap: uploaded with this call
+    const bool filter = filter_h || p->filter != nullptr;
+    const uint64_t filter_nbits = p->filter ? p->filter->nbits : p->filter_nbits;
+    const size_t fwords = filter_h ? (p->filter_nbits + 63) / 64 : 0;
+    const uint64_t *filter_dev = p->filter ? p->filter->bits : nullptr;
     size_t h2d_early = 0;
     if (has_v) {
         Packer pk0;
         const size_t o_qv = pk0.add(p->q_vecs, size_t(B) * emb->dim * 4, is_pinned_host(p->q_vecs));
-        const size_t o_flt = filter ? pk0.add(p->filter_bits, fwords * 8) : 0;
+        const size_t o_flt = filter_h ? pk0.add(p->filter_bits, fwords * 8) : 0;
         CU(cudaEventRecord(c->ev[EV_START], c->stream));
         OCTRY(upload(pk0, c->h_in0, c->in_blob0, c->stream));
         CU(cudaEventRecord(c->ev[EV_H2D], c->stream));
         h2d_early = pk0.total;
-        if (filter) filter_dev = reinterpret_cast<const uint64_t *>(c->in_blob0.as<uint8_t>() + o_flt);
+        if (filter_h) filter_dev = reinterpret_cast<const uint64_t *>(c->in_blob0.as<uint8_t>() + o_flt);
         OCTRY(run_vector_stage(c, emb, reinterpret_cast<const float *>(c->in_blob0.as<uint8_t>() + o_qv), B, vlimit, p->similarity,
-                               filter_dev, p->filter_nbits));
+                               filter_dev, filter_nbits));
     }
 
     // ------------------------------------------------------------ host: descriptors
@@ -1429,7 +1602,7 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
 
     // ------------------------------------------------------------ H2D: descriptors in one packed blob
     Packer pk;
-    const size_t o_flt = (filter && !has_v) ? pk.add(p->filter_bits, fwords * 8) : 0;
+    const size_t o_flt = (filter_h && !has_v) ? pk.add(p->filter_bits, fwords * 8) : 0;
     const size_t o_terms = has_ft ? pk.add(terms.data(), terms.size() * sizeof(TermDesc)) : 0;
     const size_t o_tokens = has_ft ? pk.add(tokens.data(), tokens.size() * sizeof(TokenDesc)) : 0;
     const size_t o_ttok = has_ft ? pk.add(term_token.data(), term_token.size() * 4) : 0;
@@ -1453,7 +1626,7 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
     if (!has_v) CU(cudaEventRecord(c->ev[EV_H2D], c->stream));   // hybrid/vector: this copy rides inside the device window
     c->timing.h2d_bytes = h2d_early + pk.total;
     uint8_t *din = c->in_blob.as<uint8_t>();
-    if (filter && !has_v) filter_dev = reinterpret_cast<const uint64_t *>(din + o_flt);
+    if (filter_h && !has_v) filter_dev = reinterpret_cast<const uint64_t *>(din + o_flt);
 
     // ------------------------------------------------------------ fulltext stage + fusion (re-runnable)
     // arg-max selection (n_keep <= 32) needs no power-of-two buffer; the bitonic fallback does
@@ -1489,7 +1662,7 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
         if (filter || tombs) {
             OCTRY(c->row_ok.ensure(ok_words * 4));
             rows_ok_kernel<<<(unsigned)((ok_words + 255) / 256), 256, 0, ps>>>(
-                S->row_doc, S->n_rows, tombs ? S->alive : nullptr, filter_dev, p->filter_nbits,
+                S->row_doc, S->n_rows, tombs ? S->alive : nullptr, filter_dev, filter_nbits,
                 c->row_ok.as<uint32_t>(), ok_words);
             launched(c);
             row_ok = c->row_ok.as<uint32_t>();
@@ -1561,6 +1734,10 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
         bp.tile_max = c->tile_max.as<float>(); bp.tile_min = c->tile_min.as<float>();
         bp.tile_first = 0;
         CU(cudaMemsetAsync(c->tau.p, 0, size_t(B) * 8, ps));
+        if (fj) {   // facets: the tile kernels also emit the bitmap of matched rows (every (query, tile) item writes its 256 words)
+            OCTRY(c->mbits.ensure(size_t(B) * std::max<uint32_t>(n_tiles, 1) * (BM25_TILE / 32) * 4));
+            bp.matched_bits = c->mbits.as<uint32_t>();
+        }
         if (n_tiles) OCTRY(launch_tile(c, bp, n_tiles * B, any_multi, thr, omc_tile, ps));
         CU(cudaEventRecord(c->ev[EV_BM1], ps));
         c->timing.bm25_postings = postings_walked;
@@ -1685,12 +1862,231 @@ extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_pa
             CU(cudaStreamSynchronize(c->stream));
         }
     }
+    if (fj) OCTRY(run_facets(c, *fj, B, has_ft, has_v, S, n_tiles, vlimit));
     c->timing.d2h_bytes = out_bytes;
     memcpy(out_doc_ids, h + o_doc, size_t(B) * p->limit * 8);
     memcpy(out_scores, h + o_sc, size_t(B) * p->limit * 4);
     memcpy(out_n, h + o_n, size_t(B) * 4);
     memcpy(out_count, h + o_cnt, size_t(B) * 8);
     return finish_timing(c, has_v && emb->n_rows > 0, has_ft, true, did_comm);
+}
+
+extern "C" int oc_search(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_params *p, uint64_t *out_doc_ids,
+                         float *out_scores, uint32_t *out_n, uint64_t *out_count) {
+    return search_impl(c, emb, str, p, out_doc_ids, out_scores, out_n, out_count, nullptr);
+}
+
+// ------------------------------------------------------------------------------------ facets
+// FacetContext::execute (read/index/facet.rs:147-209): for every requested variant of a filter field — bool
+// true/false (bool_field.rs:182-208), a number range [from, to] inclusive (number_field.rs:368-387), a
+// string_filter key (string_filter_field.rs:175-193) — count the documents of the variant that are keys of the
+// score map.  On the device the score map's key set is a bitmap over DocumentId: the matched rows of the BM25
+// tile kernels (+ the vector hits), and a variant is a slice of a device-resident document array.
+struct FacetField {
+    bool number = false;
+    uint64_t n_docs = 0;
+    uint64_t *docs = nullptr;              // device: variant-major (CSR) or value-sorted (number field)
+    std::vector<uint64_t> offsets;         // host: n_variants + 1
+    std::vector<double> values;            // host: ascending (number field)
+};
+struct oc_facets {
+    oc_ctx *ctx;
+    uint64_t nbits;                        // DocumentId space [0, nbits)
+    std::vector<FacetField> fields;
+};
+struct FacetReqDev { const uint64_t *docs; uint64_t n; };
+
+extern "C" int oc_facets_create(oc_ctx *c, uint64_t nbits, oc_facets **out) {
+    if (!c || !out || nbits == 0) return fail(OC_ERR_INVALID, "bad arguments");
+    oc_facets *f = new oc_facets();
+    f->ctx = c; f->nbits = nbits;
+    *out = f;
+    return OC_OK;
+}
+extern "C" void oc_facets_destroy(oc_facets *f) {
+    if (!f) return;
+    {
+        std::lock_guard<std::mutex> g(f->ctx->mu);
+        cudaSetDevice(f->ctx->device);
+        cudaStreamSynchronize(f->ctx->stream);
+        for (auto &fl : f->fields) cudaFree(fl.docs);
+    }
+    delete f;
+}
+static int facets_add(oc_facets *f, FacetField &&fl, const uint64_t *doc_ids, uint32_t *out_field) {
+    oc_ctx *c = f->ctx;
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    if (fl.n_docs) {
+        CU(cudaMalloc(&fl.docs, fl.n_docs * 8));
+        CU(cudaMemcpy(fl.docs, doc_ids, fl.n_docs * 8, cudaMemcpyHostToDevice));
+    }
+    f->fields.push_back(std::move(fl));
+    if (out_field) *out_field = (uint32_t)f->fields.size() - 1;
+    return OC_OK;
+}
+extern "C" int oc_facets_add_field(oc_facets *f, uint32_t n_variants, const uint64_t *variant_offsets, const uint64_t *doc_ids,
+                                   uint32_t *out_field) {
+    if (!f || !variant_offsets || n_variants == 0) return fail(OC_ERR_INVALID, "bad arguments");
+    for (uint32_t v = 0; v < n_variants; v++)
+        if (variant_offsets[v + 1] < variant_offsets[v]) return fail(OC_ERR_INVALID, "variant_offsets not monotone");
+    if (variant_offsets[n_variants] && !doc_ids) return fail(OC_ERR_INVALID, "doc_ids is NULL");
+    FacetField fl;
+    fl.n_docs = variant_offsets[n_variants];
+    fl.offsets.assign(variant_offsets, variant_offsets + n_variants + 1);
+    return facets_add(f, std::move(fl), doc_ids, out_field);
+}
+extern "C" int oc_facets_add_number_field(oc_facets *f, uint64_t n, const double *values_sorted, const uint64_t *doc_ids,
+                                          uint32_t *out_field) {
+    if (!f || (n && (!values_sorted || !doc_ids))) return fail(OC_ERR_INVALID, "bad arguments");
+    for (uint64_t i = 1; i < n; i++)
+        if (!(values_sorted[i] >= values_sorted[i - 1])) return fail(OC_ERR_INVALID, "values must be ascending (no NaN)");
+    FacetField fl;
+    fl.number = true; fl.n_docs = n;
+    fl.values.assign(values_sorted, values_sorted + n);
+    return facets_add(f, std::move(fl), doc_ids, out_field);
+}
+
+// row bitmap -> DocumentId bitmap when rows are not document ids
+__global__ void facet_rows_to_docs_kernel(const uint32_t *row_bits, uint64_t row_stride_words, const uint64_t *row_doc, uint64_t n_rows,
+                                          uint32_t *doc_bits, uint64_t doc_stride_words, uint64_t nbits) {
+    const uint32_t q = blockIdx.y;
+    const uint64_t w = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (w * 32 >= n_rows) return;
+    uint32_t v = row_bits[size_t(q) * row_stride_words + w];
+    while (v) {
+        const uint32_t b = __ffs(v) - 1;
+        v &= v - 1;
+        const uint64_t r = w * 32 + b;
+        if (r < n_rows) { const uint64_t d = row_doc[r]; if (d < nbits) atomicOr(&doc_bits[size_t(q) * doc_stride_words + (d >> 5)], 1u << (d & 31)); }
+    }
+}
+// the vector hits are keys of the score map too (token_score.rs:340-351, 416-419)
+__global__ void facet_mark_hits_kernel(const uint64_t *v_doc, const uint32_t *v_cnt, uint32_t v_stride, uint32_t B, uint32_t *doc_bits,
+                                       uint64_t doc_stride_words, uint64_t nbits_cap) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * v_stride) return;
+    const uint32_t q = i / v_stride, j = i % v_stride;
+    if (j >= v_cnt[q]) return;
+    const uint64_t d = v_doc[i];
+    if (d < nbits_cap) atomicOr(&doc_bits[size_t(q) * doc_stride_words + (d >> 5)], 1u << (d & 31));
+}
+// one block = 1024 documents of one variant, counted against every query's bitmap (the slice is read once)
+__global__ void __launch_bounds__(256) facet_count_kernel(const FacetReqDev *reqs, uint32_t n_reqs, const uint32_t *bits,
+                                                          uint64_t stride_words, uint64_t nbits_cap, uint32_t B,
+                                                          unsigned long long *out) {
+    const uint32_t r = blockIdx.y;
+    const FacetReqDev rq = reqs[r];
+    const uint64_t base = uint64_t(blockIdx.x) * 1024;
+    if (base >= rq.n) return;
+    uint64_t d[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        const uint64_t i = base + threadIdx.x + u * 256;
+        const uint64_t v = i < rq.n ? rq.docs[i] : ~0ull;
+        d[u] = v < nbits_cap ? v : ~0ull;
+    }
+    __shared__ uint32_t s_c[8];
+    for (uint32_t q = 0; q < B; q++) {
+        const uint32_t *bq = bits + size_t(q) * stride_words;
+        uint32_t c = 0;
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (d[u] != ~0ull) c += (bq[d[u] >> 5] >> (d[u] & 31)) & 1u;
+        c = __reduce_add_sync(0xffffffffu, c);
+        if ((threadIdx.x & 31) == 0) s_c[threadIdx.x >> 5] = c;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t t = 0;
+            for (int w = 0; w < 8; w++) t += s_c[w];
+            if (t) atomicAdd(out + size_t(q) * n_reqs + r, (unsigned long long)t);
+        }
+        __syncthreads();
+    }
+}
+
+static int run_facets(oc_ctx *c, const FacetJob &fj, uint32_t B, bool has_ft, bool has_v, const StrSnap *S, uint32_t n_tiles,
+                      uint32_t vlimit) {
+    oc_facets *fc = fj.fc;
+    // resolve the requests to device slices
+    std::vector<FacetReqDev> rd(fj.n_reqs);
+    uint64_t max_n = 0;
+    for (uint32_t i = 0; i < fj.n_reqs; i++) {
+        const oc_facet_req &rq = fj.reqs[i];
+        if (rq.field >= fc->fields.size()) return fail(OC_ERR_INVALID, "facet request %u: unknown field %u", i, rq.field);
+        const FacetField &fl = fc->fields[rq.field];
+        uint64_t lo, hi;
+        if (fl.number) {   // NumberFilter::Between = inclusive on both ends (number_field.rs:376, 604-631)
+            lo = uint64_t(std::lower_bound(fl.values.begin(), fl.values.end(), rq.from) - fl.values.begin());
+            hi = uint64_t(std::upper_bound(fl.values.begin(), fl.values.end(), rq.to) - fl.values.begin());
+            if (hi < lo) hi = lo;
+        } else {
+            if (rq.variant + 1 >= fl.offsets.size()) return fail(OC_ERR_INVALID, "facet request %u: unknown variant %u", i, rq.variant);
+            lo = fl.offsets[rq.variant]; hi = fl.offsets[rq.variant + 1];
+        }
+        rd[i].docs = fl.docs + lo; rd[i].n = hi - lo;
+        max_n = std::max(max_n, rd[i].n);
+    }
+    // the key set of each query's score map as a DocumentId bitmap
+    const uint64_t row_words = uint64_t(n_tiles) * (BM25_TILE / 32);
+    const uint64_t doc_words = (fc->nbits + 31) / 32;
+    const bool identity = has_ft && S->row_doc == nullptr;
+    const uint32_t *bits; uint64_t stride, cap_bits;
+    if (identity && !has_v) {   // the row bitmap is the document bitmap
+        bits = c->mbits.as<uint32_t>(); stride = row_words; cap_bits = S->n_rows;
+    } else {
+        OCTRY(c->dbits.ensure(size_t(B) * doc_words * 4));
+        CU(cudaMemsetAsync(c->dbits.p, 0, size_t(B) * doc_words * 4, c->stream));
+        if (has_ft && n_tiles) {
+            if (identity) {
+                const uint64_t wcopy = std::min(row_words, doc_words);
+                CU(cudaMemcpy2DAsync(c->dbits.p, doc_words * 4, c->mbits.p, row_words * 4, wcopy * 4, B, cudaMemcpyDeviceToDevice, c->stream));
+            } else {
+                dim3 grid((unsigned)((row_words + 255) / 256), B);
+                facet_rows_to_docs_kernel<<<grid, 256, 0, c->stream>>>(c->mbits.as<uint32_t>(), row_words, S->row_doc, S->n_rows,
+                                                                      c->dbits.as<uint32_t>(), doc_words, fc->nbits);
+                launched(c);
+            }
+        }
+        if (has_v) {
+            facet_mark_hits_kernel<<<(B * vlimit + 255) / 256, 256, 0, c->stream>>>(c->v_doc.as<uint64_t>(), c->v_cnt.as<uint32_t>(), vlimit, B,
+                                                                                  c->dbits.as<uint32_t>(), doc_words, fc->nbits);
+            launched(c);
+        }
+        bits = c->dbits.as<uint32_t>(); stride = doc_words; cap_bits = fc->nbits;
+    }
+    OCTRY(c->facet_req.ensure(size_t(fj.n_reqs) * sizeof(FacetReqDev)));
+    OCTRY(c->facet_out.ensure(size_t(B) * fj.n_reqs * 8));
+    CU(cudaMemcpyAsync(c->facet_req.p, rd.data(), size_t(fj.n_reqs) * sizeof(FacetReqDev), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemsetAsync(c->facet_out.p, 0, size_t(B) * fj.n_reqs * 8, c->stream));
+    if (max_n) {
+        dim3 grid((unsigned)((max_n + 1023) / 1024), fj.n_reqs);
+        facet_count_kernel<<<grid, 256, 0, c->stream>>>(c->facet_req.as<FacetReqDev>(), fj.n_reqs, bits, stride, cap_bits, B,
+                                                       c->facet_out.as<unsigned long long>());
+        launched(c);
+        CU(cudaGetLastError());
+    }
+    CU(cudaMemcpyAsync(fj.out_counts, c->facet_out.p, size_t(B) * fj.n_reqs * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));   // rd lives on this stack
+    return OC_OK;
+}
+
+extern "C" int oc_search_facets(oc_ctx *c, oc_emb *emb, oc_str *str, oc_facets *facets, const oc_search_params *p,
+                                const oc_facet_req *reqs, uint32_t n_reqs, uint64_t *out_counts) {
+    if (!c || !p || !facets || !out_counts || (n_reqs && !reqs)) return fail(OC_ERR_INVALID, "NULL argument");
+    if (facets->ctx != c) return fail(OC_ERR_INVALID, "facets belong to another ctx");
+    if (p->sharded) return fail(OC_ERR_UNSUPPORTED, "facets over a sharded search: count per shard and add the counts");
+    if (n_reqs == 0) return OC_OK;
+    // the reference computes facets on the score map re-scored WITHOUT the where-filter (search.rs:361-396: only the
+    // uncommitted deletes stay excluded), so that the counts do not collapse onto the selected category
+    oc_search_params q = *p;
+    q.filter_bits = nullptr; q.filter_nbits = 0; q.filter = nullptr;
+    const uint32_t B = p->n_queries;
+    std::vector<uint64_t> docs(size_t(B) * p->limit), cnt(B);
+    std::vector<float> scores(size_t(B) * p->limit);
+    std::vector<uint32_t> n(B);
+    FacetJob fj{facets, reqs, n_reqs, out_counts};
+    return search_impl(c, emb, str, &q, docs.data(), scores.data(), n.data(), cnt.data(), &fj);
 }
 
 // ------------------------------------------------------------------------------------ micro-batching front

@@ -245,6 +245,173 @@ class StringFieldStorage:
         check(lib().oc_str_set_global(self._h, int(document_count), _p(a)))
 
 
+class DeviceFilter:
+    """A FilterResult<DocumentId> evaluated to a bitmap that lives on the device (oc_filter_*): built once from
+    the And / Or / Not tree of filters.py (filter.rs:344-392), reused by any number of searches."""
+
+    def __init__(self, ctx: Context, handle, nbits: int):
+        self.ctx, self._h, self.nbits = ctx, handle, int(nbits)
+
+    @classmethod
+    def from_ids(cls, ctx: Context, doc_ids, nbits: int) -> "DeviceFilter":
+        ids = np.ascontiguousarray(np.asarray(list(doc_ids) if not isinstance(doc_ids, np.ndarray) else doc_ids, np.uint64))
+        h = C.c_void_p()
+        check(lib().oc_filter_from_ids(ctx._h, _p(ids), ids.shape[0], int(nbits), C.byref(h)))
+        return cls(ctx, h, nbits)
+
+    @classmethod
+    def from_bits(cls, ctx: Context, bits: np.ndarray, nbits: int) -> "DeviceFilter":
+        b = np.ascontiguousarray(bits, np.uint64)
+        h = C.c_void_p()
+        check(lib().oc_filter_from_bits(ctx._h, _p(b), int(nbits), C.byref(h)))
+        return cls(ctx, h, nbits)
+
+    @classmethod
+    def from_expr(cls, ctx: Context, expr, nbits: int) -> "DeviceFilter":
+        """filters.Ids / And / Or / Not tree -> device bitmap (leaves uploaded as id lists, combined on the device)."""
+        from . import filters as F
+        if isinstance(expr, F.Ids):
+            return cls.from_ids(ctx, expr.doc_ids, nbits)
+        if isinstance(expr, F.Not):
+            a = cls.from_expr(ctx, expr.a, nbits)
+            try:
+                return ~a
+            finally:
+                a.close()
+        if isinstance(expr, (F.And, F.Or)):
+            a, b = cls.from_expr(ctx, expr.a, nbits), cls.from_expr(ctx, expr.b, nbits)
+            try:
+                return (a & b) if isinstance(expr, F.And) else (a | b)
+            finally:
+                a.close(); b.close()
+        raise TypeError(f"not a filter expression: {expr!r}")
+
+    def _bin(self, fn, other):
+        h = C.c_void_p()
+        check(fn(self._h, other._h, C.byref(h)))
+        return DeviceFilter(self.ctx, h, self.nbits)
+
+    def __and__(self, o): return self._bin(lib().oc_filter_and, o)
+    def __or__(self, o): return self._bin(lib().oc_filter_or, o)
+
+    def __invert__(self):
+        h = C.c_void_p()
+        check(lib().oc_filter_not(self._h, C.byref(h)))
+        return DeviceFilter(self.ctx, h, self.nbits)
+
+    def count(self) -> int:
+        out = C.c_uint64()
+        check(lib().oc_filter_count(self._h, C.byref(out)))
+        return int(out.value)
+
+    def read(self) -> np.ndarray:
+        bits = np.zeros((self.nbits + 63) // 64, np.uint64)
+        check(lib().oc_filter_read(self._h, _p(bits)))
+        return bits
+
+    def close(self):
+        if self._h:
+            lib().oc_filter_destroy(self._h)
+            self._h = None
+
+
+class FacetStore:
+    """The filter fields of one Index laid out for facet counting on the device (oc_facets_*): per field the
+    variants' document lists — bool true/false (bool_field.rs:182-208), string_filter keys
+    (string_filter_field.rs:175-193), number fields sorted by value so a range is a slice (number_field.rs:368-387)."""
+
+    def __init__(self, ctx: Context, nbits: int):
+        self.ctx, self.nbits = ctx, int(nbits)
+        self._h = C.c_void_p()
+        check(lib().oc_facets_create(ctx._h, self.nbits, C.byref(self._h)))
+        self.fields: Dict[str, dict] = {}
+
+    def add_bool_field(self, name: str, true_docs, false_docs):
+        return self._add_variants(name, "bool", {"true": true_docs, "false": false_docs})
+
+    def add_string_field(self, name: str, docs_by_key: Dict[str, Sequence[int]]):
+        return self._add_variants(name, "string", docs_by_key)
+
+    def _add_variants(self, name, kind, docs_by_key):
+        keys = list(docs_by_key)
+        lists = [np.sort(np.asarray(list(docs_by_key[k]), np.uint64)) for k in keys]
+        offs = np.zeros(len(keys) + 1, np.uint64)
+        offs[1:] = np.cumsum([l.shape[0] for l in lists])
+        docs = np.ascontiguousarray(np.concatenate(lists) if lists else np.zeros(0, np.uint64))
+        fid = C.c_uint32()
+        check(lib().oc_facets_add_field(self._h, len(keys), _p(offs), _p(docs), C.byref(fid)))
+        self.fields[name] = {"id": fid.value, "kind": kind, "keys": keys}
+        return fid.value
+
+    def add_number_field(self, name: str, doc_ids, values):
+        v = np.asarray(values, np.float64)
+        d = np.asarray(doc_ids, np.uint64)
+        o = np.argsort(v, kind="stable")
+        v, d = np.ascontiguousarray(v[o]), np.ascontiguousarray(d[o])
+        fid = C.c_uint32()
+        check(lib().oc_facets_add_number_field(self._h, v.shape[0], _p(v), _p(d), C.byref(fid)))
+        self.fields[name] = {"id": fid.value, "kind": "number"}
+        return fid.value
+
+    def close(self):
+        if self._h:
+            lib().oc_facets_destroy(self._h)
+            self._h = None
+
+
+def _number_label(x) -> str:
+    return str(int(x)) if float(x) == int(x) else repr(float(x))
+
+
+def search_facets(tsc: "TokenScoreContext", store: FacetStore, params: "TokenScoreParams", facets: Dict[str, dict], texts=None,
+                  q_vecs: Optional[np.ndarray] = None) -> List[Dict[str, dict]]:
+    """`facets` as in the reference's SearchParams: {"field": {"true": bool, "false": bool}} for a bool field,
+    {"field": {"ranges": [{"from": a, "to": b}, ...]}} for a number field, {"field": {}} for a string_filter field.
+    Returns, per query, {field: {"count": n_values, "values": {label: count}}} (FacetResult, types.rs:1508-1511;
+    number labels "from-to", number_field.rs:382).  The where-filter of `params` is ignored, as in search.rs:361-396."""
+    reqs, labels = [], []
+    for name, d in facets.items():
+        f = store.fields[name]
+        if f["kind"] == "number":
+            for r in d["ranges"]:
+                reqs.append((f["id"], 0, float(r["from"]), float(r["to"])))
+                labels.append((name, f"{_number_label(r['from'])}-{_number_label(r['to'])}"))
+        else:
+            for vi, key in enumerate(f["keys"]):
+                if f["kind"] == "bool" and not d.get(key, False):
+                    continue
+                reqs.append((f["id"], vi, 0.0, 0.0))
+                labels.append((name, key))
+    sp, keep, B = tsc._build_params(params, texts, q_vecs)
+    arr = (_lib.FacetReq * len(reqs))(*[_lib.FacetReq(*r) for r in reqs])
+    out = np.zeros((B, max(len(reqs), 1)), np.uint64)
+    check(lib().oc_search_facets(tsc.ctx._h, tsc.emb._h if tsc.emb else None, tsc.str._h if tsc.str else None, store._h,
+                                 C.byref(sp), arr, len(reqs), _p(out)))
+    res = []
+    for q in range(B):
+        r: Dict[str, dict] = {}
+        for j, (name, label) in enumerate(labels):
+            r.setdefault(name, {"count": 0, "values": {}})["values"][label] = int(out[q, j])
+        for v in r.values():
+            v["count"] = len(v["values"])
+        res.append(r)
+    return res
+
+
+def merge_index_results(per_index, limit: int, offset: int = 0) -> List[SearchHits]:
+    """search_on_indexes' union of the per-index score maps + top_n + skip/take (search.rs:304-338, 482-498):
+    per_index = one (doc_ids [B, limit+offset], scores, n, count) tuple per index, each obtained with
+    limit' = limit+offset, offset' = 0, vector_limit = limit."""
+    k = len(per_index)
+    B, stride = per_index[0][0].shape
+    keep = [[np.ascontiguousarray(a) for a in r] for r in per_index]
+    arr = lambda j: (C.c_void_p * k)(*[r[j].ctypes.data for r in keep])
+    od, os_ = np.zeros((B, limit), np.uint64), np.zeros((B, limit), np.float32)
+    on, oc = np.zeros(B, np.uint32), np.zeros(B, np.uint64)
+    check(lib().oc_merge_results(k, B, limit, offset, stride, arr(0), arr(1), arr(2), arr(3), _p(od), _p(os_), _p(on), _p(oc)))
+    return [SearchHits(od[i, :on[i]].copy(), os_[i, :on[i]].copy(), int(oc[i])) for i in range(B)]
+
+
 class TermDictionary:
     """Native term dictionaries of the string fields of one Index + batch query resolution (oc_dict_*,
     csrc/dict.h): tokenize (+ stem hook), then per field exact / prefix / Levenshtein expansion — what
@@ -368,6 +535,8 @@ class TokenScoreParams:
     threshold: Optional[float] = None
     filtered_doc_ids: Optional[np.ndarray] = None
     filter_nbits: int = 0
+    device_filter: Optional["DeviceFilter"] = None   # device-resident bitmap (oc_filter_*); wins over filtered_doc_ids
+    vector_limit: int = 0            # 0 => limit_hint (search.rs:330-336); see oc_search_params.vector_limit
     omc_doc_ids: Optional[np.ndarray] = None   # ascending
     omc_mult: Optional[np.ndarray] = None
     sharded: bool = False
@@ -425,7 +594,11 @@ class TokenScoreContext:
             keep.append(texts)
             sp.q_token_offsets, sp.token_term_offsets = _p(texts.q_token_offsets), _p(texts.token_term_offsets)
             sp.term_field, sp.term_id, sp.term_weight = _p(texts.term_field), _p(texts.term_id), _p(texts.term_weight)
-        if params.filtered_doc_ids is not None:
+        sp.vector_limit = int(params.vector_limit)
+        if params.device_filter is not None:
+            keep.append(params.device_filter)
+            sp.filter = params.device_filter._h
+        elif params.filtered_doc_ids is not None:
             fb = np.ascontiguousarray(params.filtered_doc_ids, np.uint64)
             keep.append(fb)
             sp.filter_bits, sp.filter_nbits = _p(fb), int(params.filter_nbits)
