@@ -47,7 +47,9 @@ struct TermDesc {      // one expanded index term of one token of one query
     float weight;          // field boost x exact-match factor
     float avg_len;         // the field's avg_field_length
     uint32_t flags;        // bit0: postings are batch-precomputed (row, c) records, see bm25_precompute_kernel
+                           // bit1: DENSE: ptr is a float[n_tiles * TILE] array of per-row contributions (0 = absent)
 };
+constexpr uint32_t TD_PRE = 1u, TD_DENSE = 2u;
 
 struct TokenDesc {
     uint32_t term_begin, term_end;  // into TermDesc[]
@@ -106,7 +108,8 @@ __device__ __forceinline__ float bm25_sat(float S, float k, float kp1, float idf
 }
 struct PreDesc {        // one (term, weight) pair shared by several queries of the batch
     const Posting *src;
-    Posting *dst;
+    Posting *dst;       // list form: (row, c) records; or
+    float *dense;       // dense form (hot terms): c scattered into a zeroed float[rows] array, NULL = list form
     uint32_t len;
     float weight, idf;
     uint32_t pad;
@@ -161,10 +164,17 @@ __host__ __device__ inline size_t bm25_smem_bytes(bool multi, bool threshold, bo
 
 // Zipf query terms repeat across the queries of a batch: the per-posting contribution
 // c = idf*(k+1)*S/(k+S), S = w*tf' of a single-term token depends only on (term, weight), so it is
-// computed ONCE per batch into (row, c) records (same rounded ops => bit-identical scores); the
-// tile kernel then only adds.  items[i] = (pre index, chunk of PRE_CHUNK postings).
+// computed ONCE per batch (same rounded ops => bit-identical scores) and the tile kernel only adds:
+//   * list form: (row, c) records in posting order;
+//   * DENSE form, for hot terms (a posting in at least every ~16th row): c scattered into a zeroed
+//     float[rows] array.  A (query, tile) item then adds the tile's 8192 floats with 128-bit loads —
+//     ~0.6 instructions per row instead of ~25 per posting of the scatter loop — and adding the 0.0 of an
+//     absent row leaves every bit of the sum unchanged.  Rows failing the filter / tombstone bitmap are
+//     left at 0 here, so the tile kernel needs no per-row check for a dense term.
+// items[i] = (pre index, chunk of PRE_CHUNK postings).
 constexpr uint32_t PRE_CHUNK = 4096;
-__global__ void __launch_bounds__(256) bm25_precompute_kernel(const PreDesc *pre, const uint2 *items, float k) {
+__global__ void __launch_bounds__(256) bm25_precompute_kernel(const PreDesc *pre, const uint2 *items, float k,
+                                                              const uint32_t *row_ok_bits) {
     const uint2 it = items[blockIdx.x];
     const PreDesc d = pre[it.x];
     const float kp1 = __fadd_rn(k, 1.0f);
@@ -176,7 +186,12 @@ __global__ void __launch_bounds__(256) bm25_precompute_kernel(const PreDesc *pre
         const float ntf = __fmul_rn(d.weight, __uint_as_float(r.y));
         float c = __int_as_float(0x7fc00000);                  // NaN => skipped (bm25.rs:387,391)
         if (f32_is_normal(ntf)) c = bm25_sat(ntf, k, kp1, d.idf);
-        dst[i] = make_uint2(r.x, __float_as_uint(c));
+        if (d.dense) {
+            const bool ok = !row_ok_bits || ((row_ok_bits[r.x >> 5] >> (r.x & 31)) & 1u);
+            if (ok && c == c) d.dense[r.x] = c;
+        } else {
+            dst[i] = make_uint2(r.x, __float_as_uint(c));
+        }
     }
 }
 
@@ -640,7 +655,11 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_tile2_kernel(const Bm25P
                 const uint32_t lo = sg[tile], hi = sg[tile + 1];
                 t_ptr[tid] = reinterpret_cast<const uint2 *>(td.ptr) + lo;
                 n = hi - lo;
-                t_w[tid] = td.weight; t_pre[tid] = td.flags & 1u;
+                t_w[tid] = td.weight; t_pre[tid] = td.flags;
+                if (td.flags & TD_DENSE) {   // per-row contributions of the whole corpus: this tile's 8192 floats
+                    t_ptr[tid] = reinterpret_cast<const uint2 *>(reinterpret_cast<const float *>(td.ptr) + row0);
+                    n = td.len ? BM25_TILE : 0;
+                }
             }
             t_n[tid] = n; t_idf[tid] = tk.idf; t_bit[tid] = tk.bit;
         }
@@ -650,14 +669,45 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_tile2_kernel(const Bm25P
 
         // ---------------------------------------- accumulate, token by token (the reference's summation order)
         uint32_t total = 0;
+        bool prev_dense = false;
         for (uint32_t j = 0; j < ntok; j++) {
             const uint32_t n = t_n[j];
             if (n == 0) continue;                          // block-uniform
             total += n;
             const uint2 *pp = t_ptr[j];
-            const bool pre = t_pre[j] != 0;
+            const bool pre = (t_pre[j] & TD_PRE) != 0;
             const float w = t_w[j], idf = t_idf[j];
             const uint32_t bit = t_bit[j];
+            if (t_pre[j] & TD_DENSE) {
+                // hot term: add the tile's slice of its dense contribution array (0.0 where the row has no posting,
+                // is filtered out or its contribution was skipped: x + 0.0 == x bit for bit).  Thread t owns the
+                // float4 slots t, t+256, ... here AND in the finishing scan, so no barrier is needed between
+                // consecutive dense tokens or between the last one and the scan.
+                const float4 *dp = reinterpret_cast<const float4 *>(pp);
+#pragma unroll
+                for (uint32_t h = 0; h < 2; h++) {
+                    float4 c4[4];
+#pragma unroll
+                    for (uint32_t u = 0; u < 4; u++) c4[u] = __ldg(dp + tid + (h * 4 + u) * BM25_THREADS);
+#pragma unroll
+                    for (uint32_t u = 0; u < 4; u++) {
+                        const uint32_t i = tid + (h * 4 + u) * BM25_THREADS;
+                        float4 s4 = reinterpret_cast<float4 *>(score)[i];
+                        s4.x = __fadd_rn(s4.x, c4[u].x); s4.y = __fadd_rn(s4.y, c4[u].y);
+                        s4.z = __fadd_rn(s4.z, c4[u].z); s4.w = __fadd_rn(s4.w, c4[u].w);
+                        reinterpret_cast<float4 *>(score)[i] = s4;
+                        if (THRESH) {
+                            uint4 m4 = reinterpret_cast<uint4 *>(mask)[i];
+                            m4.x |= c4[u].x != 0.f ? bit : 0u; m4.y |= c4[u].y != 0.f ? bit : 0u;
+                            m4.z |= c4[u].z != 0.f ? bit : 0u; m4.w |= c4[u].w != 0.f ? bit : 0u;
+                            reinterpret_cast<uint4 *>(mask)[i] = m4;
+                        }
+                    }
+                }
+                prev_dense = true;
+                continue;
+            }
+            if (prev_dense) { __syncthreads(); prev_dense = false; }   // a list token scatters across the owners' slots
             auto apply = [&](const uint2 rec) {
                 const uint32_t l = rec.x - row0;
                 if (use_ok && !((okb[l >> 5] >> (l & 31)) & 1u)) return;
@@ -704,11 +754,7 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_tile2_kernel(const Bm25P
         uint32_t matched = 0;
         float lmax = 0.f, lmin = 0.f;
         const uint64_t rows_here = min(uint64_t(BM25_TILE), p.n_rows - row0);
-        auto visit = [&](float s, uint32_t l) -> bool {   // one matched row; returns true when it pushed a candidate
-            matched++;
-            if (want_bits) atomicOr(&s_mbits[l >> 5], 1u << (l & 31));
-            lmax = fmaxf(lmax, s);
-            lmin = fminf(lmin, s);
+        auto consider = [&](float s, uint32_t l) -> bool {   // candidate test of one matched row; true when it pushed
             float proxy = __fsub_rn(s, mh);
             if (OMC) proxy = __fmul_rn(proxy, aux[l]);
             if (!(proxy >= tau_f)) return false;                            // NaN fails; ties re-checked on the key
@@ -717,6 +763,13 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_tile2_kernel(const Bm25P
             const uint32_t slot = atomicAdd(&s_cnt, 1u);
             if (slot < p.cap) tbuf[slot] = key; else s_ovf = 1u;
             return true;
+        };
+        auto visit = [&](float s, uint32_t l) -> bool {   // one matched row
+            matched++;
+            if (want_bits) atomicOr(&s_mbits[l >> 5], 1u << (l & 31));
+            lmax = fmaxf(lmax, s);
+            lmin = fminf(lmin, s);
+            return consider(s, l);
         };
         // the sparse finish re-derives a candidate's raw score from its key (proxy == score): only without OMC / min hint
         const bool sparse = total != 0 && total <= BM25_SPARSE_MAX && p.cap >= BM25_SPARSE_MAX && !OMC && mh == 0.f;
@@ -762,9 +815,23 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_tile2_kernel(const Bm25P
                         for (int u = 0; u < 4; u++)
                             sv[u] = (mv[u] != 0u && uint32_t(__popc(mv[u])) >= qd.required) ? sv[u] : 0.f;
                     }
+                    if (!OMC && !want_bits) {
+                        // common case: branch-free bookkeeping of the 4 slots, one candidate test on their maximum
+                        // (absent rows hold 0.0: no-ops for the folds, which start at 0.0, token_score.rs:398-401)
+                        matched += (sv[0] != 0.f ? 1u : 0u) + (sv[1] != 0.f ? 1u : 0u) + (sv[2] != 0.f ? 1u : 0u) + (sv[3] != 0.f ? 1u : 0u);
+                        const float m4 = fmaxf(fmaxf(sv[0], sv[1]), fmaxf(sv[2], sv[3]));
+                        lmax = fmaxf(lmax, m4);
+                        lmin = fminf(lmin, fminf(fminf(sv[0], sv[1]), fminf(sv[2], sv[3])));
+                        if (__fsub_rn(m4, mh) >= tau_f) {
 #pragma unroll
-                    for (int u = 0; u < 4; u++)
-                        if (sv[u] != 0.f) pushed |= visit(sv[u], l0 + u);
+                            for (int u = 0; u < 4; u++)
+                                if (sv[u] != 0.f) pushed |= consider(sv[u], l0 + u);
+                        }
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < 4; u++)
+                            if (sv[u] != 0.f) pushed |= visit(sv[u], l0 + u);
+                    }
                     if (!chunked) continue;
                     if (!__syncthreads_or(pushed)) continue;
                     const uint32_t c = s_cnt;
@@ -876,7 +943,10 @@ __global__ void __launch_bounds__(256) bm25_point_kernel(const PointParams p) {
                 if (nt == 1) {
                     const TermDesc td = p.terms[tk.term_begin];
                     uint32_t pay;
-                    if (posting_find(td, r, &pay)) {
+                    if (td.flags & TD_DENSE) {
+                        const float cd = reinterpret_cast<const float *>(td.ptr)[r];
+                        if (cd != 0.f) c = cd;
+                    } else if (posting_find(td, r, &pay)) {
                         if (td.flags & 1u) c = __uint_as_float(pay);
                         else {
                             const float ntf = __fmul_rn(td.weight, __uint_as_float(pay));

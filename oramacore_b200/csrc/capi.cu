@@ -147,7 +147,7 @@ struct oc_ctx {
     DevBuf seg, df_dev, row_ok, tau, cand_key, cand_ft, cand_cnt, tile_cnt, tile_max, tile_min, min_hint;
     DevBuf out_blob, shard_send, shard_recv, work_ctr, mbits, dbits, facet_req, facet_out;
     bool gemm_pending = false; const float *gemm_inv_norm = nullptr;
-    DevBuf q_bf16, q_rho, pre_post, g_thr, g_eps, g_ovf, g_ovfcnt, g_resc, g_cand, g_cnt, g_flag, g_max, r_qpad, r_qinv, r_map, r_doc, r_score, r_row, r_cnt, r_raw;
+    DevBuf q_bf16, q_rho, pre_post, dense_buf, g_thr, g_eps, g_ovf, g_ovfcnt, g_resc, g_cand, g_cnt, g_flag, g_max, r_qpad, r_qinv, r_map, r_doc, r_score, r_row, r_cnt, r_raw;
 
     HostBuf h_in, h_out, h_in0;   // h_in0 / in_blob0: query vectors + filter, uploaded before the descriptors
     OcComm comm;
@@ -190,7 +190,7 @@ extern "C" void oc_shutdown(oc_ctx *c) {
     DevBuf *bufs[] = {&c->in_blob, &c->q_pad, &c->q_inv, &c->eff_norm, &c->filter_dev, &c->scan_cand, &c->v_doc,
                       &c->v_score, &c->v_row, &c->v_cnt, &c->v_srow, &c->v_ft, &c->v_present, &c->v_raw, &c->seg, &c->df_dev,
                       &c->row_ok, &c->tau, &c->cand_key, &c->cand_ft, &c->cand_cnt, &c->tile_cnt, &c->tile_max,
-                      &c->tile_min, &c->min_hint, &c->out_blob, &c->shard_send, &c->shard_recv, &c->work_ctr, &c->mbits, &c->dbits, &c->facet_req, &c->facet_out, &c->q_bf16, &c->q_rho, &c->pre_post, &c->g_thr, &c->g_eps, &c->g_ovf, &c->g_ovfcnt, &c->g_resc, &c->g_cand, &c->g_cnt, &c->g_max,
+                      &c->tile_min, &c->min_hint, &c->out_blob, &c->shard_send, &c->shard_recv, &c->work_ctr, &c->mbits, &c->dbits, &c->facet_req, &c->facet_out, &c->q_bf16, &c->q_rho, &c->pre_post, &c->dense_buf, &c->g_thr, &c->g_eps, &c->g_ovf, &c->g_ovfcnt, &c->g_resc, &c->g_cand, &c->g_cnt, &c->g_max,
                       &c->g_flag, &c->r_qpad, &c->r_qinv, &c->r_map, &c->r_doc, &c->r_score, &c->r_row, &c->r_cnt, &c->r_raw};
     for (DevBuf *b : bufs) b->release();
     c->h_in.release(); c->h_out.release();
@@ -1468,6 +1468,7 @@ static int search_impl(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_para
     std::vector<PreDesc> pre_descs;
     std::vector<uint2> pre_items;
     bool any_multi = false, need_df = false, derived_now = false;
+    uint64_t dense_bytes = 0;   // dense contribution arrays of this batch (zeroed before the precompute kernel fills them)
     // sharded: df comes from the replicated per-term table, or — OC_SHARD_COUNT_DF on every rank, e.g. after a
     // commit dropped the table — from counting + all-reduce.  A shard-local list length is never a corpus df.
     const bool count_df = multi_rank && (p->sharded & OC_SHARD_COUNT_DF) != 0;
@@ -1562,22 +1563,51 @@ static int search_impl(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_para
             }
             const char *share_env = getenv("OC_BM25_SHARE");   // "off" / "force": A/B testing of the sharing pass
             const bool share_off = share_env && !strcmp(share_env, "off"), share_force = share_env && !strcmp(share_env, "force");
-            if (distinct && !share_off && (share_force || (walked >= 2 * distinct && walked >= (64u << 20))) && distinct * 8 <= (size_t(6) << 30)) {
-                OCTRY(c->pre_post.ensure(distinct * 8 + 64));
-                uint64_t off = 0;
+            // hot terms (a posting in at least every 16th row) go DENSE: their contributions are scattered once per batch
+            // into a float[rows] array and every (query, tile) item adds 8192 floats with 128-bit loads instead of
+            // walking ~thousands of postings (posting-centred kernel only: every token of the batch has <= 1 term)
+            const char *dense_env = getenv("OC_BM25_DENSE");
+            const char *t2_env = getenv("OC_BM25_TILE2");
+            const bool dense_on = !any_multi && !(dense_env && dense_env[0] == '0') && !share_off && !(t2_env && t2_env[0] == '0');
+            const uint64_t rows_pad = uint64_t(n_tiles) * BM25_TILE;
+            const uint64_t dense_min = std::max<uint64_t>(512, S->n_rows / 16);
+            std::vector<uint8_t> u_dense(uniq.size(), 0);
+            uint64_t n_dense = 0;
+            if (dense_on)
+                for (size_t u = 0; u < uniq.size(); u++)
+                    if (terms[uniq[u].first_e].len >= dense_min && (n_dense + 1) * rows_pad * 4 <= (size_t(8) << 30)) { u_dense[u] = 1; n_dense++; }
+            uint64_t walked_l = 0, distinct_l = 0;   // what is left for the list form
+            for (size_t e = 0; e < terms.size(); e++)
+                if (e_to_u[e] != 0xffffffffu && !u_dense[e_to_u[e]]) walked_l += terms[e].len;
+            for (size_t u = 0; u < uniq.size(); u++) if (!u_dense[u]) distinct_l += terms[uniq[u].first_e].len;
+            const bool lists = distinct_l && !share_off && (share_force || (walked_l >= 2 * distinct_l && walked_l >= (64u << 20))) &&
+                               distinct_l * 8 <= (size_t(6) << 30);
+            if (lists || n_dense) {
+                if (lists) OCTRY(c->pre_post.ensure(distinct_l * 8 + 64));
+                if (n_dense) OCTRY(c->dense_buf.ensure(n_dense * rows_pad * 4));
+                dense_bytes = n_dense * rows_pad * 4;
+                uint64_t off = 0, doff = 0;
                 std::vector<uint64_t> u_off(uniq.size());
+                std::vector<uint8_t> u_used(uniq.size(), 0);
                 for (size_t u = 0; u < uniq.size(); u++) {
-                    u_off[u] = off;
+                    if (!u_dense[u] && !lists) continue;
+                    u_used[u] = 1;
                     const TermDesc &td = terms[uniq[u].first_e];
                     PreDesc pd{};
-                    pd.src = td.ptr; pd.dst = c->pre_post.as<Posting>() + off; pd.len = td.len; pd.weight = td.weight;
+                    pd.src = td.ptr; pd.len = td.len; pd.weight = td.weight;
                     pd.idf = tokens[term_token[uniq[u].first_e]].idf;
+                    if (u_dense[u]) { u_off[u] = doff; pd.dense = c->dense_buf.as<float>() + doff; doff += rows_pad; }
+                    else { u_off[u] = off; pd.dst = c->pre_post.as<Posting>() + off; off += td.len; }
+                    const uint32_t pi = (uint32_t)pre_descs.size();
                     pre_descs.push_back(pd);
-                    for (uint32_t ch = 0; ch * PRE_CHUNK < td.len; ch++) pre_items.push_back(make_uint2((uint32_t)u, ch));
-                    off += td.len;
+                    for (uint32_t ch = 0; ch * PRE_CHUNK < td.len; ch++) pre_items.push_back(make_uint2(pi, ch));
                 }
-                for (size_t e = 0; e < terms.size(); e++)
-                    if (e_to_u[e] != 0xffffffffu) { terms[e].ptr = c->pre_post.as<Posting>() + u_off[e_to_u[e]]; terms[e].flags |= 1u; }
+                for (size_t e = 0; e < terms.size(); e++) {
+                    const uint32_t u = e_to_u[e];
+                    if (u == 0xffffffffu || !u_used[u]) continue;
+                    if (u_dense[u]) { terms[e].ptr = reinterpret_cast<const Posting *>(c->dense_buf.as<float>() + u_off[u]); terms[e].flags |= TD_DENSE; }
+                    else { terms[e].ptr = c->pre_post.as<Posting>() + u_off[u]; terms[e].flags |= TD_PRE; }
+                }
             }
         }
     }
@@ -1652,12 +1682,6 @@ static int search_impl(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_para
     auto bm25_stage = [&]() -> int {
         cudaStream_t ps = side ? c->side : c->stream;
         CU(cudaEventRecord(c->ev[EV_BM0], ps));
-        if (!pre_items.empty()) {
-            bm25_precompute_kernel<<<(unsigned)pre_items.size(), 256, 0, ps>>>(
-                reinterpret_cast<const PreDesc *>(din + o_pre), reinterpret_cast<const uint2 *>(din + o_pitems), p->bm25_k);
-            launched(c);
-            CU(cudaGetLastError());
-        }
         const uint64_t ok_words = uint64_t(n_tiles) * (BM25_TILE / 32);
         if (filter || tombs) {
             OCTRY(c->row_ok.ensure(ok_words * 4));
@@ -1666,6 +1690,13 @@ static int search_impl(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_para
                 c->row_ok.as<uint32_t>(), ok_words);
             launched(c);
             row_ok = c->row_ok.as<uint32_t>();
+        }
+        if (!pre_items.empty()) {
+            if (dense_bytes) CU(cudaMemsetAsync(c->dense_buf.p, 0, dense_bytes, ps));
+            bm25_precompute_kernel<<<(unsigned)pre_items.size(), 256, 0, ps>>>(
+                reinterpret_cast<const PreDesc *>(din + o_pre), reinterpret_cast<const uint2 *>(din + o_pitems), p->bm25_k, row_ok);
+            launched(c);
+            CU(cudaGetLastError());
         }
         const size_t n_td = terms.size();
         OCTRY(c->seg.ensure((n_td * (size_t(n_tiles) + 1) + 1) * 4));
