@@ -139,9 +139,11 @@ int oc_str_commit(oc_str *s);
  * the committed rows of the document are tombstoned at once and its still-pending inserts are cancelled; an
  * insert after the delete is a new document. */
 int oc_str_delete(oc_str *s, const uint64_t *doc_ids, uint64_t n);
-/* This store is one shard of a larger index: document_count (N of the idf, token_score.rs:221) and
- * avg_field_len[n_fields] (NULL = keep) are corpus-wide values owned by the caller; oc_str_commit keeps them
- * instead of recomputing shard-local ones.  Call again after commits to refresh them. */
+/* The caller owns document_count (N of the idf = Index::document_count, token_score.rs:221 — it also counts
+ * documents that have no string field, index/mod.rs:1460) and, when avg_field_len[n_fields] is given, the
+ * corpus-wide average field lengths (this store is one shard of a larger index): oc_str_commit keeps the
+ * caller's values instead of recomputing local ones (avg_field_len == NULL: averages stay locally computed).
+ * Call again after commits to refresh them. */
 int oc_str_set_global(oc_str *s, uint64_t document_count, const float *avg_field_len);
 
 typedef struct {

@@ -819,7 +819,8 @@ struct oc_str {
     std::unordered_map<uint64_t, uint64_t> pending_deleted;   // doc -> seq of its latest delete
     bool committing = false;
     std::vector<uint64_t> deletes_during_commit;
-    bool global_stats = false;                       // document_count / avg_field_len are corpus-wide values owned by the caller (shard of a larger index)
+    bool global_count = false, global_avg = false;   // document_count / avg_field_len are values owned by the caller (shard of a larger index; an
+                                                     // Index whose document_count also counts documents without string fields): commit keeps them
     cudaStream_t load_stream = nullptr;
 };
 static std::shared_ptr<StrSnap> str_snapshot(oc_str *s) {
@@ -875,7 +876,7 @@ extern "C" int oc_str_set_rows(oc_str *s, uint64_t n_rows, const uint64_t *row_d
     ns->version = ++s->version;
     s->cur = ns;
     // a document count that differs from the row count can only be a corpus-wide N (this store is a shard)
-    s->global_stats = document_count != n_rows;
+    s->global_count = s->global_avg = document_count != n_rows;
     for (auto &p : s->pending) p.clear();
     s->pending_deleted.clear();
     return OC_OK;
@@ -891,7 +892,8 @@ extern "C" int oc_str_set_global(oc_str *s, uint64_t document_count, const float
     if (avg_field_len)
         for (size_t i = 0; i < S.fields.size(); i++)
             if (S.fields[i].avg_len != avg_field_len[i]) { S.fields[i].avg_len = avg_field_len[i]; S.fields[i].b_cached = -1.f; }
-    s->global_stats = true;
+    s->global_count = true;
+    s->global_avg = avg_field_len != nullptr;
     return OC_OK;
 }
 
@@ -994,7 +996,7 @@ extern "C" int oc_str_commit(oc_str *s) {
     std::vector<std::vector<PendingPost>> pend;
     std::unordered_map<uint64_t, uint64_t> pdel;
     std::vector<uint32_t> base_alive;
-    bool global_stats;
+    bool global_count, global_avg;
     {
         std::lock_guard<std::mutex> g(s->mu);
         if (s->committing) return fail(OC_ERR_INVALID, "a commit of this store is already in flight");
@@ -1005,7 +1007,7 @@ extern "C" int oc_str_commit(oc_str *s) {
         for (size_t i = 0; i < pend.size(); i++) pend[i].swap(s->pending[i]);
         pdel.swap(s->pending_deleted);
         base_alive = base->alive_host;
-        global_stats = s->global_stats;
+        global_count = s->global_count; global_avg = s->global_avg;
     }
     // on failure: put the taken ops back (in front of whatever arrived meanwhile) and leave `cur` alone
     auto abort_commit = [&](int rc) {
@@ -1089,7 +1091,7 @@ extern "C" int oc_str_commit(oc_str *s) {
         }
         for (uint32_t t = 0; t < max_term; t++) f.term_offsets[t + 1] += f.term_offsets[t];
         f.avg_len = of.avg_len;
-        if (!global_stats) {
+        if (!global_avg) {
             double sum = 0; uint64_t cnt = 0;
             for (uint16_t l : len_of_row) if (l) { sum += l; cnt++; }
             if (cnt) f.avg_len = (float)(sum / (double)cnt);   // info().avg_field_length
@@ -1100,7 +1102,7 @@ extern "C" int oc_str_commit(oc_str *s) {
     }
     const bool identity = !docs.empty() && docs.front() == 0 && docs.back() == docs.size() - 1;
     ns->n_rows = docs.size();
-    ns->document_count = global_stats ? B.document_count : docs.size();
+    ns->document_count = global_count ? B.document_count : docs.size();
     // ---- upload on the store's own stream (searches keep the ctx stream)
     auto upload = [&]() -> int {
         if (!identity && !docs.empty()) {

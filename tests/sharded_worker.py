@@ -29,7 +29,9 @@ def main():
 
     n, dim, vocab, B = 60000, 384, 3000, 12
     rows = synth.make_vectors(n, dim, seed=41)
+    rows[1000:7000] = rows[5]                  # 6000 exact duplicates in rank 0's shard: more ties than the re-score budget
     qv, _ = synth.make_vector_queries(rows, B, seed=42)
+    qv[3] = rows[5] * 2.0                      # -> rank 0's tensor-core scan flags query 3; EVERY rank must re-run the tail
     data = synth.make_text_corpus(n, vocab, seed=43)
     texts = synth.make_text_queries(vocab, B, seed=44)
     lo, hi = shard_range(n, rank, world)
@@ -60,8 +62,12 @@ def main():
             assert h.count == int(oc[i]), (name, rank, i, h.count, int(oc[i]))
             assert_topk_equal(h.doc_ids, h.scores, od[i, :on[i]], os_[i, :on[i]], atol=1e-5)
         t = ctx.last_timing()
+        if mode and rank == 0:
+            assert t["scan_tensor_core"] == 1 and t["scan_unproven"] >= 1, t      # the flagged query was re-run exactly
+        if mode:
+            assert t["rerun_ms"] > 0.0, (rank, t)                                  # ... and every rank re-entered the collective
         if rank == 0:
-            print(f"sharded {name} {kw} omc={omc}: ok on {world} ranks; comm_ms={t['comm_ms']:.3f} device_ms={t['device_ms']:.3f}")
+            print(f"sharded {name} {kw} omc={omc}: ok on {world} ranks; comm_ms={t['comm_ms']:.3f} device_ms={t['device_ms']:.3f} rerun_ms={t['rerun_ms']:.3f}")
     # ---- corpus df counted on device and summed across ranks (one ncclAllReduce): filter, then tombstones
     allowed = np.sort(rng.choice(n, size=n // 3, replace=False))
     fb = orc.make_filter_bits(allowed.tolist(), n)
@@ -86,6 +92,25 @@ def main():
             assert_topk_equal(h.doc_ids, h.scores, od[i, :on[i]], os_[i, :on[i]], atol=1e-5)
         if rank == 0:
             print(f"sharded {name} filter={filt is not None} tombstones={tomb}: ok on {world} ranks (df all-reduce)")
+    # ---- a shard without the replicated df tables (what a commit leaves behind): corpus-wide N / avg length are
+    # supplied by the caller (oc_str_set_global) and df is counted across ranks (OC_SHARD_COUNT_DF)
+    strs2 = ob.StringFieldStorage(ctx, sd)                     # no global_df
+    strs2.set_global(data.document_count, [data.fields[0].avg_field_len])
+    try:
+        ob.search(ctx, None, strs2, "fulltext", texts=texts, sharded=True, limit=10)
+        raise AssertionError("a shard-local posting-list length must never be taken for the corpus df")
+    except ob.OcError as e:
+        assert "OC_SHARD_COUNT_DF" in str(e)
+    hits = ob.search(ctx, emb, strs2, "hybrid", texts=texts, q_vecs=qv, sharded=True, shard_count_df=True, limit=10, similarity=0.0)
+    sb = orc.SearchBatch(ix, st)
+    for i in range(B):
+        sb.add(2, q_vec=qv[i], text=texts[i], limit=10, similarity=0.0)
+    od, os_, on, oc = sb.run(4)
+    for i, h in enumerate(hits):
+        assert h.count == int(oc[i]), ("count_df", rank, i, h.count, int(oc[i]))
+        assert_topk_equal(h.doc_ids, h.scores, od[i, :on[i]], os_[i, :on[i]], atol=1e-5)
+    if rank == 0:
+        print(f"sharded hybrid with counted df (no replicated tables): ok on {world} ranks")
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:
