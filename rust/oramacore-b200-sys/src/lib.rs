@@ -12,6 +12,10 @@ use std::ffi::{c_char, c_int, c_void, CStr};
 #[repr(C)] pub struct OcEmb { _p: [u8; 0] }
 #[repr(C)] pub struct OcStr { _p: [u8; 0] }
 #[repr(C)] pub struct OcBatcher { _p: [u8; 0] }
+#[repr(C)] pub struct OcFilter { _p: [u8; 0] }
+#[repr(C)] pub struct OcFacets { _p: [u8; 0] }
+#[repr(C)] pub struct OcDict { _p: [u8; 0] }
+#[repr(C)] pub struct OcResolved { _p: [u8; 0] }
 
 pub const OC_MODE_FULLTEXT: c_int = 0;
 pub const OC_MODE_VECTOR: c_int = 1;
@@ -22,6 +26,8 @@ pub const OC_DTYPE_BF16: c_int = 1;
 /// any rank's string store holds uncommitted deletes (the df all-reduce must be entered by all ranks).
 pub const OC_SHARDED: c_int = 1;
 pub const OC_SHARD_TOMBSTONES: c_int = 2;
+/// count corpus df across ranks instead of using replicated tables (a commit on a shard drops them)
+pub const OC_SHARD_COUNT_DF: c_int = 4;
 
 #[repr(C)]
 pub struct OcSearchParams {
@@ -45,7 +51,24 @@ pub struct OcSearchParams {
     pub omc_mult: *const f32,
     pub n_omc: u64,
     pub sharded: c_int,
+    pub vector_limit: u32,          // 0 => limit (limit_hint of the vector stage, search.rs:330-336)
+    pub filter: *const OcFilter,    // device-resident FilterResult bitmap; wins over filter_bits
 }
+
+#[repr(C)]
+pub struct OcFacetReq { pub field: u32, pub variant: u32, pub from: f64, pub to: f64 }
+
+#[repr(C)]
+pub struct OcResolveParams {
+    pub texts: *const *const c_char,
+    pub n_queries: u32,
+    pub exact: c_int,
+    pub tolerance: c_int,           // < 0 => None (prefix expansion)
+    pub field_boost: *const f32,
+    pub field_mask: *const u8,
+    pub exact_match_boost: f32,
+}
+pub type OcStemFn = unsafe extern "C" fn(tok: *const c_char, len: usize, out: *mut c_char, cap: usize, user: *mut c_void) -> usize;
 
 extern "C" {
     pub fn oc_last_error() -> *const c_char;
@@ -85,6 +108,39 @@ extern "C" {
     pub fn oc_pinned_free(p: *mut c_void);
     pub fn oc_search(ctx: *mut OcCtx, emb: *mut OcEmb, s: *mut OcStr, p: *const OcSearchParams,
                      out_doc_ids: *mut u64, out_scores: *mut f32, out_n: *mut u32, out_count: *mut u64) -> c_int;
+    /// caller-owned N / average field lengths (shards; Index::document_count), kept across commits
+    pub fn oc_str_set_global(s: *mut OcStr, document_count: u64, avg_field_len: *const f32) -> c_int;
+    // FilterResult (filter.rs:344-392) evaluated on the device
+    pub fn oc_filter_from_ids(ctx: *mut OcCtx, doc_ids: *const u64, n: u64, nbits: u64, out: *mut *mut OcFilter) -> c_int;
+    pub fn oc_filter_from_bits(ctx: *mut OcCtx, bits: *const u64, nbits: u64, out: *mut *mut OcFilter) -> c_int;
+    pub fn oc_filter_and(a: *const OcFilter, b: *const OcFilter, out: *mut *mut OcFilter) -> c_int;
+    pub fn oc_filter_or(a: *const OcFilter, b: *const OcFilter, out: *mut *mut OcFilter) -> c_int;
+    pub fn oc_filter_not(a: *const OcFilter, out: *mut *mut OcFilter) -> c_int;
+    pub fn oc_filter_count(f: *const OcFilter, out: *mut u64) -> c_int;
+    pub fn oc_filter_read(f: *const OcFilter, out_bits: *mut u64) -> c_int;
+    pub fn oc_filter_destroy(f: *mut OcFilter);
+    // facets over the score set (facet.rs:147-209)
+    pub fn oc_facets_create(ctx: *mut OcCtx, nbits: u64, out: *mut *mut OcFacets) -> c_int;
+    pub fn oc_facets_destroy(f: *mut OcFacets);
+    pub fn oc_facets_add_field(f: *mut OcFacets, n_variants: u32, variant_offsets: *const u64, doc_ids: *const u64, out_field: *mut u32) -> c_int;
+    pub fn oc_facets_add_number_field(f: *mut OcFacets, n: u64, values_sorted: *const f64, doc_ids: *const u64, out_field: *mut u32) -> c_int;
+    pub fn oc_search_facets(ctx: *mut OcCtx, emb: *mut OcEmb, s: *mut OcStr, f: *mut OcFacets, p: *const OcSearchParams,
+                            reqs: *const OcFacetReq, n_reqs: u32, out_counts: *mut u64) -> c_int;
+    /// search_on_indexes' union of the per-index maps (search.rs:304-338, 482-498), host side
+    pub fn oc_merge_results(n_indexes: u32, n_queries: u32, limit: u32, offset: u32, in_stride: u32,
+                            doc_ids: *const *const u64, scores: *const *const f32, n: *const *const u32,
+                            counts: *const *const u64, out_doc_ids: *mut u64, out_scores: *mut f32,
+                            out_n: *mut u32, out_count: *mut u64) -> c_int;
+    // term dictionary + batch query resolution (tokenize_and_stem + FST expansion), host only
+    pub fn oc_dict_create(n_fields: u32, out: *mut *mut OcDict) -> c_int;
+    pub fn oc_dict_destroy(d: *mut OcDict);
+    pub fn oc_dict_add_terms(d: *mut OcDict, field: u32, terms: *const *const c_char, n: u32, out_ids: *mut u32) -> c_int;
+    pub fn oc_dict_lookup(d: *mut OcDict, field: u32, term: *const c_char, out_id: *mut u32) -> c_int;
+    pub fn oc_dict_size(d: *mut OcDict, field: u32) -> u32;
+    pub fn oc_dict_set_stemmer(d: *mut OcDict, f: Option<OcStemFn>, user: *mut c_void) -> c_int;
+    pub fn oc_dict_resolve(d: *mut OcDict, p: *const OcResolveParams, out: *mut *mut OcResolved) -> c_int;
+    pub fn oc_resolved_fill(r: *const OcResolved, p: *mut OcSearchParams);
+    pub fn oc_resolved_free(r: *mut OcResolved);
 }
 
 fn check(rc: c_int) -> anyhow::Result<()> {
