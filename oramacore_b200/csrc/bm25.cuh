@@ -606,19 +606,62 @@ __host__ __device__ inline size_t bm25_tile2_smem_bytes(bool threshold, bool omc
     return b + 64;
 }
 
+// Per-(tile, query) item descriptors, flattened by bm25_flatten_kernel so that an item needs ONE level of
+// global loads (prefetched during the previous item) instead of the chain query -> tokens -> terms -> seg.
+struct ItemTok {            // 32 B
+    const void *ptr;        // list: first posting of the term inside this tile; dense: the tile's slice of the float array
+    uint32_t n;             // list: postings in the tile; dense: BM25_TILE (0 = token absent from this tile)
+    uint32_t flags;         // TD_PRE / TD_DENSE
+    float w, idf;
+    uint32_t bit, pad;
+};
+constexpr uint32_t BM25_FLAT_TOK = 4;   // tokens per query the flat descriptors hold (longer queries: in-kernel table build)
+__global__ void __launch_bounds__(256) bm25_flatten_kernel(const TermDesc *terms, const TokenDesc *tokens, const QueryDesc *queries,
+                                                          const uint32_t *seg, uint32_t n_tiles, uint32_t n_queries, ItemTok *flat) {
+    const uint64_t gid = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const uint64_t total = uint64_t(n_tiles) * n_queries * BM25_FLAT_TOK;
+    if (gid >= total) return;
+    const uint32_t j = uint32_t(gid % BM25_FLAT_TOK);
+    const uint64_t item = gid / BM25_FLAT_TOK;
+    const uint32_t tile = uint32_t(item / n_queries), q = uint32_t(item % n_queries);
+    const QueryDesc qd = queries[q];
+    ItemTok it{};
+    if (j < qd.token_end - qd.token_begin) {
+        const TokenDesc tk = tokens[qd.token_begin + j];
+        it.idf = tk.idf; it.bit = tk.bit;
+        if (tk.term_end > tk.term_begin) {
+            const TermDesc td = terms[tk.term_begin];
+            it.flags = td.flags; it.w = td.weight;
+            if (td.flags & TD_DENSE) {
+                it.ptr = reinterpret_cast<const float *>(td.ptr) + size_t(tile) * BM25_TILE;
+                it.n = td.len ? BM25_TILE : 0;
+            } else {
+                const uint32_t *sg = seg + size_t(tk.term_begin) * (n_tiles + 1);
+                const uint32_t lo = sg[tile], hi = sg[tile + 1];
+                it.ptr = reinterpret_cast<const uint2 *>(td.ptr) + lo;
+                it.n = hi - lo;
+            }
+        }
+    }
+    flat[gid] = it;
+}
+
 template <bool THRESH, bool OMC>
-__global__ void __launch_bounds__(BM25_THREADS, 4) bm25_tile2_kernel(const Bm25Params p, unsigned int *work_counter) {
+__global__ void __launch_bounds__(BM25_THREADS, 4) bm25_tile2_kernel(const Bm25Params p, const ItemTok *flat) {
     extern __shared__ __align__(16) uint8_t smem[];
     float *score = reinterpret_cast<float *>(smem);
     float *aux = score + BM25_TILE;                                    // OMC multipliers
     uint32_t *mask = reinterpret_cast<uint32_t *>(score + BM25_TILE * (OMC ? 2 : 1));
     uint32_t *okb = mask + (THRESH ? BM25_TILE : 0);
     uint64_t *tbuf = reinterpret_cast<uint64_t *>(okb + BM25_TILE / 32);
-    __shared__ uint32_t s_cnt, s_matched, s_item, s_ovf;
-    __shared__ unsigned int s_maxo, s_mino;
+    // per-item counters, double-buffered by item parity: the set of the NEXT item is reset while this one runs, so no
+    // thread can still be reading a counter that another thread is already resetting
+    __shared__ uint32_t s_cnt2[2], s_matched2[2];
+    __shared__ unsigned int s_maxo2[2], s_mino2[2];
     __shared__ const uint2 *t_ptr[BM25_MAX_TOK];
     __shared__ uint32_t t_n[BM25_MAX_TOK], t_bit[BM25_MAX_TOK], t_pre[BM25_MAX_TOK];
     __shared__ float t_w[BM25_MAX_TOK], t_idf[BM25_MAX_TOK];
+    __shared__ uint32_t s_ntok;
     __shared__ uint32_t s_mbits[BM25_TILE / 32];
 
     const uint32_t tid = threadIdx.x;
@@ -631,51 +674,77 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_tile2_kernel(const Bm25P
         reinterpret_cast<float4 *>(score)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (THRESH) reinterpret_cast<uint4 *>(mask)[i] = make_uint4(0u, 0u, 0u, 0u);
     }
-    for (;;) {
-        __syncthreads();                                   // previous item fully retired (tables, buffers, accumulators clean)
-        if (tid == 0) {
-            s_item = atomicAdd(work_counter, 1u);
-            s_cnt = 0; s_matched = 0; s_ovf = 0; s_maxo = f32_ordered(0.f); s_mino = f32_ordered(0.f);
-        }
-        if (want_bits) s_mbits[tid] = 0u;
-        __syncthreads();
-        const uint32_t item = s_item;
-        if (item >= n_items) break;
+    // items are dealt round-robin (tile-major: the queries sharing a tile's hot ranges run back to back through L2);
+    // the next item's descriptors travel from global memory while the current item is processed
+    auto store_tok = [&](const ItemTok &it, uint32_t j) {
+        t_ptr[j] = reinterpret_cast<const uint2 *>(it.ptr); t_n[j] = it.n; t_pre[j] = it.flags;
+        t_w[j] = it.w; t_idf[j] = it.idf; t_bit[j] = it.bit;
+    };
+    uint32_t item = blockIdx.x;
+    if (flat && item < n_items && tid < BM25_FLAT_TOK) store_tok(flat[size_t(item) * BM25_FLAT_TOK + tid], tid);
+    if (tid < 2) { s_cnt2[tid] = 0; s_matched2[tid] = 0; s_maxo2[tid] = f32_ordered(0.f); s_mino2[tid] = f32_ordered(0.f); }
+    if (tid == 0) s_ntok = BM25_FLAT_TOK;
+    for (uint32_t par = 0; item < n_items; item += gridDim.x, par ^= 1u) {
         const uint32_t tile = item / p.n_queries, q = item % p.n_queries;
         const uint32_t row0 = tile * BM25_TILE;
-        const QueryDesc qd = p.queries[q];
-        const uint32_t ntok = min(qd.token_end - qd.token_begin, BM25_MAX_TOK);
-        if (tid < ntok) {
-            const TokenDesc tk = p.tokens[qd.token_begin + tid];
-            uint32_t n = 0;
-            if (tk.term_end > tk.term_begin) {
-                const uint32_t e = tk.term_begin;
-                const TermDesc td = p.terms[e];
-                const uint32_t *sg = p.seg + size_t(e) * (p.n_tiles + 1);
-                const uint32_t lo = sg[tile], hi = sg[tile + 1];
-                t_ptr[tid] = reinterpret_cast<const uint2 *>(td.ptr) + lo;
-                n = hi - lo;
-                t_w[tid] = td.weight; t_pre[tid] = td.flags;
-                if (td.flags & TD_DENSE) {   // per-row contributions of the whole corpus: this tile's 8192 floats
-                    t_ptr[tid] = reinterpret_cast<const uint2 *>(reinterpret_cast<const float *>(td.ptr) + row0);
-                    n = td.len ? BM25_TILE : 0;
+        uint32_t &s_cnt = s_cnt2[par], &s_matched = s_matched2[par];
+        unsigned int &s_maxo = s_maxo2[par], &s_mino = s_mino2[par];
+        if (want_bits) s_mbits[tid] = 0u;
+        __syncthreads();                                   // previous item retired: accumulators clean, table + counters set
+        if (tid == 0) { s_cnt2[par ^ 1u] = 0; s_matched2[par ^ 1u] = 0; s_maxo2[par ^ 1u] = f32_ordered(0.f); s_mino2[par ^ 1u] = f32_ordered(0.f); }
+        const QueryDesc qd = p.queries[q];                 // (required / slow-path token range; L2-hot, off the critical path)
+        if (!flat) {   // a query of this batch has more than BM25_FLAT_TOK tokens: build the table here
+            const uint32_t ntok = min(qd.token_end - qd.token_begin, BM25_MAX_TOK);
+            if (tid < ntok) {
+                const TokenDesc tk = p.tokens[qd.token_begin + tid];
+                ItemTok it{};
+                it.idf = tk.idf; it.bit = tk.bit;
+                if (tk.term_end > tk.term_begin) {
+                    const TermDesc td = p.terms[tk.term_begin];
+                    it.flags = td.flags; it.w = td.weight;
+                    if (td.flags & TD_DENSE) { it.ptr = reinterpret_cast<const float *>(td.ptr) + row0; it.n = td.len ? BM25_TILE : 0; }
+                    else {
+                        const uint32_t *sg = p.seg + size_t(tk.term_begin) * (p.n_tiles + 1);
+                        it.ptr = reinterpret_cast<const uint2 *>(td.ptr) + sg[tile]; it.n = sg[tile + 1] - sg[tile];
+                    }
                 }
+                store_tok(it, tid);
             }
-            t_n[tid] = n; t_idf[tid] = tk.idf; t_bit[tid] = tk.bit;
+            if (tid == 0) s_ntok = ntok;
         }
         if (use_ok)
             for (uint32_t i = tid; i < BM25_TILE / 32; i += BM25_THREADS) okb[i] = p.row_ok_bits[row0 / 32 + i];
-        __syncthreads();
+        if (!flat || use_ok) __syncthreads();
+        const uint32_t ntok = s_ntok;
+        // in flight during this item: the next item's descriptors and this query's running threshold
+        const uint32_t next = item + gridDim.x;
+        ItemTok nx{};
+        if (flat && next < n_items && tid < BM25_FLAT_TOK) nx = flat[size_t(next) * BM25_FLAT_TOK + tid];
+        unsigned long long tau = p.tau[q];
 
         // ---------------------------------------- accumulate, token by token (the reference's summation order)
         uint32_t total = 0;
         bool prev_dense = false;
+        // first batch of the next LIST token is requested before the current token is applied
+        uint2 pre[4];
+        auto preload = [&](uint32_t j, uint2 (&r)[4]) {
+            const uint2 *pp = t_ptr[j];
+            const uint32_t n = t_n[j];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t pi = tid + u * BM25_THREADS;
+                r[u] = pi < n ? __ldg(pp + pi) : make_uint2(0xffffffffu, 0u);
+            }
+        };
+        auto next_list = [&](uint32_t j) { while (j < ntok && (t_n[j] == 0 || (t_pre[j] & TD_DENSE))) j++; return j; };
+        uint32_t jl = next_list(0);
+        if (jl < ntok) preload(jl, pre);
         for (uint32_t j = 0; j < ntok; j++) {
             const uint32_t n = t_n[j];
             if (n == 0) continue;                          // block-uniform
             total += n;
             const uint2 *pp = t_ptr[j];
-            const bool pre = (t_pre[j] & TD_PRE) != 0;
+            const bool pre_c = (t_pre[j] & TD_PRE) != 0;
             const float w = t_w[j], idf = t_idf[j];
             const uint32_t bit = t_bit[j];
             if (t_pre[j] & TD_DENSE) {
@@ -709,10 +778,11 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_tile2_kernel(const Bm25P
             }
             if (prev_dense) { __syncthreads(); prev_dense = false; }   // a list token scatters across the owners' slots
             auto apply = [&](const uint2 rec) {
+                if (rec.x == 0xffffffffu) return;
                 const uint32_t l = rec.x - row0;
                 if (use_ok && !((okb[l >> 5] >> (l & 31)) & 1u)) return;
                 float c;
-                if (pre) c = __uint_as_float(rec.y);       // contribution precomputed once per batch (NaN = skip)
+                if (pre_c) c = __uint_as_float(rec.y);       // contribution precomputed once per batch (NaN = skip)
                 else {
                     const float ntf = __fmul_rn(w, __uint_as_float(rec.y));
                     c = f32_is_normal(ntf) ? bm25_sat(ntf, p.k, kp1, idf) : __int_as_float(0x7fc00000);   // bm25.rs:387,501
@@ -722,15 +792,24 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_tile2_kernel(const Bm25P
                     if (THRESH) mask[l] |= bit;
                 }
             };
-            uint32_t base = 0;
-            for (; base + BM25_THREADS * 4 <= n; base += BM25_THREADS * 4) {   // full batches: 4 loads in flight per lane
+            // this token's first batch is already here; request the next list token's before applying it
+            uint2 cur[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) cur[u] = pre[u];
+            jl = next_list(j + 1);
+            if (jl < ntok) preload(jl, pre);
+#pragma unroll
+            for (int u = 0; u < 4; u++) apply(cur[u]);
+            for (uint32_t base = BM25_THREADS * 4; base < n; base += BM25_THREADS * 4) {   // long ranges: 4 loads in flight per lane
                 uint2 r[4];
 #pragma unroll
-                for (int u = 0; u < 4; u++) r[u] = __ldg(pp + base + tid + u * BM25_THREADS);
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t pi = base + tid + u * BM25_THREADS;
+                    r[u] = pi < n ? __ldg(pp + pi) : make_uint2(0xffffffffu, 0u);
+                }
 #pragma unroll
                 for (int u = 0; u < 4; u++) apply(r[u]);
             }
-            for (uint32_t pi = base + tid; pi < n; pi += BM25_THREADS) apply(__ldg(pp + pi));
             __syncthreads();                               // the next token may touch the same rows
         }
 
@@ -749,7 +828,6 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_tile2_kernel(const Bm25P
 
         // ---------------------------------------- finish: count, extrema, gated top-n; leave the accumulators clean
         const float mh = p.min_hint ? p.min_hint[q] : 0.f;
-        unsigned long long tau = p.tau[q];
         float tau_f = tau ? key_score(tau) : -INFINITY;
         uint32_t matched = 0;
         float lmax = 0.f, lmin = 0.f;
@@ -761,7 +839,7 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_tile2_kernel(const Bm25P
             const unsigned long long key = make_key(proxy, row0 + l);
             if (key <= tau) return false;
             const uint32_t slot = atomicAdd(&s_cnt, 1u);
-            if (slot < p.cap) tbuf[slot] = key; else s_ovf = 1u;
+            if (slot < p.cap) tbuf[slot] = key;                             // s_cnt > cap afterwards == overflow
             return true;
         };
         auto visit = [&](float s, uint32_t l) -> bool {   // one matched row
@@ -771,8 +849,65 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_tile2_kernel(const Bm25P
             lmin = fminf(lmin, s);
             return consider(s, l);
         };
-        // the sparse finish re-derives a candidate's raw score from its key (proxy == score): only without OMC / min hint
-        const bool sparse = total != 0 && total <= BM25_SPARSE_MAX && p.cap >= BM25_SPARSE_MAX && !OMC && mh == 0.f;
+        // without OMC / a min hint a candidate's raw score is its key's score (proxy == score): nothing is re-read at emit
+        const bool ft_from_key = !OMC && mh == 0.f;
+        const bool sparse = total != 0 && total <= BM25_SPARSE_MAX && p.cap >= BM25_SPARSE_MAX && ft_from_key;
+        auto scan_pass = [&](const bool chunked) {
+            matched = 0; lmax = 0.f; lmin = 0.f;
+            for (uint32_t base = 0; base < rows_here; base += BM25_CHUNK) {
+                const uint32_t l0 = base + tid * 4;
+                bool pushed = false;
+                const float4 s4 = *reinterpret_cast<const float4 *>(score + l0);
+                float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+                if (THRESH) {
+                    const uint4 m4 = *reinterpret_cast<const uint4 *>(mask + l0);
+                    const uint32_t mv[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+                    for (int u = 0; u < 4; u++)   // bm25.rs:416-428: keep popcount(mask) >= required
+                        sv[u] = (mv[u] != 0u && uint32_t(__popc(mv[u])) >= qd.required) ? sv[u] : 0.f;
+                }
+                if (!OMC && !want_bits) {
+                    // common case: branch-free bookkeeping of the 4 slots, one candidate test on their maximum
+                    // (absent rows hold 0.0: no-ops for the folds, which start at 0.0, token_score.rs:398-401)
+                    matched += (sv[0] != 0.f ? 1u : 0u) + (sv[1] != 0.f ? 1u : 0u) + (sv[2] != 0.f ? 1u : 0u) + (sv[3] != 0.f ? 1u : 0u);
+                    const float m4 = fmaxf(fmaxf(sv[0], sv[1]), fmaxf(sv[2], sv[3]));
+                    lmax = fmaxf(lmax, m4);
+                    lmin = fminf(lmin, fminf(fminf(sv[0], sv[1]), fminf(sv[2], sv[3])));
+                    if (__fsub_rn(m4, mh) >= tau_f) {
+#pragma unroll
+                        for (int u = 0; u < 4; u++)
+                            if (sv[u] != 0.f) pushed |= consider(sv[u], l0 + u);
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+                        if (sv[u] != 0.f) pushed |= visit(sv[u], l0 + u);
+                }
+                if (!chunked) continue;
+                if (!__syncthreads_or(pushed)) continue;
+                const uint32_t c = s_cnt;
+                __syncthreads();
+                if (c + BM25_CHUNK > p.cap && base + BM25_CHUNK < rows_here) {
+                    block_keep_top(tbuf, c, p.cap, p.n_keep, tid);
+                    const uint32_t kept = min(c, p.n_keep);
+                    if (tid == 0) s_cnt = kept;
+                    if (kept == p.n_keep) { tau = max(tau, (unsigned long long)tbuf[p.n_keep - 1]); tau_f = key_score(tau); }
+                    __syncthreads();
+                }
+            }
+        };
+        auto reduce = [&]() {   // block reductions of count / extrema
+            matched = __reduce_add_sync(0xffffffffu, matched);
+            for (int o = 16; o > 0; o >>= 1) {
+                lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+                lmin = fminf(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+            }
+            if ((tid & 31) == 0 && matched) {
+                atomicAdd(&s_matched, matched);
+                atomicMax(&s_maxo, f32_ordered(lmax));
+                atomicMin(&s_mino, f32_ordered(lmin));
+            }
+        };
         if (sparse) {
             // walk the postings again; the first visitor of a row takes its sum and clears the slot
             for (uint32_t j = 0; j < ntok; j++) {
@@ -790,83 +925,32 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_tile2_kernel(const Bm25P
                     }
                 }
             }
-            __syncthreads();
             if (THRESH) {
+                __syncthreads();
                 for (uint32_t j = 0; j < ntok; j++) {
                     const uint32_t n = t_n[j];
                     const uint2 *pp = t_ptr[j];
                     for (uint32_t pi = tid; pi < n; pi += BM25_THREADS) mask[__ldg(&pp[pi].x) - row0] = 0u;
                 }
             }
-        } else if (total != 0) {
-            // DENSE: scan the slots (4 per thread per step: one LDS.128); overflow of the candidate buffer (cold
-            // threshold) -> redo chunk by chunk with a compress between chunks, as K3 does
-            auto scan_pass = [&](const bool chunked) {
-                matched = 0; lmax = 0.f; lmin = 0.f;
-                for (uint32_t base = 0; base < rows_here; base += BM25_CHUNK) {
-                    const uint32_t l0 = base + tid * 4;
-                    bool pushed = false;
-                    const float4 s4 = *reinterpret_cast<const float4 *>(score + l0);
-                    float sv[4] = {s4.x, s4.y, s4.z, s4.w};
-                    if (THRESH) {
-                        const uint4 m4 = *reinterpret_cast<const uint4 *>(mask + l0);
-                        const uint32_t mv[4] = {m4.x, m4.y, m4.z, m4.w};
-#pragma unroll
-                        for (int u = 0; u < 4; u++)
-                            sv[u] = (mv[u] != 0u && uint32_t(__popc(mv[u])) >= qd.required) ? sv[u] : 0.f;
-                    }
-                    if (!OMC && !want_bits) {
-                        // common case: branch-free bookkeeping of the 4 slots, one candidate test on their maximum
-                        // (absent rows hold 0.0: no-ops for the folds, which start at 0.0, token_score.rs:398-401)
-                        matched += (sv[0] != 0.f ? 1u : 0u) + (sv[1] != 0.f ? 1u : 0u) + (sv[2] != 0.f ? 1u : 0u) + (sv[3] != 0.f ? 1u : 0u);
-                        const float m4 = fmaxf(fmaxf(sv[0], sv[1]), fmaxf(sv[2], sv[3]));
-                        lmax = fmaxf(lmax, m4);
-                        lmin = fminf(lmin, fminf(fminf(sv[0], sv[1]), fminf(sv[2], sv[3])));
-                        if (__fsub_rn(m4, mh) >= tau_f) {
-#pragma unroll
-                            for (int u = 0; u < 4; u++)
-                                if (sv[u] != 0.f) pushed |= consider(sv[u], l0 + u);
-                        }
-                    } else {
-#pragma unroll
-                        for (int u = 0; u < 4; u++)
-                            if (sv[u] != 0.f) pushed |= visit(sv[u], l0 + u);
-                    }
-                    if (!chunked) continue;
-                    if (!__syncthreads_or(pushed)) continue;
-                    const uint32_t c = s_cnt;
-                    __syncthreads();
-                    if (c + BM25_CHUNK > p.cap && base + BM25_CHUNK < rows_here) {
-                        block_keep_top(tbuf, c, p.cap, p.n_keep, tid);
-                        const uint32_t kept = min(c, p.n_keep);
-                        if (tid == 0) s_cnt = kept;
-                        if (kept == p.n_keep) { tau = max(tau, (unsigned long long)tbuf[p.n_keep - 1]); tau_f = key_score(tau); }
-                        __syncthreads();
-                    }
-                }
-            };
-            scan_pass(false);
+            reduce();
             __syncthreads();
-            if (s_ovf) {
+        } else if (total != 0) {
+            // DENSE: scan the slots (4 per thread per step: one LDS.128, owner-aligned with the dense adds)
+            scan_pass(false);
+            reduce();
+            __syncthreads();
+            if (s_cnt > p.cap) {   // cold threshold overflowed the candidate buffer: redo chunk by chunk with a compress between chunks
                 __syncthreads();
-                if (tid == 0) { s_cnt = 0u; s_ovf = 0u; }
+                if (tid == 0) { s_cnt = 0u; s_matched = 0u; s_maxo = f32_ordered(0.f); s_mino = f32_ordered(0.f); }
                 __syncthreads();
                 scan_pass(true);
+                reduce();
                 __syncthreads();
             }
+        } else {
+            __syncthreads();
         }
-        // ---- block reductions of count / extrema
-        matched = __reduce_add_sync(0xffffffffu, matched);
-        for (int o = 16; o > 0; o >>= 1) {
-            lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
-            lmin = fminf(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
-        }
-        if ((tid & 31) == 0 && matched) {
-            atomicAdd(&s_matched, matched);
-            atomicMax(&s_maxo, f32_ordered(lmax));
-            atomicMin(&s_mino, f32_ordered(lmin));
-        }
-        __syncthreads();
         // ---- emit: best <= n_keep of the buffer
         const size_t slot_base = (size_t(q) * p.n_tiles + tile);
         uint32_t c = min(s_cnt, p.cap);
@@ -878,7 +962,15 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_tile2_kernel(const Bm25P
         for (uint32_t i = tid; i < c; i += BM25_THREADS) {
             const uint64_t key = tbuf[i];
             p.cand_key[slot_base * p.n_keep + i] = key;
-            p.cand_ft[slot_base * p.n_keep + i] = sparse ? key_score(key) : score[key_idx(key) - row0];
+            p.cand_ft[slot_base * p.n_keep + i] = ft_from_key ? key_score(key) : score[key_idx(key) - row0];
+        }
+        if (want_bits) p.matched_bits[slot_base * (BM25_TILE / 32) + tid] = s_mbits[tid];
+        if (!sparse && total != 0) {
+            if (!ft_from_key) __syncthreads();             // emit read the scores of other owners' slots
+            for (uint32_t i = tid; i < BM25_TILE / 4; i += BM25_THREADS) {   // owner-aligned with the scan: no barrier needed before it
+                reinterpret_cast<float4 *>(score)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (THRESH) reinterpret_cast<uint4 *>(mask)[i] = make_uint4(0u, 0u, 0u, 0u);
+            }
         }
         if (tid == 0) {
             p.cand_cnt[slot_base] = c;
@@ -886,14 +978,7 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_tile2_kernel(const Bm25P
             p.tile_max[slot_base] = f32_unordered(s_maxo);
             p.tile_min[slot_base] = f32_unordered(s_mino);
         }
-        if (want_bits) p.matched_bits[slot_base * (BM25_TILE / 32) + tid] = s_mbits[tid];
-        if (!sparse && total != 0) {
-            __syncthreads();                               // emit read the scores
-            for (uint32_t i = tid; i < BM25_TILE / 4; i += BM25_THREADS) {   // leave the accumulators clean
-                reinterpret_cast<float4 *>(score)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (THRESH) reinterpret_cast<uint4 *>(mask)[i] = make_uint4(0u, 0u, 0u, 0u);
-            }
-        }
+        if (flat && tid < BM25_FLAT_TOK) store_tok(nx, tid);   // the next item's table (this item no longer reads it)
     }
 }
 

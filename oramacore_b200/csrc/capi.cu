@@ -145,7 +145,7 @@ struct oc_ctx {
     // workspaces
     DevBuf in_blob, in_blob0, q_pad, q_inv, eff_norm, filter_dev, scan_cand, v_doc, v_score, v_row, v_cnt, v_srow, v_ft, v_present, v_raw;
     DevBuf seg, df_dev, row_ok, tau, cand_key, cand_ft, cand_cnt, tile_cnt, tile_max, tile_min, min_hint;
-    DevBuf out_blob, shard_send, shard_recv, work_ctr, mbits, dbits, facet_req, facet_out;
+    DevBuf out_blob, shard_send, shard_recv, work_ctr, flat_desc, mbits, dbits, facet_req, facet_out;
     bool gemm_pending = false; const float *gemm_inv_norm = nullptr;
     DevBuf q_bf16, q_rho, pre_post, dense_buf, g_thr, g_eps, g_ovf, g_ovfcnt, g_resc, g_cand, g_cnt, g_flag, g_max, r_qpad, r_qinv, r_map, r_doc, r_score, r_row, r_cnt, r_raw;
 
@@ -190,7 +190,7 @@ extern "C" void oc_shutdown(oc_ctx *c) {
     DevBuf *bufs[] = {&c->in_blob, &c->q_pad, &c->q_inv, &c->eff_norm, &c->filter_dev, &c->scan_cand, &c->v_doc,
                       &c->v_score, &c->v_row, &c->v_cnt, &c->v_srow, &c->v_ft, &c->v_present, &c->v_raw, &c->seg, &c->df_dev,
                       &c->row_ok, &c->tau, &c->cand_key, &c->cand_ft, &c->cand_cnt, &c->tile_cnt, &c->tile_max,
-                      &c->tile_min, &c->min_hint, &c->out_blob, &c->shard_send, &c->shard_recv, &c->work_ctr, &c->mbits, &c->dbits, &c->facet_req, &c->facet_out, &c->q_bf16, &c->q_rho, &c->pre_post, &c->dense_buf, &c->g_thr, &c->g_eps, &c->g_ovf, &c->g_ovfcnt, &c->g_resc, &c->g_cand, &c->g_cnt, &c->g_max,
+                      &c->tile_min, &c->min_hint, &c->out_blob, &c->shard_send, &c->shard_recv, &c->work_ctr, &c->flat_desc, &c->mbits, &c->dbits, &c->facet_req, &c->facet_out, &c->q_bf16, &c->q_rho, &c->pre_post, &c->dense_buf, &c->g_thr, &c->g_eps, &c->g_ovf, &c->g_ovfcnt, &c->g_resc, &c->g_cand, &c->g_cnt, &c->g_max,
                       &c->g_flag, &c->r_qpad, &c->r_qinv, &c->r_map, &c->r_doc, &c->r_score, &c->r_row, &c->r_cnt, &c->r_raw};
     for (DevBuf *b : bufs) b->release();
     c->h_in.release(); c->h_out.release();
@@ -1329,31 +1329,42 @@ static int launch_tile_t(oc_ctx *c, const Bm25Params &bp, uint32_t grid, size_t 
     return OC_OK;
 }
 template <bool THRESH, bool OMC>
-static int launch_tile2_t(oc_ctx *c, const Bm25Params &bp, size_t smem, cudaStream_t st) {
+static int launch_tile2_t(oc_ctx *c, const Bm25Params &bp, size_t smem, cudaStream_t st, const ItemTok *flat) {
     if (smem_cfg_needed(c->device, (const void *)bm25_tile2_kernel<THRESH, OMC>, smem))
         CU(cudaFuncSetAttribute(bm25_tile2_kernel<THRESH, OMC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bm25_tile2_kernel<THRESH, OMC>, BM25_THREADS, smem));
     const uint64_t items = uint64_t(bp.n_tiles) * bp.n_queries;
     const uint32_t grid = (uint32_t)std::min<uint64_t>(items, uint64_t(std::max(per_sm, 1)) * c->prop.multiProcessorCount);
-    OCTRY(c->work_ctr.ensure(4));
-    CU(cudaMemsetAsync(c->work_ctr.p, 0, 4, st));
-    bm25_tile2_kernel<THRESH, OMC><<<grid, BM25_THREADS, smem, st>>>(bp, c->work_ctr.as<unsigned int>());
+    bm25_tile2_kernel<THRESH, OMC><<<grid, BM25_THREADS, smem, st>>>(bp, flat);
     launched(c);
     CU(cudaGetLastError());
     return OC_OK;
 }
 // multi == false (every token resolves to <= 1 term): the posting-centred persistent kernel; else the slot-scan kernel
-static int launch_tile(oc_ctx *c, const Bm25Params &bp, uint32_t grid, bool multi, bool thr, bool omc, cudaStream_t st) {
+static int launch_tile(oc_ctx *c, const Bm25Params &bp, uint32_t grid, bool multi, bool thr, bool omc, cudaStream_t st,
+                       uint32_t max_tokens) {
     const char *env = getenv("OC_BM25_TILE2");
     if (!multi && !(env && env[0] == '0')) {
+        // one level of descriptors per (tile, query) item, prefetched by the kernel during the previous item
+        const ItemTok *flat = nullptr;
+        const char *fenv = getenv("OC_BM25_FLAT");
+        if (max_tokens <= BM25_FLAT_TOK && !(fenv && fenv[0] == '0')) {
+            const uint64_t n_it = uint64_t(bp.n_tiles) * bp.n_queries * BM25_FLAT_TOK;
+            OCTRY(c->flat_desc.ensure(n_it * sizeof(ItemTok)));
+            bm25_flatten_kernel<<<(unsigned)((n_it + 255) / 256), 256, 0, st>>>(bp.terms, bp.tokens, bp.queries, bp.seg, bp.n_tiles,
+                                                                                bp.n_queries, c->flat_desc.as<ItemTok>());
+            launched(c);
+            CU(cudaGetLastError());
+            flat = c->flat_desc.as<ItemTok>();
+        }
         const size_t smem = bm25_tile2_smem_bytes(thr, omc, bp.cap);
         const int sel = (thr ? 2 : 0) | (omc ? 1 : 0);
         switch (sel) {
-            case 0: return launch_tile2_t<false, false>(c, bp, smem, st);
-            case 1: return launch_tile2_t<false, true>(c, bp, smem, st);
-            case 2: return launch_tile2_t<true, false>(c, bp, smem, st);
-            default: return launch_tile2_t<true, true>(c, bp, smem, st);
+            case 0: return launch_tile2_t<false, false>(c, bp, smem, st, flat);
+            case 1: return launch_tile2_t<false, true>(c, bp, smem, st, flat);
+            case 2: return launch_tile2_t<true, false>(c, bp, smem, st, flat);
+            default: return launch_tile2_t<true, true>(c, bp, smem, st, flat);
         }
     }
     const size_t smem = bm25_smem_bytes(multi, thr, omc, bp.cap);
@@ -1470,6 +1481,7 @@ static int search_impl(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_para
     std::vector<PreDesc> pre_descs;
     std::vector<uint2> pre_items;
     bool any_multi = false, need_df = false, derived_now = false;
+    uint32_t max_tokens = 0;    // tokens of the longest query of the batch
     uint64_t dense_bytes = 0;   // dense contribution arrays of this batch (zeroed before the precompute kernel fills them)
     // sharded: df comes from the replicated per-term table, or — OC_SHARD_COUNT_DF on every rank, e.g. after a
     // commit dropped the table — from counting + all-reduce.  A shard-local list length is never a corpus df.
@@ -1493,6 +1505,7 @@ static int search_impl(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_para
             QueryDesc qd{};
             qd.token_begin = (uint32_t)tokens.size();
             const uint32_t ntok = t1 - t0;
+            max_tokens = std::max(max_tokens, ntok);
             qd.required = thr ? (uint32_t)floorf((float)ntok * p->threshold) : 0;  // token_score.rs:211-218
             qd.flags = thr ? QF_THRESHOLD : 0;
             for (uint32_t t = t0; t < t1; t++) {
@@ -1771,7 +1784,7 @@ static int search_impl(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_para
             OCTRY(c->mbits.ensure(size_t(B) * std::max<uint32_t>(n_tiles, 1) * (BM25_TILE / 32) * 4));
             bp.matched_bits = c->mbits.as<uint32_t>();
         }
-        if (n_tiles) OCTRY(launch_tile(c, bp, n_tiles * B, any_multi, thr, omc_tile, ps));
+        if (n_tiles) OCTRY(launch_tile(c, bp, n_tiles * B, any_multi, thr, omc_tile, ps, max_tokens));
         CU(cudaEventRecord(c->ev[EV_BM1], ps));
         c->timing.bm25_postings = postings_walked;
         if (side) {   // join: the lookups and the fusion need the vector hits (main stream) and the tiles (side stream)
@@ -1888,7 +1901,7 @@ static int search_impl(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_para
         if (redo) {
             CU(cudaMemcpyAsync(min_hint_dev, mins, size_t(B) * 4, cudaMemcpyHostToDevice, c->stream));
             CU(cudaMemsetAsync(c->tau.p, 0, size_t(B) * 8, c->stream));
-            OCTRY(launch_tile(c, bp, n_tiles * B, any_multi, thr, omc_tile, c->stream));
+            OCTRY(launch_tile(c, bp, n_tiles * B, any_multi, thr, omc_tile, c->stream, max_tokens));
             fuse_topk_kernel<<<B, 256, fuse_smem, c->stream>>>(fp);
             launched(c);
             CU(cudaMemcpyAsync(c->h_out.p, dout, out_bytes, cudaMemcpyDeviceToHost, c->stream));
