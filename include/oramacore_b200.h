@@ -281,6 +281,10 @@ int oc_dict_add_terms(oc_dict *d, uint32_t field, const char *const *terms, uint
 int oc_dict_lookup(oc_dict *d, uint32_t field, const char *term, uint32_t *out_id);   /* 0xffffffff = absent */
 uint32_t oc_dict_size(oc_dict *d, uint32_t field);
 int oc_dict_set_stemmer(oc_dict *d, oc_stem_fn fn, void *user);
+/* the Snowball English (Porter2) algorithm as an oc_stem_fn (csrc/stem_en.h; pinned to the algorithm's published
+ * sample vocabulary): oc_dict_set_stemmer(d, oc_stem_english, NULL).  The reference's own stemmer lives in the
+ * un-vendored oramacore_lib::nlp::TextParser; a host that links it passes its own function instead. */
+size_t oc_stem_english(const char *tok, size_t len, char *out, size_t cap, void *user);
 int oc_dict_resolve(oc_dict *d, const oc_resolve_params *p, oc_resolved **out);
 void oc_resolved_arrays(const oc_resolved *r, const uint32_t **q_token_offsets, const uint32_t **token_term_offsets,
                         const uint32_t **term_field, const uint32_t **term_id, const float **term_weight,

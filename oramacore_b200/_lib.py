@@ -27,7 +27,7 @@ EXPORTED_SYMBOLS = [
     "oc_filter_from_ids", "oc_filter_from_bits", "oc_filter_and", "oc_filter_or", "oc_filter_not", "oc_filter_count",
     "oc_filter_read", "oc_filter_destroy", "oc_merge_results",
     "oc_facets_create", "oc_facets_destroy", "oc_facets_add_field", "oc_facets_add_number_field", "oc_search_facets",
-    "oc_dict_create", "oc_dict_destroy", "oc_dict_add_terms", "oc_dict_lookup", "oc_dict_size", "oc_dict_set_stemmer",
+    "oc_dict_create", "oc_dict_destroy", "oc_dict_add_terms", "oc_dict_lookup", "oc_dict_size", "oc_dict_set_stemmer", "oc_stem_english",
     "oc_dict_resolve", "oc_resolved_arrays", "oc_resolved_fill", "oc_resolved_free",
 ]
 
@@ -166,7 +166,9 @@ def lib():
     L.oc_dict_lookup.argtypes = [vp, u32, C.c_char_p, C.POINTER(u32)]
     L.oc_dict_size.argtypes = [vp, u32]
     L.oc_dict_size.restype = u32
-    L.oc_dict_set_stemmer.argtypes = [vp, STEM_FN, vp]
+    L.oc_dict_set_stemmer.argtypes = [vp, vp, vp]
+    L.oc_stem_english.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, vp]
+    L.oc_stem_english.restype = C.c_size_t
     L.oc_dict_resolve.argtypes = [vp, C.POINTER(ResolveParams), C.POINTER(vp)]
     L.oc_resolved_arrays.argtypes = [vp] + [C.POINTER(vp)] * 5 + [C.POINTER(u32)] * 2
     L.oc_resolved_arrays.restype = None

@@ -647,7 +647,7 @@ __global__ void __launch_bounds__(256) bm25_flatten_kernel(const TermDesc *terms
 }
 
 template <bool THRESH, bool OMC>
-__global__ void __launch_bounds__(BM25_THREADS, 4) bm25_tile2_kernel(const Bm25Params p, const ItemTok *flat) {
+__global__ void __launch_bounds__(BM25_THREADS, 4) bm25_tile2_kernel(const Bm25Params p, const ItemTok *flat, unsigned int *work_counter) {
     extern __shared__ __align__(16) uint8_t smem[];
     float *score = reinterpret_cast<float *>(smem);
     float *aux = score + BM25_TILE;                                    // OMC multipliers
@@ -661,7 +661,7 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_tile2_kernel(const Bm25P
     __shared__ const uint2 *t_ptr[BM25_MAX_TOK];
     __shared__ uint32_t t_n[BM25_MAX_TOK], t_bit[BM25_MAX_TOK], t_pre[BM25_MAX_TOK];
     __shared__ float t_w[BM25_MAX_TOK], t_idf[BM25_MAX_TOK];
-    __shared__ uint32_t s_ntok;
+    __shared__ uint32_t s_ntok, s_item_cur, s_item_next;
     __shared__ uint32_t s_mbits[BM25_TILE / 32];
 
     const uint32_t tid = threadIdx.x;
@@ -674,23 +674,29 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_tile2_kernel(const Bm25P
         reinterpret_cast<float4 *>(score)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (THRESH) reinterpret_cast<uint4 *>(mask)[i] = make_uint4(0u, 0u, 0u, 0u);
     }
-    // items are dealt round-robin (tile-major: the queries sharing a tile's hot ranges run back to back through L2);
-    // the next item's descriptors travel from global memory while the current item is processed
+    // items come from a global counter (tile-major: the queries sharing a tile's hot ranges run back to back through
+    // L2; dense and sparse items differ 3x in cost, so the deal is dynamic), fetched TWO ahead: while item k runs, the
+    // id of item k+1 is already known — its descriptors travel from global memory now — and the id of k+2 is requested
     auto store_tok = [&](const ItemTok &it, uint32_t j) {
         t_ptr[j] = reinterpret_cast<const uint2 *>(it.ptr); t_n[j] = it.n; t_pre[j] = it.flags;
         t_w[j] = it.w; t_idf[j] = it.idf; t_bit[j] = it.bit;
     };
-    uint32_t item = blockIdx.x;
-    if (flat && item < n_items && tid < BM25_FLAT_TOK) store_tok(flat[size_t(item) * BM25_FLAT_TOK + tid], tid);
+    if (tid == 0) { s_item_cur = atomicAdd(work_counter, 1u); s_item_next = atomicAdd(work_counter, 1u); s_ntok = BM25_FLAT_TOK; }
     if (tid < 2) { s_cnt2[tid] = 0; s_matched2[tid] = 0; s_maxo2[tid] = f32_ordered(0.f); s_mino2[tid] = f32_ordered(0.f); }
-    if (tid == 0) s_ntok = BM25_FLAT_TOK;
-    for (uint32_t par = 0; item < n_items; item += gridDim.x, par ^= 1u) {
+    __syncthreads();
+    if (flat && s_item_cur < n_items && tid < BM25_FLAT_TOK) store_tok(flat[size_t(s_item_cur) * BM25_FLAT_TOK + tid], tid);
+    for (uint32_t par = 0;; par ^= 1u) {
+        if (want_bits) s_mbits[tid] = 0u;
+        __syncthreads();                                   // previous item retired: accumulators clean, table + counters + ids set
+        const uint32_t item = s_item_cur;
+        if (item >= n_items) break;
+        const uint32_t next = s_item_next;
+        uint32_t next2 = 0;
+        if (tid == 0) next2 = atomicAdd(work_counter, 1u);   // consumed at the end of this item
         const uint32_t tile = item / p.n_queries, q = item % p.n_queries;
         const uint32_t row0 = tile * BM25_TILE;
         uint32_t &s_cnt = s_cnt2[par], &s_matched = s_matched2[par];
         unsigned int &s_maxo = s_maxo2[par], &s_mino = s_mino2[par];
-        if (want_bits) s_mbits[tid] = 0u;
-        __syncthreads();                                   // previous item retired: accumulators clean, table + counters set
         if (tid == 0) { s_cnt2[par ^ 1u] = 0; s_matched2[par ^ 1u] = 0; s_maxo2[par ^ 1u] = f32_ordered(0.f); s_mino2[par ^ 1u] = f32_ordered(0.f); }
         const QueryDesc qd = p.queries[q];                 // (required / slow-path token range; L2-hot, off the critical path)
         if (!flat) {   // a query of this batch has more than BM25_FLAT_TOK tokens: build the table here
@@ -717,7 +723,6 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_tile2_kernel(const Bm25P
         if (!flat || use_ok) __syncthreads();
         const uint32_t ntok = s_ntok;
         // in flight during this item: the next item's descriptors and this query's running threshold
-        const uint32_t next = item + gridDim.x;
         ItemTok nx{};
         if (flat && next < n_items && tid < BM25_FLAT_TOK) nx = flat[size_t(next) * BM25_FLAT_TOK + tid];
         unsigned long long tau = p.tau[q];
@@ -736,7 +741,9 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_tile2_kernel(const Bm25P
                 r[u] = pi < n ? __ldg(pp + pi) : make_uint2(0xffffffffu, 0u);
             }
         };
-        auto next_list = [&](uint32_t j) { while (j < ntok && (t_n[j] == 0 || (t_pre[j] & TD_DENSE))) j++; return j; };
+        uint32_t list_mask = 0;   // tokens that are non-empty posting ranges (ntok <= 32)
+        for (uint32_t j = 0; j < ntok; j++) list_mask |= (t_n[j] != 0 && !(t_pre[j] & TD_DENSE)) ? (1u << j) : 0u;
+        auto next_list = [&](uint32_t j) { const uint32_t m = j < 32 ? (list_mask >> j) : 0u; return m ? j + uint32_t(__ffs(m)) - 1u : ntok; };
         uint32_t jl = next_list(0);
         if (jl < ntok) preload(jl, pre);
         for (uint32_t j = 0; j < ntok; j++) {
@@ -979,6 +986,7 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_tile2_kernel(const Bm25P
             p.tile_min[slot_base] = f32_unordered(s_mino);
         }
         if (flat && tid < BM25_FLAT_TOK) store_tok(nx, tid);   // the next item's table (this item no longer reads it)
+        if (tid == 0) { s_item_cur = next; s_item_next = next2; }
     }
 }
 

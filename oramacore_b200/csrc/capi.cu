@@ -19,6 +19,7 @@
 #include "bm25.cuh"
 #include "comm.h"
 #include "dict.h"
+#include "stem_en.h"
 #include "emb_gemm.cuh"
 #include "emb_scan.cuh"
 #include "fuse.cuh"
@@ -1062,41 +1063,62 @@ extern "C" int oc_str_commit(oc_str *s) {
     for (size_t fi = 0; fi < nf; fi++) {
         const StrField &of = B.fields[fi];
         StrField &f = ns->fields[fi];
-        std::vector<Rec> recs;
-        recs.reserve(of.host_post.size() + pend[fi].size());
+        // the committed postings are already term-major / row-ascending and the row remap is monotone, so only the
+        // PENDING postings are sorted; the next CSR is a per-term linear merge of (surviving old list, new list):
+        // O(P_old + p log p) instead of a sort of everything
         std::vector<uint8_t> replaced(docs.size(), 0);   // a re-inserted document replaces its old postings in this field
         for (auto &pn : pend[fi]) replaced[row_of(pn.doc)] = 1;
-        for (uint32_t t = 0; t < of.n_terms; t++)
-            for (uint64_t i = of.term_offsets[t]; i < of.term_offsets[t + 1]; i++) {
-                const uint32_t nr = remap[of.host_post[i].row];
-                if (nr != 0xffffffffu && !replaced[nr]) recs.push_back({t, nr, of.host_post[i].tf, of.host_post[i].len});
-            }
+        std::vector<Rec> add;
+        add.reserve(pend[fi].size());
         uint32_t max_term = of.n_terms;
         for (auto &pn : pend[fi]) {
             if (pn.term == 0xffffffffu) continue;
-            recs.push_back({pn.term, row_of(pn.doc), pn.tf, pn.len});
+            add.push_back({pn.term, row_of(pn.doc), pn.tf, pn.len});
             max_term = std::max(max_term, pn.term + 1);
         }
-        std::sort(recs.begin(), recs.end(), [](const Rec &a, const Rec &b) { return a.term != b.term ? a.term < b.term : a.row < b.row; });
+        std::sort(add.begin(), add.end(), [](const Rec &a, const Rec &b) { return a.term != b.term ? a.term < b.term : a.row < b.row; });
+        for (size_t i = 1; i < add.size(); i++)
+            if (add[i].term == add[i - 1].term && add[i].row == add[i - 1].row)
+                return abort_commit(fail(OC_ERR_INVALID, "field %zu: term %u listed twice in one insert of a document", fi, add[i].term));
         f.n_terms = max_term;
         f.term_offsets.assign(size_t(max_term) + 1, 0);
-        f.host_post.resize(recs.size());
+        f.host_post.clear();
+        f.host_post.reserve(of.host_post.size() + add.size());
         std::vector<uint16_t> len_of_row(docs.size(), 0);
-        for (size_t i = 0; i < recs.size(); i++) {
-            if (i && recs[i].term == recs[i - 1].term && recs[i].row == recs[i - 1].row)
-                return abort_commit(fail(OC_ERR_INVALID, "field %zu: term %u listed twice in one insert of a document", fi, recs[i].term));
-            f.term_offsets[recs[i].term + 1]++;
-            f.host_post[i].row = recs[i].row; f.host_post[i].tf = recs[i].tf; f.host_post[i].len = recs[i].len;
-            len_of_row[recs[i].row] = recs[i].len;
+        size_t ai = 0;
+        for (uint32_t t = 0; t < max_term; t++) {
+            f.term_offsets[t] = f.host_post.size();
+            uint64_t oi = t < of.n_terms ? of.term_offsets[t] : 0, oe = t < of.n_terms ? of.term_offsets[t + 1] : 0;
+            auto old_next = [&]() -> bool {   // advances oi to the next surviving old posting of this term
+                while (oi < oe) {
+                    const uint32_t nr = remap[of.host_post[oi].row];
+                    if (nr != 0xffffffffu && !replaced[nr]) return true;
+                    oi++;
+                }
+                return false;
+            };
+            for (;;) {
+                const bool ho = old_next(), hn = ai < add.size() && add[ai].term == t;
+                if (!ho && !hn) break;
+                PostingRaw pr;
+                if (ho && (!hn || remap[of.host_post[oi].row] < add[ai].row)) {
+                    pr.row = remap[of.host_post[oi].row]; pr.tf = of.host_post[oi].tf; pr.len = of.host_post[oi].len; oi++;
+                } else {   // (equal rows cannot happen: a row with a pending insert is `replaced`)
+                    pr.row = add[ai].row; pr.tf = add[ai].tf; pr.len = add[ai].len; ai++;
+                }
+                f.host_post.push_back(pr);
+                len_of_row[pr.row] = pr.len;
+            }
         }
-        for (uint32_t t = 0; t < max_term; t++) f.term_offsets[t + 1] += f.term_offsets[t];
+        f.term_offsets[max_term] = f.host_post.size();
+        const size_t n_recs = f.host_post.size();
         f.avg_len = of.avg_len;
         if (!global_avg) {
             double sum = 0; uint64_t cnt = 0;
             for (uint16_t l : len_of_row) if (l) { sum += l; cnt++; }
             if (cnt) f.avg_len = (float)(sum / (double)cnt);   // info().avg_field_length
         }
-        f.n_post = recs.size();
+        f.n_post = n_recs;
         // per-term corpus df of a shard cannot be refreshed locally: sharded searches on this snapshot count
         // df across ranks (OC_SHARD_COUNT_DF) until the caller loads new global tables
     }
@@ -1336,7 +1358,9 @@ static int launch_tile2_t(oc_ctx *c, const Bm25Params &bp, size_t smem, cudaStre
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bm25_tile2_kernel<THRESH, OMC>, BM25_THREADS, smem));
     const uint64_t items = uint64_t(bp.n_tiles) * bp.n_queries;
     const uint32_t grid = (uint32_t)std::min<uint64_t>(items, uint64_t(std::max(per_sm, 1)) * c->prop.multiProcessorCount);
-    bm25_tile2_kernel<THRESH, OMC><<<grid, BM25_THREADS, smem, st>>>(bp, flat);
+    OCTRY(c->work_ctr.ensure(8));
+    CU(cudaMemsetAsync(c->work_ctr.p, 0, 8, st));
+    bm25_tile2_kernel<THRESH, OMC><<<grid, BM25_THREADS, smem, st>>>(bp, flat, c->work_ctr.as<unsigned int>());
     launched(c);
     CU(cudaGetLastError());
     return OC_OK;
@@ -2194,6 +2218,15 @@ extern "C" int oc_dict_lookup(oc_dict *d, uint32_t field, const char *term, uint
     return OC_OK;
 }
 extern "C" uint32_t oc_dict_size(oc_dict *d, uint32_t field) { return (d && field < d->d.n_fields()) ? d->d.size(field) : 0; }
+// Snowball English (Porter2), restated in csrc/stem_en.h: an oc_stem_fn a host without its own parser can install
+extern "C" size_t oc_stem_english(const char *tok, size_t len, char *out, size_t cap, void *user) {
+    (void)user;
+    if (!tok || !out) return 0;
+    const std::string st = ocs::stem_english(std::string(tok, len));
+    if (st.size() > cap) return 0;
+    memcpy(out, st.data(), st.size());
+    return st.size();
+}
 extern "C" int oc_dict_set_stemmer(oc_dict *d, oc_stem_fn fn, void *user) {
     if (!d) return fail(OC_ERR_INVALID, "dict is NULL");
     d->d.set_stemmer(fn, user);

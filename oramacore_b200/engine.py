@@ -455,8 +455,19 @@ class TermDictionary:
                 return 0
             C.memmove(out, b, len(b))
             return len(b)
-        self._stem_cb = _lib.STEM_FN(cb) if fn is not None else _lib.STEM_FN()
-        check(lib().oc_dict_set_stemmer(self._h, self._stem_cb, None))
+        self._stem_cb = _lib.STEM_FN(cb) if fn is not None else None
+        check(lib().oc_dict_set_stemmer(self._h, C.cast(self._stem_cb, C.c_void_p) if fn is not None else None, None))
+
+    def use_english_stemmer(self):
+        """Install the built-in Snowball English (Porter2) stemmer (oc_stem_english)."""
+        check(lib().oc_dict_set_stemmer(self._h, C.cast(lib().oc_stem_english, C.c_void_p), None))
+
+    @staticmethod
+    def stem_english(token: str) -> str:
+        b = token.encode("utf-8")
+        out = C.create_string_buffer(len(b) + 8)
+        n = lib().oc_stem_english(b, len(b), out, len(b) + 8, None)
+        return out.raw[:n].decode("utf-8") if n else token
 
     def resolve_batch(self, texts: Sequence[str], exact: bool = False, tolerance: Optional[int] = None,
                       boost: Optional[Sequence[float]] = None, properties: Optional[Sequence[int]] = None,
