@@ -16,7 +16,11 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "l1tex__m_xbar2l1tex_read_bytes.sum", "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "launch__registers_per_thread",
-        "launch__grid_size", "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_shared_mem"]
+        "launch__grid_size", "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_shared_mem",
+        "lts__t_sector_hit_rate.pct", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio"]
 
 
 def launches(name):
@@ -70,7 +74,7 @@ if __name__ == "__main__":
         launches(n)
     traffic = {}
     for rep, label, wl in (("prof_gemm_h1.ncu-rep", "ncu_emb_gemm_h1", "h1"), ("prof_bm25_h1.ncu-rep", "ncu_bm25_tile_h1", None),
-                           ("prof_scan_v1.ncu-rep", "ncu_emb_scan_v1", "v1")):
+                           ("prof_merge_h1.ncu-rep", "ncu_emb_merge_h1", None), ("prof_scan_v1.ncu-rep", "ncu_emb_scan_v1", "v1")):
         d = full(rep, label)
         if d and wl:
             def gb(s):

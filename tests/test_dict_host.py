@@ -104,3 +104,33 @@ def test_batch_resolution_is_fast():
     assert best["prefix"] < 5e-3 and best["exact"] < 5e-3      # includes the ctypes marshalling of 256 strings
     assert best["tolerance1"] < 2.0
     d.close()
+
+
+SNOWBALL_SAMPLE = """consign consign consigned consign consigning consign consignment consign consist consist consisted consist
+consistency consist consistent consist consistently consist consisting consist consists consist consolation consol
+consolations consol consolatory consolatori console consol consoled consol consoles consol consolidate consolid
+consolidated consolid consolidating consolid consoling consol consolingly consol consols consol consonant conson
+consort consort consorted consort consorting consort conspicuous conspicu conspicuously conspicu conspiracy conspiraci
+conspirator conspir conspirators conspir conspire conspir conspired conspir conspiring conspir constable constabl
+constables constabl constance constanc constancy constanc constant constant knack knack knackeries knackeri knacks knack
+knag knag knave knave knaves knave knavish knavish kneaded knead kneading knead knee knee kneel kneel kneeled kneel
+kneeling kneel kneels kneel knees knee knell knell knelt knelt knew knew knick knick knif knif knife knife knight knight
+knightly knight knights knight knit knit knits knit knitted knit knitting knit knives knive knob knob knobs knob
+knock knock knocked knock knocker knocker knockers knocker knocking knock knocks knock knopp knopp knot knot knots knot
+skies sky dying die cries cri ties tie gas gas this this gaps gap kiwis kiwi hopping hop hoping hope running run happy happi
+generously generous communication communic relational relat conditional condit sensibility sensibl""".split()
+
+
+def test_english_stemmer_reproduces_the_snowball_sample_vocabulary():
+    """oc_stem_english (csrc/stem_en.h) on the sample pairs published with the Snowball English (Porter2) algorithm."""
+    for w, e in zip(SNOWBALL_SAMPLE[0::2], SNOWBALL_SAMPLE[1::2]):
+        assert ob.TermDictionary.stem_english(w) == e, (w, ob.TermDictionary.stem_english(w), e)
+    d = ob.TermDictionary(1)
+    d.add_terms(0, ["consol", "consolations", "knight"])
+    d.use_english_stemmer()
+    q = d.resolve_batch(["Consolations knightly"]).query(0)          # originals + stems, flattened (token_score.rs:196-204)
+    assert q.n_tokens == 4
+    assert [q.term_id[a:b].tolist() for a, b in zip(q.token_term_offsets[:-1], q.token_term_offsets[1:])] == [[1], [0, 1], [], [2]]
+    q = d.resolve_batch(["Consolations knightly"], exact=True).query(0)
+    assert q.n_tokens == 2 and q.term_id.tolist() == [1]
+    d.close()
