@@ -11,7 +11,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "liboramacore_b200.so")
+SO_PATH = os.environ.get("OC_SO_PATH") or os.path.join(_HERE, "liboramacore_b200.so")   # OC_SO_PATH: A/B builds (csrc/Makefile)
 CSRC = os.path.join(_HERE, "csrc")
 
 OC_OK = 0

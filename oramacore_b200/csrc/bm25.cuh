@@ -28,8 +28,14 @@
 
 namespace oc {
 
-constexpr uint32_t BM25_TILE = 8192;           // rows per tile (32 KB of fp32 accumulators: 4 CTAs per SM)
-constexpr uint32_t BM25_THREADS = 256;
+#ifndef OC_BM25_TILE_ROWS
+#define OC_BM25_TILE_ROWS 8192
+#endif
+constexpr uint32_t BM25_TILE = OC_BM25_TILE_ROWS;   // rows per tile (8192: 32 KB of fp32 accumulators, 4 CTAs per SM); multiple of 1024
+#ifndef OC_BM25_THREADS
+#define OC_BM25_THREADS 256
+#endif
+constexpr uint32_t BM25_THREADS = OC_BM25_THREADS;   // threads per scorer CTA (1024 resident threads per SM either way)
 constexpr uint32_t BM25_CHUNK = BM25_THREADS * 4;
 
 struct PostingRaw {    // 8 bytes, as handed over by the host (string_field.rs:162: field_length is u16)
@@ -304,7 +310,7 @@ __global__ void __launch_bounds__(BM25_THREADS) bm25_tile_kernel(const Bm25Param
     if (use_ok)
         for (uint32_t i = tid; i < BM25_TILE / 32; i += BM25_THREADS) okb[i] = p.row_ok_bits[row0 / 32 + i];
     if (tid == 0) { s_cnt = 0; s_matched = 0; s_maxo = f32_ordered(0.f); s_mino = f32_ordered(0.f); s_tau = p.tau[q]; }
-    if (p.matched_bits) s_mbits[tid] = 0u;
+    if (p.matched_bits && tid < BM25_TILE / 32) s_mbits[tid] = 0u;
     __syncthreads();
 
     // ------------------------------------------------ accumulate, token by token, term by term.
@@ -574,7 +580,7 @@ __global__ void __launch_bounds__(BM25_THREADS) bm25_tile_kernel(const Bm25Param
         p.tile_max[slot_base] = f32_unordered(s_maxo);
         p.tile_min[slot_base] = f32_unordered(s_mino);
     }
-    if (p.matched_bits) p.matched_bits[slot_base * (BM25_TILE / 32) + tid] = s_mbits[tid];
+    if (p.matched_bits && tid < BM25_TILE / 32) p.matched_bits[slot_base * (BM25_TILE / 32) + tid] = s_mbits[tid];
 }
 
 
@@ -594,7 +600,7 @@ __global__ void __launch_bounds__(BM25_THREADS) bm25_tile_kernel(const Bm25Param
 // The hybrid lookup of the vector hits' fulltext scores is not done here (bm25_point_kernel), so this kernel
 // does not depend on the vector stage and can overlap the matrix sweep on another stream.
 // =======================================================================================
-constexpr uint32_t BM25_SPARSE_MAX = 2048;     // postings of one (query, tile) item up to which the sparse finish is used
+constexpr uint32_t BM25_SPARSE_MAX = BM25_TILE / 4;     // postings of one (query, tile) item up to which the sparse finish is used
 constexpr uint32_t BM25_MAX_TOK = 32;          // tokens per query (u32 bitmask, token_score.rs:293)
 
 __host__ __device__ inline size_t bm25_tile2_smem_bytes(bool threshold, bool omc, uint32_t cap) {
@@ -647,7 +653,7 @@ __global__ void __launch_bounds__(256) bm25_flatten_kernel(const TermDesc *terms
 }
 
 template <bool THRESH, bool OMC>
-__global__ void __launch_bounds__(BM25_THREADS, 4) bm25_tile2_kernel(const Bm25Params p, const ItemTok *flat, unsigned int *work_counter) {
+__global__ void __launch_bounds__(BM25_THREADS, 1024 / BM25_THREADS) bm25_tile2_kernel(const Bm25Params p, const ItemTok *flat, unsigned int *work_counter) {
     extern __shared__ __align__(16) uint8_t smem[];
     float *score = reinterpret_cast<float *>(smem);
     float *aux = score + BM25_TILE;                                    // OMC multipliers
@@ -686,7 +692,7 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_tile2_kernel(const Bm25P
     __syncthreads();
     if (flat && s_item_cur < n_items && tid < BM25_FLAT_TOK) store_tok(flat[size_t(s_item_cur) * BM25_FLAT_TOK + tid], tid);
     for (uint32_t par = 0;; par ^= 1u) {
-        if (want_bits) s_mbits[tid] = 0u;
+        if (want_bits && tid < BM25_TILE / 32) s_mbits[tid] = 0u;
         __syncthreads();                                   // previous item retired: accumulators clean, table + counters + ids set
         const uint32_t item = s_item_cur;
         if (item >= n_items) break;
@@ -760,14 +766,17 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_tile2_kernel(const Bm25P
                 // float4 slots t, t+256, ... here AND in the finishing scan, so no barrier is needed between
                 // consecutive dense tokens or between the last one and the scan.
                 const float4 *dp = reinterpret_cast<const float4 *>(pp);
+                constexpr uint32_t F4 = BM25_TILE / 4 / BM25_THREADS;        // float4 slots per thread (8 at 8192 rows)
+                static_assert(F4 >= 1 && F4 % (F4 >= 4 ? 4 : F4) == 0, "tile size");
+                constexpr uint32_t FB = F4 >= 4 ? 4 : F4;                    // loads in flight per batch
 #pragma unroll
-                for (uint32_t h = 0; h < 2; h++) {
-                    float4 c4[4];
+                for (uint32_t h = 0; h < F4 / FB; h++) {
+                    float4 c4[FB];
 #pragma unroll
-                    for (uint32_t u = 0; u < 4; u++) c4[u] = __ldg(dp + tid + (h * 4 + u) * BM25_THREADS);
+                    for (uint32_t u = 0; u < FB; u++) c4[u] = __ldg(dp + tid + (h * FB + u) * BM25_THREADS);
 #pragma unroll
-                    for (uint32_t u = 0; u < 4; u++) {
-                        const uint32_t i = tid + (h * 4 + u) * BM25_THREADS;
+                    for (uint32_t u = 0; u < FB; u++) {
+                        const uint32_t i = tid + (h * FB + u) * BM25_THREADS;
                         float4 s4 = reinterpret_cast<float4 *>(score)[i];
                         s4.x = __fadd_rn(s4.x, c4[u].x); s4.y = __fadd_rn(s4.y, c4[u].y);
                         s4.z = __fadd_rn(s4.z, c4[u].z); s4.w = __fadd_rn(s4.w, c4[u].w);
@@ -971,7 +980,7 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_tile2_kernel(const Bm25P
             p.cand_key[slot_base * p.n_keep + i] = key;
             p.cand_ft[slot_base * p.n_keep + i] = ft_from_key ? key_score(key) : score[key_idx(key) - row0];
         }
-        if (want_bits) p.matched_bits[slot_base * (BM25_TILE / 32) + tid] = s_mbits[tid];
+        if (want_bits && tid < BM25_TILE / 32) p.matched_bits[slot_base * (BM25_TILE / 32) + tid] = s_mbits[tid];
         if (!sparse && total != 0) {
             if (!ft_from_key) __syncthreads();             // emit read the scores of other owners' slots
             for (uint32_t i = tid; i < BM25_TILE / 4; i += BM25_THREADS) {   // owner-aligned with the scan: no barrier needed before it
