@@ -580,7 +580,7 @@ static int run_vector_stage(oc_ctx *c, oc_emb *e, const float *q_dev, uint32_t B
     GemmParams gp{};
     gp.n_rows = e->n_rows; gp.n_kblocks = e->stride / (bf16 ? 2 * GEMM_KB : GEMM_KB); gp.inv_norm = inv_norm; gp.n_queries = B;   // cvt: 32-element K-blocks too
     gp.n_qgroups = n_qgroups; gp.ctas_per_group = cpg; gp.cap = cap; gp.lists_per_query = lists;
-    gp.thr = c->g_thr.as<float>(); gp.cand = c->g_cand.as<uint64_t>(); gp.cand_cnt = c->g_cnt.as<uint32_t>();
+    gp.thr = c->g_thr.as<unsigned int>(); gp.eps_v = c->g_eps.as<float>(); gp.limit = limit; gp.cand = c->g_cand.as<uint64_t>(); gp.cand_cnt = c->g_cnt.as<uint32_t>();
     gp.gmax = c->g_max.as<float>();
     gp.ovf = c->g_ovf.as<uint64_t>(); gp.ovf_cnt = c->g_ovfcnt.as<uint32_t>(); gp.ovf_cap = GEMM_OVF_CAP;
     // ring depth of the converting sweep: 5 stages alone on the SM; 4 stages (OC_CVT_STAGES=4) leave ~60 KB of shared
@@ -619,7 +619,7 @@ static int run_vector_stage(oc_ctx *c, oc_emb *e, const float *q_dev, uint32_t B
     tp.eps_const = (bf16 || cvt) ? GEMM_EPS_ACC : GEMM_EPS_TF32;
     tp.rho_x = cvt ? e->rho_x : nullptr;                          // bf16 store: the rows are exact
     tp.rho_q = (bf16 || cvt) ? c->q_rho.as<float>() : nullptr;
-    tp.thr = c->g_thr.as<float>(); tp.eps_v = c->g_eps.as<float>();
+    tp.thr = c->g_thr.as<unsigned int>(); tp.eps_v = c->g_eps.as<float>();
     gemm_thr_kernel<<<B, 256, 0, c->stream>>>(tp);
     launched(c);
     // the sweep

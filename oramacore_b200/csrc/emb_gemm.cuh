@@ -73,7 +73,10 @@ struct GemmParams {
     uint32_t n_qgroups;        // ceil(B / 128)
     uint32_t ctas_per_group;   // gridDim.x / n_qgroups
     uint32_t cap;              // GEMM_LIST_CAP
-    const float *thr;          // [n_queries] FIXED per-query gather thresholds (cos*|q| units), from gemm_thr_kernel
+    unsigned int *thr;         // [n_queries] per-query gather thresholds (cos*|q| units, order-preserving uint): seeded by
+                               // gemm_thr_kernel, raised with atomicMax whenever a list proves a better bound (see gemm_compact)
+    const float *eps_v;        // [n_queries] error bound of the sweep's scores in the same units
+    uint32_t limit;            // top-`limit` wanted
     uint32_t lists_per_query;  // candidate lists per query (NG=1: 2 per row partition, NG=2: 1)
     int max_mode;              // 1 => threshold pass: record each list's best approximate score, push nothing
     uint32_t tile_limit;       // max row tiles per CTA (0 = all); the threshold pass looks at one
@@ -170,8 +173,13 @@ constexpr uint64_t TMA_EVICT_LAST = 0x14F0000000000000ull;
 // ---- the epilogue all sweep variants share: thread = TMEM lane = ONE QUERY --------------------------------
 // Reads n_chunks x 32 accumulator columns (rows rbase ..) of this thread's lane, scales by the rows' inverse
 // norms (inr: shared memory, warp-wide broadcast LDS.128) and gathers every row whose approximate score
-// clears the query's FIXED threshold into the thread's private list; a full list is appended to the query's
-// spill area (one global atomic; rare).  max_mode: only the best score is tracked (threshold pass).
+// clears the query's threshold into the thread's private list.  max_mode: only the best score is tracked
+// (threshold pass).
+// The threshold only has to stay <= a_lim - 2 eps (a_lim = the limit-th best approximate score of the whole
+// store): the seed is a coarse sample bound, so when a list fills up the warp tightens it — the limit-th largest
+// score of ANY `limit` distinct rows bounds a_lim from below — drops what fell under the new threshold and shares
+// it with the other CTAs through an atomicMax'd global (gemm_compact).  Only a list that is still full after
+// that is appended to the query's spill area.
 struct GemmEpi {
     uint32_t cnt = 0;
     float thr = 0.f;
@@ -182,9 +190,71 @@ __device__ __noinline__ void gemm_spill(const GemmParams &p, uint32_t q, const u
     if (base + cnt <= p.ovf_cap)
         for (uint32_t i = 0; i < cnt; i++) p.ovf[size_t(q) * p.ovf_cap + base + i] = mybuf[i];
 }
+// Warp-cooperative tightening of the lists of the lanes in `need` (register-only: 4 keys per lane, cap <= 128).
+// For lane l: kth = limit-th largest score of its list (bitwise search on the order-preserving key, one
+// __reduce_add_sync per bit); thr_l = max(thr_l, kth - 2 eps_l); entries <= thr_l are dropped, the rest compacted
+// in place.  Returns, for the calling lane, its new (cnt, thr).
+__device__ __noinline__ void gemm_compact(const GemmParams &p, uint32_t need, uint32_t q_lane0, uint32_t lists, uint32_t my_list,
+                                          uint32_t lane, GemmEpi &e) {
+    while (need) {
+        const uint32_t l = __ffs(need) - 1;
+        need &= need - 1;
+        const uint32_t lq = q_lane0 + l;
+        uint64_t *lbuf = p.cand + (size_t(lq) * lists + my_list) * p.cap;
+        const uint32_t lcnt = __shfl_sync(0xffffffffu, e.cnt, l);
+        float lthr = __shfl_sync(0xffffffffu, e.thr, l);
+        __syncwarp();                                         // lane l's pushes are visible to the whole warp
+        uint64_t k[4];
+        uint32_t o[4];
+#pragma unroll
+        for (uint32_t u = 0; u < 4; u++) {
+            const uint32_t i = lane + 32 * u;
+            k[u] = i < lcnt ? lbuf[i] : KEY_NONE;
+            o[u] = uint32_t(k[u] >> 32);                      // order-preserving score bits (0 for KEY_NONE)
+        }
+        if (lcnt >= p.limit) {
+            uint32_t prefix = 0;
+            for (int bit = 31; bit >= 0; bit--) {             // largest value v with |{keys >= v}| >= limit
+                const uint32_t cand = prefix | (1u << bit);
+                uint32_t c = 0;
+#pragma unroll
+                for (uint32_t u = 0; u < 4; u++) c += o[u] >= cand ? 1u : 0u;
+                c = __reduce_add_sync(0xffffffffu, c);
+                if (c >= p.limit) prefix = cand;
+            }
+            const float kth = f32_unordered(prefix);
+            const float ev = p.eps_v[lq];
+            const float nthr = kth - 2.0f * ev;               // eps = inf (zero query) -> -inf: no change
+            if (nthr > lthr) lthr = nthr;
+        }
+        // compact: keep the entries above the (possibly raised) threshold
+        uint32_t base = 0;
+        __syncwarp();
+#pragma unroll
+        for (uint32_t u = 0; u < 4; u++) {
+            const bool keep = k[u] != KEY_NONE && key_score(k[u]) > lthr;
+            const uint32_t m = __ballot_sync(0xffffffffu, keep);
+            if (keep) lbuf[base + __popc(m & ((1u << lane) - 1u))] = k[u];
+            base += __popc(m);
+        }
+        __syncwarp();
+        if (lane == l) {
+            e.cnt = base;
+            if (lthr > e.thr) { e.thr = lthr; atomicMax(p.thr + lq, f32_ordered(lthr)); }
+            if (e.cnt + 32 > p.cap) { gemm_spill(p, lq, lbuf, e.cnt); e.cnt = 0; }   // still full: a dense cluster
+        }
+        __syncwarp();
+    }
+}
 __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams &p, uint32_t taddr, const float *inr, uint32_t n_chunks,
-                                                   uint32_t rbase, uint32_t q, uint64_t *__restrict__ mybuf, GemmEpi &e) {
+                                                   uint32_t rbase, uint32_t q, uint32_t lists, uint32_t my_list, bool live,
+                                                   uint64_t *__restrict__ mybuf, GemmEpi &e) {
     const float4 *inr4 = reinterpret_cast<const float4 *>(inr);
+    const uint32_t lane = threadIdx.x & 31;
+    if (live && !p.max_mode) {   // the query's threshold as raised by every CTA so far
+        const unsigned int tg = *reinterpret_cast<volatile unsigned int *>(p.thr + q);
+        e.thr = fmaxf(e.thr, f32_unordered(tg));
+    }
     for (uint32_t ch = 0; ch < n_chunks; ch++) {
         uint32_t d[32];
         tmem_ld32(taddr + ch * 32, d);
@@ -206,12 +276,13 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams &p, uint32_t
         uint32_t mask = 0;
 #pragma unroll
         for (uint32_t j = 0; j < 32; j++) mask |= (v[j] > e.thr ? 1u : 0u) << j;   // NaN fails
-        if (mask) {   // rare: a few hundred rows per query and sweep clear the threshold
+        if (mask) {   // rare once the threshold has tightened
 #pragma unroll
             for (uint32_t j = 0; j < 32; j++)
                 if ((mask >> j) & 1u) { mybuf[e.cnt] = make_key(v[j], rbase + ch * 32 + j); e.cnt++; }
-            if (e.cnt + 32 > p.cap) { gemm_spill(p, q, mybuf, e.cnt); e.cnt = 0; }
         }
+        const uint32_t need = __ballot_sync(0xffffffffu, e.cnt + 32 > p.cap);
+        if (need) gemm_compact(p, need, q - lane, lists, my_list, lane, e);
     }
 }
 
@@ -332,7 +403,7 @@ emb_gemm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const uint32_t my_list = NG == 1 ? c * 2 + sel : c;
         uint64_t *__restrict__ mybuf = p.cand + (size_t(q) * lists + my_list) * p.cap;
         GemmEpi e;
-        e.thr = live ? p.thr[q] : INFINITY;                // fixed for the whole sweep (gemm_thr_kernel)
+        e.thr = live ? -INFINITY : INFINITY;               // refreshed from the query's global threshold before every tile
         e.best = -INFINITY;                                // max_mode: best approximate score seen by this list
         const uint32_t ncols = NG == 1 ? 128u : 256u, col0 = NG == 1 ? sel * 128u : 0u;
         for (uint64_t it = 0; it < my_tiles; it++) {
@@ -348,7 +419,7 @@ emb_gemm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             mbar_wait(&tfull[slot], ph);
             tc_fence_after();
             gemm_epilogue_tile(p, tmem_base + ((quad * 32u) << 16) + slot * GEMM_N + col0, inr + col0, ncols / 32,
-                               uint32_t(row0) + col0, q, mybuf, e);
+                               uint32_t(row0) + col0, q, lists, my_list, live, mybuf, e);
             tc_fence_before();
             mbar_arrive(&tempty[slot]);
         }
@@ -544,7 +615,7 @@ emb_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         uint64_t *__restrict__ mybuf = p.cand + (size_t(q) * lists + my_list) * p.cap;
         const uint32_t tempty_remote = mapa_shared(smem_u32(&tempty[sel]), 0);
         GemmEpi e;
-        e.thr = live ? p.thr[q] : INFINITY;
+        e.thr = live ? -INFINITY : INFINITY;
         e.best = -INFINITY;
         for (uint64_t it = 0; it < my_tiles; it++) {
             const uint32_t ph = uint32_t(it & 1);
@@ -559,7 +630,7 @@ emb_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             mbar_wait(&tfull[sel], ph);
             tc_fence_after();
             gemm_epilogue_tile(p, tmem_base + ((quad * 32u) << 16) + sel * 256, inr + sel * 256, 8, uint32_t(row0) + sel * 256, q,
-                               mybuf, e);
+                               lists, my_list, live, mybuf, e);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(tempty_remote);   // one arrival per warp on the leader's barrier
@@ -760,7 +831,7 @@ emb_gemm_cvt_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         uint64_t *__restrict__ mybuf = p.cand + (size_t(q) * lists + my_list) * p.cap;
         const uint32_t tempty_remote = mapa_shared(smem_u32(&tempty[sel]), 0);
         GemmEpi e;
-        e.thr = live ? p.thr[q] : INFINITY;
+        e.thr = live ? -INFINITY : INFINITY;
         e.best = -INFINITY;
         for (uint64_t it = 0; it < my_tiles; it++) {
             const uint32_t ph = uint32_t(it & 1);
@@ -775,7 +846,7 @@ emb_gemm_cvt_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
             mbar_wait(&tfull[sel], ph);
             tc_fence_after();
             gemm_epilogue_tile(p, tmem_base + ((quad * 32u) << 16) + sel * 256, inr + sel * 256, 8, uint32_t(row0) + sel * 256, q,
-                               mybuf, e);
+                               lists, my_list, live, mybuf, e);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(tempty_remote);   // one arrival per warp on the leader's barrier
@@ -979,7 +1050,8 @@ struct GemmThrParams {
     float eps_const;
     const float *rho_x;       // device scalar: max relative bf16 residual norm over the store's rows, or NULL
     const float *rho_q;       // [B] relative bf16 residual norm of each query, or NULL
-    float *thr, *eps_v;       // [B] outputs
+    unsigned int *thr;        // [B] out: seed threshold, order-preserving uint (atomicMax'ed by the sweep)
+    float *eps_v;             // [B] out
 };
 __global__ void __launch_bounds__(256) gemm_thr_kernel(const GemmThrParams p) {
     __shared__ uint64_t keys[512];
@@ -998,7 +1070,7 @@ __global__ void __launch_bounds__(256) gemm_thr_kernel(const GemmThrParams p) {
         const float ev = iqn > 0.f ? __fdiv_ru(eps_cos, iqn) : INFINITY;
         float thr = -INFINITY;
         if (n >= p.limit && keys[p.limit - 1] != KEY_NONE && ev < INFINITY) thr = key_score(keys[p.limit - 1]) - 2.0f * ev;
-        p.thr[q] = thr;
+        p.thr[q] = f32_ordered(thr);
         p.eps_v[q] = ev;
     }
 }
