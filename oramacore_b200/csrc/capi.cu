@@ -518,7 +518,8 @@ static int run_vector_stage(oc_ctx *c, oc_emb *e, const float *q_dev, uint32_t B
     // at least `limit` row groups of <= 256 rows with data (its seeds are the limit-th largest group maximum; with
     // fewer live groups the threshold degenerates to "gather everything" and the query falls back to the exact sweep)
     const bool use_gemm = !g_disable_gemm && B >= 8 && limit <= GEMM_MAX_LIMIT && e->n_rows >= std::max<uint64_t>(4096, uint64_t(limit) * 256);
-    if (use_gemm) CU(cudaMemsetAsync(c->q_pad.p, 0, size_t(Bpad) * e->stride * 4, c->stream));
+    // (the prep kernel writes rows [0, B) whole, zero padded: only the rows of a partial last query group need clearing)
+    if (use_gemm && Bpad != B) CU(cudaMemsetAsync(c->q_pad.as<float>() + size_t(B) * e->stride, 0, size_t(Bpad - B) * e->stride * 4, c->stream));
     emb_prep_queries_kernel<<<(B + 7) / 8, 256, 0, c->stream>>>(q_dev, e->dim, e->stride, B, c->q_pad.as<float>(), c->q_inv.as<float>(),
                                                                 c->q_rho.as<float>());
     launched(c);
@@ -576,7 +577,6 @@ static int run_vector_stage(oc_ctx *c, oc_emb *e, const float *q_dev, uint32_t B
     OCTRY(c->g_resc.ensure(size_t(B) * 4));
     OCTRY(c->g_flag.ensure(B));
     OCTRY(c->g_max.ensure(size_t(Bpad2) * lists * 4));
-    CU(cudaMemsetAsync(c->g_ovfcnt.p, 0, size_t(B) * 4, c->stream));
     GemmParams gp{};
     gp.n_rows = e->n_rows; gp.n_kblocks = e->stride / (bf16 ? 2 * GEMM_KB : GEMM_KB); gp.inv_norm = inv_norm; gp.n_queries = B;   // cvt: 32-element K-blocks too
     gp.n_qgroups = n_qgroups; gp.ctas_per_group = cpg; gp.cap = cap; gp.lists_per_query = lists;
@@ -619,7 +619,7 @@ static int run_vector_stage(oc_ctx *c, oc_emb *e, const float *q_dev, uint32_t B
     tp.eps_const = (bf16 || cvt) ? GEMM_EPS_ACC : GEMM_EPS_TF32;
     tp.rho_x = cvt ? e->rho_x : nullptr;                          // bf16 store: the rows are exact
     tp.rho_q = (bf16 || cvt) ? c->q_rho.as<float>() : nullptr;
-    tp.thr = c->g_thr.as<unsigned int>(); tp.eps_v = c->g_eps.as<float>();
+    tp.thr = c->g_thr.as<unsigned int>(); tp.eps_v = c->g_eps.as<float>(); tp.ovf_cnt = c->g_ovfcnt.as<uint32_t>();
     gemm_thr_kernel<<<B, 256, 0, c->stream>>>(tp);
     launched(c);
     // the sweep
@@ -1351,23 +1351,21 @@ static int launch_tile_t(oc_ctx *c, const Bm25Params &bp, uint32_t grid, size_t 
     return OC_OK;
 }
 template <bool THRESH, bool OMC>
-static int launch_tile2_t(oc_ctx *c, const Bm25Params &bp, size_t smem, cudaStream_t st, const ItemTok *flat) {
+static int launch_tile2_t(oc_ctx *c, const Bm25Params &bp, size_t smem, cudaStream_t st, const ItemTok *flat, unsigned int *counter) {
     if (smem_cfg_needed(c->device, (const void *)bm25_tile2_kernel<THRESH, OMC>, smem))
         CU(cudaFuncSetAttribute(bm25_tile2_kernel<THRESH, OMC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bm25_tile2_kernel<THRESH, OMC>, BM25_THREADS, smem));
     const uint64_t items = uint64_t(bp.n_tiles) * bp.n_queries;
     const uint32_t grid = (uint32_t)std::min<uint64_t>(items, uint64_t(std::max(per_sm, 1)) * c->prop.multiProcessorCount);
-    OCTRY(c->work_ctr.ensure(8));
-    CU(cudaMemsetAsync(c->work_ctr.p, 0, 8, st));
-    bm25_tile2_kernel<THRESH, OMC><<<grid, BM25_THREADS, smem, st>>>(bp, flat, c->work_ctr.as<unsigned int>());
+    bm25_tile2_kernel<THRESH, OMC><<<grid, BM25_THREADS, smem, st>>>(bp, flat, counter);
     launched(c);
     CU(cudaGetLastError());
     return OC_OK;
 }
 // multi == false (every token resolves to <= 1 term): the posting-centred persistent kernel; else the slot-scan kernel
 static int launch_tile(oc_ctx *c, const Bm25Params &bp, uint32_t grid, bool multi, bool thr, bool omc, cudaStream_t st,
-                       uint32_t max_tokens) {
+                       uint32_t max_tokens, unsigned int *counter /* zeroed by the caller */) {
     const char *env = getenv("OC_BM25_TILE2");
     if (!multi && !(env && env[0] == '0')) {
         // one level of descriptors per (tile, query) item, prefetched by the kernel during the previous item
@@ -1385,10 +1383,10 @@ static int launch_tile(oc_ctx *c, const Bm25Params &bp, uint32_t grid, bool mult
         const size_t smem = bm25_tile2_smem_bytes(thr, omc, bp.cap);
         const int sel = (thr ? 2 : 0) | (omc ? 1 : 0);
         switch (sel) {
-            case 0: return launch_tile2_t<false, false>(c, bp, smem, st, flat);
-            case 1: return launch_tile2_t<false, true>(c, bp, smem, st, flat);
-            case 2: return launch_tile2_t<true, false>(c, bp, smem, st, flat);
-            default: return launch_tile2_t<true, true>(c, bp, smem, st, flat);
+            case 0: return launch_tile2_t<false, false>(c, bp, smem, st, flat, counter);
+            case 1: return launch_tile2_t<false, true>(c, bp, smem, st, flat, counter);
+            case 2: return launch_tile2_t<true, false>(c, bp, smem, st, flat, counter);
+            default: return launch_tile2_t<true, true>(c, bp, smem, st, flat, counter);
         }
     }
     const size_t smem = bm25_smem_bytes(multi, thr, omc, bp.cap);
@@ -1703,6 +1701,7 @@ static int search_impl(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_para
     const uint32_t cap = n_keep <= 32 ? std::max<uint32_t>(n_keep + BM25_CHUNK, BM25_SPARSE_MAX) : next_pow2(std::max<uint32_t>(n_keep + BM25_CHUNK, BM25_SPARSE_MAX));
     Bm25Params bp{};
     float *min_hint_dev = nullptr;
+    unsigned int *tile_counter = nullptr;
     const size_t o_doc = 0, o_sc = size_t(B) * p->limit * 8, o_n = o_sc + size_t(B) * p->limit * 4;
     const size_t o_cnt = (o_n + size_t(B) * 4 + 7) & ~size_t(7), o_min = o_cnt + size_t(B) * 8;
     const size_t o_gflag = o_min + size_t(B) * 4;                       // sharded: OR over the ranks of the per-query overflow flags
@@ -1772,16 +1771,16 @@ static int search_impl(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_para
             CU(cudaMemcpyAsync(din + o_tokens, tokens.data(), ntok * sizeof(TokenDesc), cudaMemcpyHostToDevice, c->stream));
         }
         const size_t slots = size_t(B) * std::max<uint32_t>(n_tiles, 1);
-        OCTRY(c->tau.ensure(size_t(B) * 8));
+        OCTRY(c->tau.ensure(size_t(B) * 16 + 16));   // [tau B x 8][min_hint B x 8][work counter]: one memset
         OCTRY(c->cand_key.ensure(slots * n_keep * 8));
         OCTRY(c->cand_ft.ensure(slots * n_keep * 4));
         OCTRY(c->cand_cnt.ensure(slots * 4));
         OCTRY(c->tile_cnt.ensure(slots * 4));
         OCTRY(c->tile_max.ensure(slots * 4));
         OCTRY(c->tile_min.ensure(slots * 4));
-        OCTRY(c->min_hint.ensure(size_t(B) * 8));
-        min_hint_dev = c->min_hint.as<float>();
-        CU(cudaMemsetAsync(c->min_hint.p, 0, size_t(B) * 8, ps));
+        min_hint_dev = reinterpret_cast<float *>(c->tau.as<uint8_t>() + size_t(B) * 8);
+        tile_counter = reinterpret_cast<unsigned int *>(c->tau.as<uint8_t>() + size_t(B) * 16);
+        CU(cudaMemsetAsync(c->tau.p, 0, size_t(B) * 16 + 16, ps));
         bp.terms = reinterpret_cast<const TermDesc *>(din + o_terms);
         bp.tokens = reinterpret_cast<const TokenDesc *>(din + o_tokens);
         bp.queries = reinterpret_cast<const QueryDesc *>(din + o_queries);
@@ -1803,12 +1802,11 @@ static int search_impl(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_para
         bp.cand_cnt = c->cand_cnt.as<uint32_t>(); bp.tile_count = c->tile_cnt.as<uint32_t>();
         bp.tile_max = c->tile_max.as<float>(); bp.tile_min = c->tile_min.as<float>();
         bp.tile_first = 0;
-        CU(cudaMemsetAsync(c->tau.p, 0, size_t(B) * 8, ps));
         if (fj) {   // facets: the tile kernels also emit the bitmap of matched rows (every (query, tile) item writes its 256 words)
             OCTRY(c->mbits.ensure(size_t(B) * std::max<uint32_t>(n_tiles, 1) * (BM25_TILE / 32) * 4));
             bp.matched_bits = c->mbits.as<uint32_t>();
         }
-        if (n_tiles) OCTRY(launch_tile(c, bp, n_tiles * B, any_multi, thr, omc_tile, ps, max_tokens));
+        if (n_tiles) OCTRY(launch_tile(c, bp, n_tiles * B, any_multi, thr, omc_tile, ps, max_tokens, tile_counter));
         CU(cudaEventRecord(c->ev[EV_BM1], ps));
         c->timing.bm25_postings = postings_walked;
         if (side) {   // join: the lookups and the fusion need the vector hits (main stream) and the tiles (side stream)
@@ -1925,7 +1923,8 @@ static int search_impl(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_para
         if (redo) {
             CU(cudaMemcpyAsync(min_hint_dev, mins, size_t(B) * 4, cudaMemcpyHostToDevice, c->stream));
             CU(cudaMemsetAsync(c->tau.p, 0, size_t(B) * 8, c->stream));
-            OCTRY(launch_tile(c, bp, n_tiles * B, any_multi, thr, omc_tile, c->stream, max_tokens));
+            CU(cudaMemsetAsync(tile_counter, 0, 8, c->stream));
+            OCTRY(launch_tile(c, bp, n_tiles * B, any_multi, thr, omc_tile, c->stream, max_tokens, tile_counter));
             fuse_topk_kernel<<<B, 256, fuse_smem, c->stream>>>(fp);
             launched(c);
             CU(cudaMemcpyAsync(c->h_out.p, dout, out_bytes, cudaMemcpyDeviceToHost, c->stream));

@@ -247,14 +247,11 @@ __device__ __noinline__ void gemm_compact(const GemmParams &p, uint32_t need, ui
     }
 }
 __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams &p, uint32_t taddr, const float *inr, uint32_t n_chunks,
-                                                   uint32_t rbase, uint32_t q, uint32_t lists, uint32_t my_list, bool live,
-                                                   uint64_t *__restrict__ mybuf, GemmEpi &e) {
+                                                   uint32_t rbase, uint32_t q, uint32_t lists, uint32_t my_list,
+                                                   unsigned int thr_global, uint64_t *__restrict__ mybuf, GemmEpi &e) {
     const float4 *inr4 = reinterpret_cast<const float4 *>(inr);
     const uint32_t lane = threadIdx.x & 31;
-    if (live && !p.max_mode) {   // the query's threshold as raised by every CTA so far
-        const unsigned int tg = *reinterpret_cast<volatile unsigned int *>(p.thr + q);
-        e.thr = fmaxf(e.thr, f32_unordered(tg));
-    }
+    if (thr_global) e.thr = fmaxf(e.thr, f32_unordered(thr_global));   // the query's threshold as raised by every CTA so far
     for (uint32_t ch = 0; ch < n_chunks; ch++) {
         uint32_t d[32];
         tmem_ld32(taddr + ch * 32, d);
@@ -415,11 +412,13 @@ emb_gemm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 const uint64_t r = row0 + et;
                 inr[et] = r < p.n_rows ? __ldg(p.inv_norm + r) : __int_as_float(0x7fc00000);
             }
+            // requested before the waits below, consumed after them: the L2 round trip hides behind the MMAs of this tile
+            const unsigned int tg = (live && !p.max_mode) ? *reinterpret_cast<volatile unsigned int *>(p.thr + q) : 0u;
             named_bar_sync(1, GEMM_EPI_WARPS * 32);
             mbar_wait(&tfull[slot], ph);
             tc_fence_after();
             gemm_epilogue_tile(p, tmem_base + ((quad * 32u) << 16) + slot * GEMM_N + col0, inr + col0, ncols / 32,
-                               uint32_t(row0) + col0, q, lists, my_list, live, mybuf, e);
+                               uint32_t(row0) + col0, q, lists, my_list, tg, mybuf, e);
             tc_fence_before();
             mbar_arrive(&tempty[slot]);
         }
@@ -626,11 +625,12 @@ emb_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                 const uint64_t r = row0 + et + h * 256;
                 inr[et + h * 256] = r < p.n_rows ? __ldg(p.inv_norm + r) : __int_as_float(0x7fc00000);
             }
+            const unsigned int tg = (live && !p.max_mode) ? *reinterpret_cast<volatile unsigned int *>(p.thr + q) : 0u;
             named_bar_sync(1, GEMM_EPI_WARPS * 32);
             mbar_wait(&tfull[sel], ph);
             tc_fence_after();
             gemm_epilogue_tile(p, tmem_base + ((quad * 32u) << 16) + sel * 256, inr + sel * 256, 8, uint32_t(row0) + sel * 256, q,
-                               lists, my_list, live, mybuf, e);
+                               lists, my_list, tg, mybuf, e);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(tempty_remote);   // one arrival per warp on the leader's barrier
@@ -842,11 +842,12 @@ emb_gemm_cvt_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                 const uint64_t r = row0 + et + h * 256;
                 inr[et + h * 256] = r < p.n_rows ? __ldg(p.inv_norm + r) : __int_as_float(0x7fc00000);
             }
+            const unsigned int tg = (live && !p.max_mode) ? *reinterpret_cast<volatile unsigned int *>(p.thr + q) : 0u;
             named_bar_sync(1, GEMM_EPI_WARPS * 32);
             mbar_wait(&tfull[sel], ph);
             tc_fence_after();
             gemm_epilogue_tile(p, tmem_base + ((quad * 32u) << 16) + sel * 256, inr + sel * 256, 8, uint32_t(row0) + sel * 256, q,
-                               lists, my_list, live, mybuf, e);
+                               lists, my_list, tg, mybuf, e);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(tempty_remote);   // one arrival per warp on the leader's barrier
@@ -1052,6 +1053,7 @@ struct GemmThrParams {
     const float *rho_q;       // [B] relative bf16 residual norm of each query, or NULL
     unsigned int *thr;        // [B] out: seed threshold, order-preserving uint (atomicMax'ed by the sweep)
     float *eps_v;             // [B] out
+    uint32_t *ovf_cnt;        // [B] reset here: the spill cursors of the sweep that follows
 };
 __global__ void __launch_bounds__(256) gemm_thr_kernel(const GemmThrParams p) {
     __shared__ uint64_t keys[512];
@@ -1072,6 +1074,7 @@ __global__ void __launch_bounds__(256) gemm_thr_kernel(const GemmThrParams p) {
         if (n >= p.limit && keys[p.limit - 1] != KEY_NONE && ev < INFINITY) thr = key_score(keys[p.limit - 1]) - 2.0f * ev;
         p.thr[q] = f32_ordered(thr);
         p.eps_v[q] = ev;
+        p.ovf_cnt[q] = 0u;
     }
 }
 
