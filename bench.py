@@ -314,6 +314,12 @@ def main():
         uid = [ob.Context.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         ctx.comm_init(world, rank, uid[0])
+        if os.environ.get("OC_SHARD_P2P", "1") != "0":   # direct NVLink exchange of the shard records (else ncclAllGather)
+            def _ag(blob):
+                out = [None] * world
+                dist.all_gather_object(out, blob)
+                return out
+            ctx.comm_enable_p2p(_ag)
 
     check = not args.no_cpu_baseline
     wl = make_workload(w, n_docs, batch, rank, world, keep_all=(rank == 0 and check))

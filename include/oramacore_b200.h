@@ -74,6 +74,15 @@ int oc_device_info(oc_ctx *ctx, int *sm_count, size_t *hbm_bytes, char *name, si
 #define OC_COMM_ID_BYTES 128
 int oc_comm_unique_id(uint8_t out_id[OC_COMM_ID_BYTES]);
 int oc_comm_init(oc_ctx *ctx, int world_size, int rank, const uint8_t id[OC_COMM_ID_BYTES]);
+/* Optional: direct NVLink exchange of the per-shard top-k records instead of the NCCL all-gather.  After
+ * oc_comm_init every rank exports the CUDA-IPC handle of its receive window, the host runtime all-gathers the
+ * blobs (world x OC_P2P_HANDLE_BYTES, rank order) and every rank imports them.  From then on the pack kernel of a
+ * sharded oc_search stores each query's record straight into all ranks' windows (peer memory over NVLink /
+ * NVSwitch) and bumps a per-query arrival counter; the merge kernel waits on the counters: no library collective
+ * on the data path.  Batches whose records exceed the 1 MiB window fall back to ncclAllGather. */
+#define OC_P2P_HANDLE_BYTES 128
+int oc_comm_p2p_export(oc_ctx *ctx, uint8_t out_handle[OC_P2P_HANDLE_BYTES]);
+int oc_comm_p2p_import(oc_ctx *ctx, const uint8_t *handles);
 
 /* ---- embedding store ------------------------------------------------------------------
  * EmbeddingFieldStorage::new (embedding_field.rs:64-78): metric fixed = cosine;
@@ -281,8 +290,8 @@ int oc_dict_add_terms(oc_dict *d, uint32_t field, const char *const *terms, uint
 int oc_dict_lookup(oc_dict *d, uint32_t field, const char *term, uint32_t *out_id);   /* 0xffffffff = absent */
 uint32_t oc_dict_size(oc_dict *d, uint32_t field);
 int oc_dict_set_stemmer(oc_dict *d, oc_stem_fn fn, void *user);
-/* the Snowball English (Porter2) algorithm as an oc_stem_fn (csrc/stem_en.h; pinned to the algorithm's published
- * sample vocabulary): oc_dict_set_stemmer(d, oc_stem_english, NULL).  The reference's own stemmer lives in the
+/* the Snowball English (Porter2) algorithm with the oc_stem_fn signature, from csrc/stem_en.h; pinned to its published
+ * sample vocabulary: oc_dict_set_stemmer(d, oc_stem_english, NULL).  The reference's own stemmer lives in the
  * un-vendored oramacore_lib::nlp::TextParser; a host that links it passes its own function instead. */
 size_t oc_stem_english(const char *tok, size_t len, char *out, size_t cap, void *user);
 int oc_dict_resolve(oc_dict *d, const oc_resolve_params *p, oc_resolved **out);

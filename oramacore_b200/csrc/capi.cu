@@ -128,6 +128,11 @@ static bool is_pinned_host(const void *p) {
 
 enum { EV_START, EV_H2D, EV_DEV, EV_D2H, EV_SCAN0, EV_SCAN1, EV_BM0, EV_BM1, EV_FUSE0, EV_FUSE1, EV_COMM0, EV_COMM1, EV_SWEEP0, EV_SWEEP1, EV_RR0, EV_RR1, EV_N };
 
+constexpr size_t P2P_WIN_BYTES = size_t(1) << 20;   // per (parity, source rank): a batch's records must fit (256 queries x 520 B = 133 KB)
+constexpr uint32_t P2P_MAX_Q = 4096;
+constexpr size_t P2P_FLAG_BYTES = size_t(2) * P2P_MAX_Q * 4;
+constexpr uint32_t P2P_MAX_WORLD = 16;
+
 struct oc_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -152,6 +157,14 @@ struct oc_ctx {
 
     HostBuf h_in, h_out, h_in0;   // h_in0 / in_blob0: query vectors + filter, uploaded before the descriptors
     OcComm comm;
+    // direct NVLink exchange of the shard records (oc_comm_p2p_*): one IPC-shared window per rank —
+    // [2 parities][P2P_MAX_Q] arrival counters, then [2 parities][world source ranks][P2P_WIN_BYTES] records
+    struct P2P {
+        bool ready = false;
+        uint8_t *local = nullptr;
+        uint8_t *peer[16] = {};      // peer[rank] == local
+        uint64_t seq = 0;            // exchanges done (all ranks run the same batches): parity = seq & 1
+    } p2p;
 };
 
 static inline void launched(oc_ctx *c, bool scan = false) {
@@ -187,6 +200,8 @@ extern "C" void oc_shutdown(oc_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    for (int r = 0; r < 16; r++) if (c->p2p.ready && c->p2p.peer[r] && c->p2p.peer[r] != c->p2p.local) cudaIpcCloseMemHandle(c->p2p.peer[r]);
+    if (c->p2p.local) cudaFree(c->p2p.local);
     c->comm.destroy();
     DevBuf *bufs[] = {&c->in_blob, &c->q_pad, &c->q_inv, &c->eff_norm, &c->filter_dev, &c->scan_cand, &c->v_doc,
                       &c->v_score, &c->v_row, &c->v_cnt, &c->v_srow, &c->v_ft, &c->v_present, &c->v_raw, &c->seg, &c->df_dev,
@@ -236,6 +251,46 @@ extern "C" int oc_comm_init(oc_ctx *c, int world, int rank, const uint8_t id[OC_
     CU(cudaSetDevice(c->device));
     std::string err;
     if (!c->comm.init(world, rank, id, &err)) return fail(OC_ERR_COMM, "%s", err.c_str());
+    return OC_OK;
+}
+
+// Direct NVLink exchange: rank r exports the IPC handle of its window, the host runtime all-gathers the blobs (like
+// the NCCL unique id) and every rank maps all peers' windows.  Afterwards the sharded oc_search stores each query's
+// shard record straight into every rank's window from the pack kernel and the merge kernel waits on arrival
+// counters — no library collective on the data path (ncclAllGather stays the fallback for batches larger than a window).
+extern "C" int oc_comm_p2p_export(oc_ctx *c, uint8_t out[OC_P2P_HANDLE_BYTES]) {
+    if (!c || !out) return fail(OC_ERR_INVALID, "NULL argument");
+    if (c->comm.world < 2 || c->comm.world > (int)P2P_MAX_WORLD) return fail(OC_ERR_INVALID, "oc_comm_init first (2..%u ranks)", P2P_MAX_WORLD);
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    if (!c->p2p.local) {
+        const size_t bytes = P2P_FLAG_BYTES + size_t(2) * c->comm.world * P2P_WIN_BYTES;
+        CU(cudaMalloc(&c->p2p.local, bytes));
+        CU(cudaMemset(c->p2p.local, 0, bytes));
+    }
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, c->p2p.local));
+    static_assert(sizeof(h) <= OC_P2P_HANDLE_BYTES, "handle blob");
+    memset(out, 0, OC_P2P_HANDLE_BYTES);
+    memcpy(out, &h, sizeof(h));
+    return OC_OK;
+}
+extern "C" int oc_comm_p2p_import(oc_ctx *c, const uint8_t *handles) {
+    if (!c || !handles) return fail(OC_ERR_INVALID, "NULL argument");
+    if (!c->p2p.local) return fail(OC_ERR_INVALID, "oc_comm_p2p_export first");
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    for (int r = 0; r < c->comm.world; r++) {
+        if (r == c->comm.rank) { c->p2p.peer[r] = c->p2p.local; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + size_t(r) * OC_P2P_HANDLE_BYTES, sizeof(h));
+        void *ptr = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) return fail(OC_ERR_COMM, "cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e));
+        c->p2p.peer[r] = static_cast<uint8_t *>(ptr);
+    }
+    c->p2p.seq = 0;
+    c->p2p.ready = true;
     return OC_OK;
 }
 

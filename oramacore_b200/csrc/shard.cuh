@@ -46,6 +46,13 @@ struct ShardPackParams {
     uint32_t n_rows_str, n_rows_emb;
     const uint8_t *unproven;   // [q] local overflow flags of the tensor-core scan, or NULL
     uint8_t *out;              // [q] records
+    // direct NVLink exchange (oc_comm_p2p_*): after packing, the CTA stores its query's record into the receive
+    // window of EVERY rank (peer memory mapped through CUDA IPC) and bumps that rank's arrival counter of the query
+    uint32_t p2p_world;        // 0 = off (the records travel by ncclAllGather)
+    uint32_t p2p_rank;
+    uint8_t *p2p_win[16];      // base of each rank's window for this batch's parity
+    uint32_t *p2p_flag[16];    // [q] arrival counters of each rank for this parity
+    uint64_t p2p_rank_stride;  // bytes between the slots of two source ranks inside a window
 };
 
 __global__ void __launch_bounds__(256) shard_pack_kernel(const ShardPackParams pp) {
@@ -154,10 +161,28 @@ __global__ void __launch_bounds__(256) shard_pack_kernel(const ShardPackParams p
         hdr->n_ft = got; hdr->n_v = vc; hdr->n_rows_str = pp.n_rows_str; hdr->n_rows_emb = pp.n_rows_emb;
         hdr->unproven = pp.unproven ? pp.unproven[q] : 0u; hdr->pad = 0u;
     }
+    if (pp.p2p_world) {
+        // the record is complete in local memory: push it to every rank's window over NVLink (8-byte stores,
+        // coalesced), make it visible system-wide, then signal one arrival per destination
+        __threadfence();
+        __syncthreads();
+        const uint64_t *src = reinterpret_cast<const uint64_t *>(pp.out + size_t(q) * rb);
+        const uint32_t n8 = uint32_t(rb / 8);
+        for (uint32_t r = 0; r < pp.p2p_world; r++) {
+            uint64_t *dst = reinterpret_cast<uint64_t *>(pp.p2p_win[r] + size_t(pp.p2p_rank) * pp.p2p_rank_stride + size_t(q) * rb);
+            for (uint32_t i = tid; i < n8; i += blockDim.x) dst[i] = src[i];
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (tid < pp.p2p_world) atomicAdd_system(pp.p2p_flag[tid] + q, 1u);
+    }
 }
 
 struct ShardFuseParams {
     const uint8_t *recv;      // [world][B] records
+    uint64_t rank_stride;     // bytes between two source ranks' blocks (n_queries * record bytes after an all-gather)
+    const uint32_t *p2p_flag; // NULL, or [B] arrival counters of this rank's window: wait until p2p_expected arrivals
+    uint32_t p2p_expected;
     uint32_t world, n_queries;
     int mode;
     uint32_t n_keep, limit, offset, v_stride, capb;
@@ -186,9 +211,18 @@ __global__ void __launch_bounds__(256) shard_fuse_kernel(const ShardFuseParams p
     const bool has_ft = p.mode != OC_MODE_VECTOR, has_v = p.mode != OC_MODE_FULLTEXT;
     const bool hybrid = has_ft && has_v;
     const size_t rb = shard_rec_bytes(p.n_keep, p.v_stride);
-    auto hdr_of = [&](uint32_t s) { return reinterpret_cast<const ShardHdr *>(p.recv + (size_t(s) * p.n_queries + q) * rb); };
+    auto hdr_of = [&](uint32_t s) { return reinterpret_cast<const ShardHdr *>(p.recv + size_t(s) * p.rank_stride + size_t(q) * rb); };
     auto ft_of = [&](uint32_t s) { return reinterpret_cast<const ShardFt *>(hdr_of(s) + 1); };
     auto v_of = [&](uint32_t s) { return reinterpret_cast<const ShardV *>(ft_of(s) + p.n_keep); };
+    if (p.p2p_flag) {
+        // direct exchange: every rank's pack kernel stored this query's record into our window and bumped the counter
+        if (tid == 0) {
+            unsigned int seen;
+            do { asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.p2p_flag + q) : "memory"); } while (seen < p.p2p_expected);
+        }
+        __syncthreads();
+        asm volatile("fence.acq_rel.sys;" ::: "memory");
+    }
     if (tid == 0) {
         base_str[0] = 0; base_emb[0] = 0;
         for (uint32_t s = 0; s < W; s++) {
@@ -354,6 +388,19 @@ static int run_sharded_merge(oc_ctx *c, const oc_search_params *p, const oc::Fus
     pp.n_rows_str = n_rows_str; pp.n_rows_emb = n_rows_emb;
     pp.unproven = unproven_dev;
     pp.out = c->shard_send.as<uint8_t>();
+    // direct NVLink exchange when the runtime imported the peers' windows and the batch fits them (every rank takes the
+    // same decision: it depends on the batch shape only); OC_SHARD_P2P=0: A/B switch back to ncclAllGather
+    const char *p2env = getenv("OC_SHARD_P2P");
+    const bool p2p = c->p2p.ready && !(p2env && p2env[0] == '0') && rb * B <= P2P_WIN_BYTES && B <= P2P_MAX_Q;
+    uint32_t par = 0;
+    if (p2p) {
+        par = uint32_t(c->p2p.seq & 1u);
+        pp.p2p_world = W; pp.p2p_rank = (uint32_t)c->comm.rank; pp.p2p_rank_stride = P2P_WIN_BYTES;
+        for (uint32_t r = 0; r < W; r++) {
+            pp.p2p_win[r] = c->p2p.peer[r] + P2P_FLAG_BYTES + size_t(par) * W * P2P_WIN_BYTES;
+            pp.p2p_flag[r] = reinterpret_cast<uint32_t *>(c->p2p.peer[r]) + size_t(par) * P2P_MAX_Q;
+        }
+    }
     const size_t pack_smem = size_t(fp.capb) * 8 + size_t(std::max<uint32_t>(32, next_pow2(fp.n_keep))) * 8 + 64;
     if (smem_cfg_needed(c->device, (const void *)shard_pack_kernel, pack_smem))
         CU(cudaFuncSetAttribute(shard_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pack_smem));
@@ -361,10 +408,20 @@ static int run_sharded_merge(oc_ctx *c, const oc_search_params *p, const oc::Fus
     launched(c);
     CU(cudaGetLastError());
     CU(cudaEventRecord(c->ev[EV_COMM0], c->stream));
-    std::string err;
-    if (!c->comm.all_gather(c->shard_send.p, c->shard_recv.p, rb * B, c->stream, &err)) return fail(OC_ERR_COMM, "%s", err.c_str());
     ShardFuseParams sp{};
-    sp.recv = c->shard_recv.as<uint8_t>(); sp.world = W; sp.n_queries = B; sp.mode = p->mode;
+    if (p2p) {
+        sp.recv = c->p2p.peer[c->comm.rank] + P2P_FLAG_BYTES + size_t(par) * W * P2P_WIN_BYTES;
+        sp.rank_stride = P2P_WIN_BYTES;
+        sp.p2p_flag = reinterpret_cast<const uint32_t *>(c->p2p.peer[c->comm.rank]) + size_t(par) * P2P_MAX_Q;
+        sp.p2p_expected = W * uint32_t((c->p2p.seq >> 1) + 1);
+        c->p2p.seq++;
+    } else {
+        std::string err;
+        if (!c->comm.all_gather(c->shard_send.p, c->shard_recv.p, rb * B, c->stream, &err)) return fail(OC_ERR_COMM, "%s", err.c_str());
+        sp.recv = c->shard_recv.as<uint8_t>();
+        sp.rank_stride = rb * B;
+    }
+    sp.world = W; sp.n_queries = B; sp.mode = p->mode;
     sp.n_keep = fp.n_keep; sp.limit = fp.limit; sp.offset = fp.offset; sp.v_stride = fp.v_stride;
     sp.capb = std::min<uint32_t>(2048, std::max<uint32_t>(64, next_pow2(std::max<uint32_t>(W * fp.n_keep + fp.v_stride, W * fp.v_stride))));
     sp.capb = std::max<uint32_t>(sp.capb, next_pow2(2 * std::max(fp.n_keep, fp.v_stride)));

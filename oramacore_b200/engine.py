@@ -81,6 +81,16 @@ class Context:
         buf = (C.c_uint8 * _lib.OC_COMM_ID_BYTES).from_buffer_copy(unique_id)
         check(lib().oc_comm_init(self._h, world_size, rank, buf))
 
+    def comm_enable_p2p(self, all_gather):
+        """Direct NVLink exchange of the shard records (oc_comm_p2p_*).  `all_gather(blob: bytes) -> list[bytes]`
+        is the host runtime's all-gather in rank order (e.g. torch.distributed.all_gather_object)."""
+        buf = (C.c_uint8 * 128)()
+        check(lib().oc_comm_p2p_export(self._h, buf))
+        blobs = all_gather(bytes(buf))
+        cat = b"".join(blobs)
+        arr = (C.c_uint8 * len(cat)).from_buffer_copy(cat)
+        check(lib().oc_comm_p2p_import(self._h, arr))
+
 
 def to_bf16(x: np.ndarray) -> np.ndarray:
     """fp32 -> bf16 bit patterns (uint16), round to nearest even."""

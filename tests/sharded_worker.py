@@ -26,6 +26,12 @@ def main():
     uid = [ob.Context.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     ctx.comm_init(world, rank, uid[0])
+    if os.environ.get("OC_SHARD_P2P", "1") != "0":     # the records travel by direct NVLink stores (else ncclAllGather)
+        def _ag(blob):
+            out = [None] * world
+            dist.all_gather_object(out, blob)
+            return out
+        ctx.comm_enable_p2p(_ag)
 
     n, dim, vocab, B = 60000, 384, 3000, 12
     rows = synth.make_vectors(n, dim, seed=41)
