@@ -1409,8 +1409,17 @@ template <bool THRESH, bool OMC>
 static int launch_tile2_t(oc_ctx *c, const Bm25Params &bp, size_t smem, cudaStream_t st, const ItemTok *flat, unsigned int *counter) {
     if (smem_cfg_needed(c->device, (const void *)bm25_tile2_kernel<THRESH, OMC>, smem))
         CU(cudaFuncSetAttribute(bm25_tile2_kernel<THRESH, OMC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static std::mutex occ_mu;                         // occupancy per (device, shared-memory size): queried once
+    static std::map<std::pair<int, size_t>, int> occ;
     int per_sm = 1;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bm25_tile2_kernel<THRESH, OMC>, BM25_THREADS, smem));
+    {
+        std::lock_guard<std::mutex> g(occ_mu);
+        auto it = occ.find(std::make_pair(c->device, smem));
+        if (it == occ.end()) {
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bm25_tile2_kernel<THRESH, OMC>, BM25_THREADS, smem));
+            occ[std::make_pair(c->device, smem)] = per_sm;
+        } else per_sm = it->second;
+    }
     const uint64_t items = uint64_t(bp.n_tiles) * bp.n_queries;
     const uint32_t grid = (uint32_t)std::min<uint64_t>(items, uint64_t(std::max(per_sm, 1)) * c->prop.multiProcessorCount);
     bm25_tile2_kernel<THRESH, OMC><<<grid, BM25_THREADS, smem, st>>>(bp, flat, counter);
