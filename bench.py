@@ -480,7 +480,9 @@ def main():
     if w["dim"] and w["vocab"] and postings:
         line["roofline_bm25"] = {"kernel": "bm25_tile_kernel", "bound": "hbm", "achieved": (postings * 8 / 1e9) / (bm_ms * 1e-3),
                                  "peak": peak, "unit": "GB/s", "frac": (postings * 8 / 1e9) / (bm_ms * 1e-3) / peak,
-                                 "postings_per_s": postings / (bm_ms * 1e-3), "stage_ms": bm_ms / K}
+                                 "postings_per_s": postings / (bm_ms * 1e-3), "stage_ms": bm_ms / K,
+                                 "note": "the fulltext stage runs on the side stream under the matrix sweep: its window includes the wait for "
+                                         "the SMs' shared memory the sweep holds (OC_SIDE_STREAM=0 times it alone: profiles/)"}
 
     def hits_of(raw, i):
         return ob.SearchHits(raw[0][i, :raw[2][i]].copy(), raw[1][i, :raw[2][i]].copy(), int(raw[3][i]))

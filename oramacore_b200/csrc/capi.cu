@@ -1906,7 +1906,10 @@ static int search_impl(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_para
     fp.mode = p->mode; fp.n_tiles = n_tiles; fp.n_keep = n_keep; fp.limit = p->limit; fp.offset = p->offset;
     {   // smallest power-of-two key buffer that takes the candidates in one round (sort cost ~ capb log^2 capb)
         const uint64_t total = (has_ft ? uint64_t(n_tiles) * n_keep : 0) + (has_v ? vlimit : 0);
-        fp.capb = next_pow2((uint32_t)std::min<uint64_t>(2048, std::max<uint64_t>(total, 2 * n_keep)));
+        // up to 16 K keys (128 KB) stay in shared memory and go through one radix select; the streaming bitonic path behind
+        // it cost 0.44 ms per batch on the 10M-document fulltext workload (1221 tiles x 10 candidate slots per query:
+        // profiles/r02_ncu_fuse_t1.md)
+        fp.capb = next_pow2((uint32_t)std::min<uint64_t>(16384, std::max<uint64_t>(total, 2 * n_keep)));
         fp.capb = std::max<uint32_t>(fp.capb, std::max<uint32_t>(64, next_pow2(2 * n_keep)));
     }
     if (has_ft) {
