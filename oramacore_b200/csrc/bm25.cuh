@@ -125,6 +125,7 @@ __device__ __forceinline__ bool f32_is_normal(float x) {
     return e != 0u && e != 0xffu;
 }
 
+constexpr uint32_t BM25_CLASSES = 5;   // 4, 3, 2, 1, 0 dense tokens
 struct Bm25Params {
     const TermDesc *terms;
     const TokenDesc *tokens;
@@ -157,7 +158,22 @@ struct Bm25Params {
     uint32_t tile_first;          // first tile handled by this launch (sharding of launches)
     uint32_t *matched_bits;       // NULL, or out: [n_queries][n_tiles * TILE/32] bitmap of the matched rows (the keys of the
                                   // score map) — what the facet counts run over (read/index/facet.rs:147-209)
+    // item order of the register-folded scorers: queries grouped by their number of dense tokens, most expensive class
+    // first, tile-major inside a class — so the ragged end of the persistent schedule consists of the cheap items.
+    // perm == NULL: natural order (item = tile * n_queries + q)
+    const uint32_t *perm;         // [n_queries] query ids, class by class
+    uint32_t cls_off[BM25_CLASSES];   // first item of each class
+    uint32_t cls_nq[BM25_CLASSES];    // queries in the class
+    uint32_t cls_q0[BM25_CLASSES];    // first perm entry of the class
 };
+__host__ __device__ __forceinline__ void bm25_item_decode(const Bm25Params &p, const uint32_t k, uint32_t &tile, uint32_t &q) {
+    if (!p.perm) { tile = k / p.n_queries; q = k % p.n_queries; return; }
+    uint32_t g = 0;
+    while (g + 1 < BM25_CLASSES && k >= p.cls_off[g + 1]) g++;   // (an empty class has off[g + 1] == off[g]: skipped)
+    const uint32_t local = k - p.cls_off[g], nqg = p.cls_nq[g];
+    tile = local / nqg;
+    q = p.perm[p.cls_q0[g] + local % nqg];
+}
 
 __host__ __device__ inline size_t bm25_smem_bytes(bool multi, bool threshold, bool omc, uint32_t cap) {
     size_t b = size_t(BM25_TILE) * 4;                 // score
@@ -622,14 +638,17 @@ struct ItemTok {            // 32 B
     uint32_t bit, pad;
 };
 constexpr uint32_t BM25_FLAT_TOK = 4;   // tokens per query the flat descriptors hold (longer queries: in-kernel table build)
-__global__ void __launch_bounds__(256) bm25_flatten_kernel(const TermDesc *terms, const TokenDesc *tokens, const QueryDesc *queries,
-                                                          const uint32_t *seg, uint32_t n_tiles, uint32_t n_queries, ItemTok *flat) {
+__global__ void __launch_bounds__(256) bm25_flatten_kernel(const Bm25Params p, ItemTok *flat) {
+    const TermDesc *terms = p.terms; const TokenDesc *tokens = p.tokens; const QueryDesc *queries = p.queries;
+    const uint32_t *seg = p.seg;
+    const uint32_t n_tiles = p.n_tiles, n_queries = p.n_queries;
     const uint64_t gid = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     const uint64_t total = uint64_t(n_tiles) * n_queries * BM25_FLAT_TOK;
     if (gid >= total) return;
     const uint32_t j = uint32_t(gid % BM25_FLAT_TOK);
     const uint64_t item = gid / BM25_FLAT_TOK;
-    const uint32_t tile = uint32_t(item / n_queries), q = uint32_t(item % n_queries);
+    uint32_t tile, q;
+    bm25_item_decode(p, uint32_t(item), tile, q);
     const QueryDesc qd = queries[q];
     ItemTok it{};
     if (j < qd.token_end - qd.token_begin) {
@@ -999,6 +1018,510 @@ __global__ void __launch_bounds__(BM25_THREADS, 1024 / BM25_THREADS) bm25_tile2_
     }
 }
 
+// =======================================================================================
+// K3c — the scorer without accumulator arrays (plain queries: no threshold, no OMC, <= BM25_FLAT_TOK tokens,
+// every token <= 1 term).  Same contract, outputs and bits as bm25_tile2_kernel<false, false>.
+//
+// A row's score is the fold of its tokens' contributions in token order.  K3b materialises that fold in a
+// float[TILE] array per item: every dense token costs a shared-memory read-modify-write of the whole tile, then a
+// scan re-reads it and a zeroing pass clears it.  Here the fold lives in REGISTERS:
+//   * rows that appear in some LIST token (few: list tokens are the non-hot terms) are marked in 1 KB bitmaps (one per
+//     list token + their union) by a first walk over the postings; after the scan below, a second walk scores them: the
+//     posting of the FIRST list token that holds the row folds all tokens in order — a scalar load from each dense
+//     token's contribution array (L1-hot: the scan just streamed those slices), and a binary search in another list
+//     token's tile slice only where that token's bitmap has the row;
+//   * every other row can only receive dense contributions: the scan folds the dense tokens' float4 slices
+//     straight from L2 into registers (adding the 0.0 of an absent row changes no bit), masks the rows the union
+//     bitmap marks, and does the bookkeeping (count, extrema, gated candidates) on the spot.
+// An item without dense tokens costs its postings only; an item without list tokens needs no bitmap and one
+// barrier.  No float accumulators, no zeroing passes: ~21 KB of shared memory per CTA (bitmaps + candidate buffer).  When a cold threshold lets more
+// than `cap` candidates through, the best n_keep of the first `cap` arrivals give a valid tighter threshold and the
+// item is redone with it (first tiles of a query only).
+// =======================================================================================
+__host__ __device__ inline size_t bm25_tile3_smem_bytes(uint32_t cap) { return size_t(BM25_TILE) / 8 * (BM25_FLAT_TOK + 1) + size_t(cap) * 8 + 64; }
+
+__device__ __forceinline__ void t3_consider(float s, uint32_t row, unsigned long long tau, float tau_f, uint32_t *s_cnt,
+                                            uint64_t *tbuf, uint32_t cap) {
+    if (!(s >= tau_f)) return;                                          // NaN fails; ties re-checked on the key
+    const unsigned long long key = make_key(s, row);
+    if (key <= tau) return;
+    const uint32_t slot = atomicAdd(s_cnt, 1u);
+    if (slot < cap) tbuf[slot] = key;                                   // *s_cnt > cap afterwards == overflow
+}
+__device__ __forceinline__ bool t3_find(const uint2 *pp, uint32_t n, uint32_t row, uint32_t *payload) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if (__ldg(&pp[m].x) < row) lo = m + 1; else hi = m; }
+    if (lo < n) { const uint2 r = __ldg(pp + lo); if (r.x == row) { *payload = r.y; return true; } }
+    return false;
+}
+// score of a row that list token j holds (posting `rec`): the item's tokens folded in token order (the reference's
+// summation order) — dense tokens by row, other list tokens by binary search where their bitmap has the row
+__device__ __noinline__ float t3_fold(const ItemTok *tab, const uint32_t *bm, const uint32_t j, const uint2 rec, const uint32_t l,
+                                         const float k, const float kp1) {
+    constexpr uint32_t W = BM25_TILE / 32;
+    const uint32_t w = l >> 5, bit = 1u << (l & 31u);
+    float s = 0.f;
+#pragma unroll 1
+    for (uint32_t i = 0; i < BM25_FLAT_TOK; i++) {
+        const uint32_t ni = tab[i].n;
+        if (ni == 0) continue;
+        const uint32_t fi = tab[i].flags;
+        float ci;
+        if (fi & TD_DENSE) ci = __ldg(reinterpret_cast<const float *>(tab[i].ptr) + l);   // 0.0 = absent
+        else {
+            uint32_t pay = rec.y;
+            if (i != j) {                              // (another non-empty list token: the per-token bitmaps are in use)
+                if (!(bm[i * W + w] & bit)) continue;
+                if (!t3_find(reinterpret_cast<const uint2 *>(tab[i].ptr), ni, rec.x, &pay)) continue;
+            }
+            if (fi & TD_PRE) ci = __uint_as_float(pay);                    // NaN = skipped contribution
+            else {
+                const float ntf = __fmul_rn(tab[i].w, __uint_as_float(pay));
+                ci = f32_is_normal(ntf) ? bm25_sat(ntf, k, kp1, tab[i].idf) : __int_as_float(0x7fc00000);   // bm25.rs:387,501
+            }
+        }
+        if (ci == ci) s = __fadd_rn(s, ci);
+    }
+    return s;
+}
+// candidate test of the 4 rows of one float4 slot (rare once the threshold is warm: kept out of line so the scan loop
+// stays small — the scorers' code footprint is what the instruction cache sees from 30 unsynchronised warps)
+__device__ __noinline__ void t3_consider4(const float s0, const float s1, const float s2, const float s3, const uint32_t row,
+                                          const unsigned long long tau, const float tau_f, uint32_t *s_cnt, uint64_t *tbuf, const uint32_t cap) {
+    if (s0 != 0.f) t3_consider(s0, row, tau, tau_f, s_cnt, tbuf, cap);
+    if (s1 != 0.f) t3_consider(s1, row + 1u, tau, tau_f, s_cnt, tbuf, cap);
+    if (s2 != 0.f) t3_consider(s2, row + 2u, tau, tau_f, s_cnt, tbuf, cap);
+    if (s3 != 0.f) t3_consider(s3, row + 3u, tau, tau_f, s_cnt, tbuf, cap);
+}
+__device__ __forceinline__ uint32_t f32_ne0_mask(const float x) {   // 0xffffffff when x != 0 (or NaN), else 0: one FSET
+    uint32_t r;
+    asm("set.neu.u32.f32 %0, %1, 0f00000000;" : "=r"(r) : "f"(x));
+    return r;
+}
+// the dense part of an item: ND dense tokens (token order); thread t owns the float4 slots t, t + STRIDE, ...
+// Software-pipelined: the loads of batch h+1 are in flight while batch h is folded.  `pos`: every contribution of the
+// item is >= 0 (weights, idf, k non-negative), so no score is below the fold's start and the minimum stays 0.
+template <uint32_t ND, uint32_t STRIDE>
+__device__ __forceinline__ void t3_scan(const float4 *d0, const float4 *d1, const float4 *d2, const float4 *d3,
+                                        const uint32_t *touched, const bool any_list, const bool pos, const uint32_t row0, const uint32_t tid,
+                                        const unsigned long long tau, const float tau_f, uint32_t *s_cnt, uint64_t *tbuf,
+                                        const uint32_t cap, uint32_t &matched, float &lmax, float &lmin) {
+    constexpr uint32_t F4 = BM25_TILE / 4 / STRIDE;         // float4 slots per thread (8 at 8192 rows x 256 threads, 64 per lane of a warp)
+    constexpr uint32_t FB = (ND <= 2 && F4 >= 4) ? 2 : 1;   // slots per batch
+    constexpr uint32_t NB = F4 / FB;                        // batches
+    static_assert(F4 >= 2 && NB % 2 == 0, "tile size");
+    const float4 *dp[4] = {d0, d1, d2, d3};
+    const uint32_t *tw = touched + (tid >> 3);              // slot i = tid + j * STRIDE: word (tid >> 3) + j * STRIDE / 8, shift (tid & 7) * 4
+    const uint32_t tsh = (tid & 7u) * 4u;
+    float4 ca[ND][FB], cb[ND][FB];
+    auto load = [&](float4 (&c)[ND][FB], const uint32_t h) {
+#pragma unroll
+        for (uint32_t u = 0; u < FB; u++)
+#pragma unroll
+            for (uint32_t d = 0; d < ND; d++) c[d][u] = __ldg(dp[d] + tid + (h * FB + u) * STRIDE);
+    };
+    auto fold = [&](const float4 (&c)[ND][FB], const uint32_t h) {
+#pragma unroll
+        for (uint32_t u = 0; u < FB; u++) {
+            const uint32_t i = tid + (h * FB + u) * STRIDE;
+            float sv[4] = {c[0][u].x, c[0][u].y, c[0][u].z, c[0][u].w};   // 0.0 + c == c for the values stored (never -0.0)
+#pragma unroll
+            for (uint32_t d = 1; d < ND; d++) {
+                sv[0] = __fadd_rn(sv[0], c[d][u].x); sv[1] = __fadd_rn(sv[1], c[d][u].y);
+                sv[2] = __fadd_rn(sv[2], c[d][u].z); sv[3] = __fadd_rn(sv[3], c[d][u].w);
+            }
+            if (any_list) {   // rows scored by a posting walker (4 rows = 4 bits of one bitmap word)
+                const uint32_t bits = (tw[(h * FB + u) * (STRIDE / 8)] >> tsh) & 0xfu;
+                if (bits) {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) sv[k] = ((bits >> k) & 1u) ? 0.f : sv[k];
+                }
+            }
+            matched -= f32_ne0_mask(sv[0]) + f32_ne0_mask(sv[1]) + f32_ne0_mask(sv[2]) + f32_ne0_mask(sv[3]);   // -(-1) per non-zero
+            const float m4 = fmaxf(fmaxf(sv[0], sv[1]), fmaxf(sv[2], sv[3]));
+            lmax = fmaxf(lmax, m4);
+            if (!pos) lmin = fminf(lmin, fminf(fminf(sv[0], sv[1]), fminf(sv[2], sv[3])));
+            if (m4 >= tau_f) t3_consider4(sv[0], sv[1], sv[2], sv[3], row0 + i * 4u, tau, tau_f, s_cnt, tbuf, cap);
+        }
+    };
+    load(ca, 0);
+#pragma unroll 1
+    for (uint32_t h = 0; h < NB; h += 2) {
+        load(cb, h + 1);
+        fold(ca, h);
+        if (h + 2 < NB) load(ca, h + 2);
+        fold(cb, h + 1);
+    }
+}
+
+__global__ void __launch_bounds__(BM25_THREADS, 1024 / BM25_THREADS) bm25_tile3_kernel(const Bm25Params p, const ItemTok *flat, unsigned int *work_counter) {
+    constexpr uint32_t W = BM25_TILE / 32;                                  // bitmap words per tile
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint32_t *touched = reinterpret_cast<uint32_t *>(smem);                 // rows that appear in some list token
+    uint32_t *bm = touched + W;                                             // [BM25_FLAT_TOK][W]: rows of each list token
+    uint64_t *tbuf = reinterpret_cast<uint64_t *>(bm + BM25_FLAT_TOK * W);
+    // per-item counters and the token table, double-buffered by item parity (the next item's set is prepared while
+    // this one still reads its own)
+    __shared__ uint32_t s_cnt2[2], s_matched2[2];
+    __shared__ unsigned int s_maxo2[2], s_mino2[2];
+    __shared__ ItemTok s_tab[2][BM25_FLAT_TOK];
+    __shared__ uint32_t s_item_cur, s_item_next;
+
+    const uint32_t tid = threadIdx.x;
+    const float kp1 = __fadd_rn(p.k, 1.0f);
+    const uint32_t n_items = p.n_tiles * p.n_queries;
+    const uint32_t *okbits = p.row_ok_bits;
+
+    for (uint32_t i = tid; i < (BM25_FLAT_TOK + 1) * W; i += BM25_THREADS) touched[i] = 0u;
+    if (tid == 0) { s_item_cur = atomicAdd(work_counter, 1u); s_item_next = atomicAdd(work_counter, 1u); }
+    if (tid < 2) { s_cnt2[tid] = 0; s_matched2[tid] = 0; s_maxo2[tid] = f32_ordered(0.f); s_mino2[tid] = f32_ordered(0.f); }
+    __syncthreads();
+    if (s_item_cur < n_items && tid < BM25_FLAT_TOK) s_tab[0][tid] = flat[size_t(s_item_cur) * BM25_FLAT_TOK + tid];
+    unsigned long long tau_next = 0ull;
+    if (s_item_cur < n_items) { uint32_t t0, q0; bm25_item_decode(p, s_item_cur, t0, q0); tau_next = __ldcg(p.tau + q0); }   // (L2: other CTAs raise it)
+
+    for (uint32_t par = 0;; par ^= 1u) {
+        __syncthreads();                                   // previous item retired: bitmaps clean, table + counters + ids set
+        const uint32_t item = s_item_cur;
+        if (item >= n_items) break;
+        const uint32_t next = s_item_next;
+        uint32_t next2 = 0;
+        if (tid == 0) next2 = atomicAdd(work_counter, 1u);   // consumed at the end of this item
+        uint32_t tile, q;
+        bm25_item_decode(p, item, tile, q);
+        const uint32_t row0 = tile * BM25_TILE;
+        uint32_t *s_cnt = &s_cnt2[par];
+        if (tid == 0) { s_cnt2[par ^ 1u] = 0; s_matched2[par ^ 1u] = 0; s_maxo2[par ^ 1u] = f32_ordered(0.f); s_mino2[par ^ 1u] = f32_ordered(0.f); }
+        // in flight during this item: the next item's descriptors and its query's running threshold
+        ItemTok nx{};
+        if (next < n_items && tid < BM25_FLAT_TOK) nx = flat[size_t(next) * BM25_FLAT_TOK + tid];
+        unsigned long long tau = tau_next;
+        if (next < n_items) { uint32_t tn, qn; bm25_item_decode(p, next, tn, qn); tau_next = __ldcg(p.tau + qn); }
+
+        // the item's tokens: dense slices in token order; list tokens counted
+        const ItemTok *tab = s_tab[par];
+        const float4 *d0 = nullptr, *d1 = nullptr, *d2 = nullptr, *d3 = nullptr;
+        uint32_t nd = 0, n_list = 0;
+        bool pos = p.k >= 0.f;
+#pragma unroll
+        for (uint32_t j = 0; j < BM25_FLAT_TOK; j++) {
+            const uint32_t n = tab[j].n;
+            if (n == 0) continue;
+            pos = pos && tab[j].w >= 0.f && tab[j].idf >= 0.f;
+            if (tab[j].flags & TD_DENSE) {
+                const float4 *dp = reinterpret_cast<const float4 *>(tab[j].ptr);
+                if (nd == 0) d0 = dp; else if (nd == 1) d1 = dp; else if (nd == 2) d2 = dp; else d3 = dp;
+                nd++;
+            } else n_list++;
+        }
+        const bool any_list = n_list != 0;
+        // per-token bitmaps are needed to find the owner of a row that sits in several list tokens, and they carry the
+        // outcome of the filter / tombstone check; one unfiltered list token needs neither
+        const bool use_bm = n_list > 1 || okbits != nullptr;
+
+        for (;;) {   // (repeats only when a cold threshold overflowed the candidate buffer)
+            const float tau_f = tau ? key_score(tau) : -INFINITY;
+            uint32_t matched = 0;
+            float lmax = 0.f, lmin = 0.f;
+            // ---------------------------------------- mark the rows of the list tokens
+            if (any_list && (nd || use_bm)) {
+#pragma unroll 1
+                for (uint32_t j = 0; j < BM25_FLAT_TOK; j++) {
+                    const uint32_t n = tab[j].n;
+                    if (n == 0 || (tab[j].flags & TD_DENSE)) continue;     // block-uniform
+                    const uint2 *pp = reinterpret_cast<const uint2 *>(tab[j].ptr);
+                    for (uint32_t pi = tid; pi < n; pi += BM25_THREADS) {
+                        const uint32_t row = __ldg(&pp[pi].x);
+                        if (okbits && !((__ldg(okbits + (row >> 5)) >> (row & 31u)) & 1u)) continue;
+                        const uint32_t l = row - row0, bit = 1u << (l & 31u);
+                        if (nd) atomicOr(&touched[l >> 5], bit);
+                        if (use_bm) atomicOr(&bm[j * W + (l >> 5)], bit);
+                    }
+                }
+                __syncthreads();
+            }
+            // ---------------------------------------- rows outside every list: dense tokens only, folded in registers
+            switch (nd) {
+                case 0: break;
+                case 1: t3_scan<1, BM25_THREADS>(d0, d1, d2, d3, touched, any_list, pos, row0, tid, tau, tau_f, s_cnt, tbuf, p.cap, matched, lmax, lmin); break;
+                case 2: t3_scan<2, BM25_THREADS>(d0, d1, d2, d3, touched, any_list, pos, row0, tid, tau, tau_f, s_cnt, tbuf, p.cap, matched, lmax, lmin); break;
+                case 3: t3_scan<3, BM25_THREADS>(d0, d1, d2, d3, touched, any_list, pos, row0, tid, tau, tau_f, s_cnt, tbuf, p.cap, matched, lmax, lmin); break;
+                default: t3_scan<4, BM25_THREADS>(d0, d1, d2, d3, touched, any_list, pos, row0, tid, tau, tau_f, s_cnt, tbuf, p.cap, matched, lmax, lmin); break;
+            }
+            // ---------------------------------------- rows of the list tokens: the FIRST list token holding the row folds
+            // it (the scan just pulled the dense slices through L1; other lists are consulted only where their bit is set)
+            if (any_list) {
+#pragma unroll 1
+                for (uint32_t j = 0; j < BM25_FLAT_TOK; j++) {
+                    const uint32_t n = tab[j].n;
+                    if (n == 0 || (tab[j].flags & TD_DENSE)) continue;
+                    const uint2 *pp = reinterpret_cast<const uint2 *>(tab[j].ptr);
+                    for (uint32_t pi = tid; pi < n; pi += BM25_THREADS) {
+                        const uint2 rec = __ldg(pp + pi);
+                        const uint32_t l = rec.x - row0, w = l >> 5, bit = 1u << (l & 31u);
+                        if (use_bm) {
+                            if (!(bm[j * W + w] & bit)) continue;          // failed the row check
+                            uint32_t earlier = 0;
+                            for (uint32_t jj = 0; jj < j; jj++) earlier |= bm[jj * W + w];   // (all-zero for dense / empty tokens)
+                            if (earlier & bit) continue;                   // an earlier list token owns the row
+                        }
+                        const float s = t3_fold(tab, bm, j, rec, l, p.k, kp1);
+                        if (s != 0.f) {
+                            matched++;
+                            lmax = fmaxf(lmax, s);
+                            lmin = fminf(lmin, s);
+                            t3_consider(s, rec.x, tau, tau_f, s_cnt, tbuf, p.cap);
+                        }
+                    }
+                }
+            }
+            // block reductions of count / extrema
+            matched = __reduce_add_sync(0xffffffffu, matched);
+            if (matched) {   // (warp-uniform)
+                for (int o = 16; o > 0; o >>= 1) {
+                    lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+                    lmin = fminf(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+                }
+                if ((tid & 31) == 0) {
+                    atomicAdd(&s_matched2[par], matched);
+                    atomicMax(&s_maxo2[par], f32_ordered(lmax));
+                    atomicMin(&s_mino2[par], f32_ordered(lmin));
+                }
+            }
+            __syncthreads();                                   // counters final; nobody reads the bitmaps any more
+            if (any_list) {
+                if (nd) for (uint32_t i = tid; i < W; i += BM25_THREADS) touched[i] = 0u;
+                if (use_bm) for (uint32_t i = tid; i < BM25_FLAT_TOK * W; i += BM25_THREADS) bm[i] = 0u;
+            }
+            if (*s_cnt <= p.cap) break;
+            // overflow: the n_keep-th best of the first `cap` arrivals bounds the tile's n_keep-th best from below
+            block_keep_top(tbuf, p.cap, p.cap, p.n_keep, tid);
+            const unsigned long long kth = tbuf[p.n_keep - 1] - 1ull;   // keys are unique: "> kth" keeps that row itself
+            tau = kth > tau ? kth : tau;
+            __syncthreads();                                   // everybody has read tbuf / the counters
+            if (tid == 0) { s_cnt2[par] = 0; s_matched2[par] = 0; s_maxo2[par] = f32_ordered(0.f); s_mino2[par] = f32_ordered(0.f); }
+            __syncthreads();
+        }
+        // ---- emit: best <= n_keep of the buffer
+        const size_t slot_base = (size_t(q) * p.n_tiles + tile);
+        uint32_t c = *s_cnt;
+        if (c >= p.n_keep && c > 0) {
+            block_keep_top(tbuf, c, p.cap, p.n_keep, tid);
+            c = p.n_keep;
+            if (tid == 0) atomicMax(p.tau + q, (unsigned long long)tbuf[p.n_keep - 1]);
+        }
+        for (uint32_t i = tid; i < c; i += BM25_THREADS) {
+            const uint64_t key = tbuf[i];
+            p.cand_key[slot_base * p.n_keep + i] = key;
+            p.cand_ft[slot_base * p.n_keep + i] = key_score(key);   // no OMC, no min hint: the key's score IS the raw score
+        }
+        if (tid == 0) {
+            p.cand_cnt[slot_base] = c;
+            p.tile_count[slot_base] = s_matched2[par];
+            p.tile_max[slot_base] = f32_unordered(s_maxo2[par]);
+            p.tile_min[slot_base] = f32_unordered(s_mino2[par]);
+        }
+        if (tid < BM25_FLAT_TOK) s_tab[par ^ 1u][tid] = nx;   // the next item's table
+        if (tid == 0) { s_item_cur = next; s_item_next = next2; }
+    }
+}
+
+// =======================================================================================
+// K3d — the same scorer with a WARP per (tile, query) item instead of a CTA: no block barrier anywhere, the per-item
+// fixed work (descriptors, reductions, selection, emit) is executed by one warp instead of eight, and 30 warps per
+// SM progress independently (an item's latency chain stalls only its own warp).  Plain queries with n_keep <= 32.
+// Per warp: the ownership bitmaps (5 KB), 256 candidate keys, the token table.
+// =======================================================================================
+constexpr uint32_t BW_WARPS = 6, BW_CAP = 256;
+struct __align__(16) WarpScratch {
+    uint32_t touched[BM25_TILE / 32];
+    uint32_t bm[BM25_FLAT_TOK * (BM25_TILE / 32)];
+    uint64_t tbuf[BW_CAP];
+    ItemTok tab[BM25_FLAT_TOK];
+    uint32_t cnt, pad[3];
+};
+// the n largest of buf[0, count) (count <= BW_CAP, n <= 32), descending, into buf[0, n); returns the n-th (0 if count < n)
+__device__ __noinline__ unsigned long long warp_keep_top(uint64_t *buf, const uint32_t count, const uint32_t n, const uint32_t lane) {
+    constexpr uint32_t PER = BW_CAP / 32;
+    unsigned long long k[PER];
+#pragma unroll
+    for (uint32_t u = 0; u < PER; u++) k[u] = lane + 32u * u < count ? buf[lane + 32u * u] : 0ull;
+    __syncwarp();
+    unsigned long long mine = 0ull, last = 0ull;
+    for (uint32_t r = 0; r < n; r++) {
+        unsigned long long m = k[0];
+#pragma unroll
+        for (uint32_t u = 1; u < PER; u++) m = k[u] > m ? k[u] : m;
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long om = __shfl_xor_sync(0xffffffffu, m, o);
+            m = om > m ? om : m;
+        }
+        last = m;
+        if (m == 0ull) break;
+        if (lane == r) mine = m;
+#pragma unroll
+        for (uint32_t u = 0; u < PER; u++) if (k[u] == m) k[u] = 0ull;   // keys are unique
+    }
+    if (lane < n) buf[lane] = mine;
+    __syncwarp();
+    return last;
+}
+__global__ void __launch_bounds__(BW_WARPS * 32, 5) bm25_warp_kernel(const Bm25Params p, const ItemTok *flat, unsigned int *work_counter) {
+    constexpr uint32_t W = BM25_TILE / 32;
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t lane = threadIdx.x & 31u;
+    WarpScratch &ws = reinterpret_cast<WarpScratch *>(smem)[threadIdx.x >> 5];
+    uint32_t *touched = ws.touched, *bm = ws.bm;
+    const ItemTok *tab = ws.tab;
+    const float kp1 = __fadd_rn(p.k, 1.0f);
+    const uint32_t n_items = p.n_tiles * p.n_queries;
+    const uint32_t *okbits = p.row_ok_bits;
+
+    for (uint32_t i = lane; i < W; i += 32) touched[i] = 0u;
+    for (uint32_t i = lane; i < BM25_FLAT_TOK * W; i += 32) bm[i] = 0u;
+    if (lane == 0) ws.cnt = 0u;
+    uint32_t item = 0, next = 0;
+    if (lane == 0) { item = atomicAdd(work_counter, 1u); next = atomicAdd(work_counter, 1u); }
+    item = __shfl_sync(0xffffffffu, item, 0); next = __shfl_sync(0xffffffffu, next, 0);
+    ItemTok cur{};
+    if (item < n_items && lane < BM25_FLAT_TOK) cur = flat[size_t(item) * BM25_FLAT_TOK + lane];
+    unsigned long long tau_next = 0ull;
+    if (item < n_items) { uint32_t t0, q0; bm25_item_decode(p, item, t0, q0); tau_next = __ldcg(p.tau + q0); }
+
+    while (item < n_items) {
+        uint32_t next2 = 0;
+        if (lane == 0) next2 = atomicAdd(work_counter, 1u);   // consumed at the end of this item
+        uint32_t tile, q;
+        bm25_item_decode(p, item, tile, q);
+        const uint32_t row0 = tile * BM25_TILE;
+        if (lane < BM25_FLAT_TOK) ws.tab[lane] = cur;
+        ItemTok nx{};
+        if (next < n_items && lane < BM25_FLAT_TOK) nx = flat[size_t(next) * BM25_FLAT_TOK + lane];
+        unsigned long long tau = tau_next;
+        if (next < n_items) { uint32_t tn, qn; bm25_item_decode(p, next, tn, qn); tau_next = __ldcg(p.tau + qn); }
+        __syncwarp();
+
+        const float4 *d0 = nullptr, *d1 = nullptr, *d2 = nullptr, *d3 = nullptr;
+        uint32_t nd = 0, n_list = 0;
+        bool pos = p.k >= 0.f;
+#pragma unroll
+        for (uint32_t j = 0; j < BM25_FLAT_TOK; j++) {
+            const uint32_t n = tab[j].n;
+            if (n == 0) continue;
+            pos = pos && tab[j].w >= 0.f && tab[j].idf >= 0.f;
+            if (tab[j].flags & TD_DENSE) {
+                const float4 *dp = reinterpret_cast<const float4 *>(tab[j].ptr);
+                if (nd == 0) d0 = dp; else if (nd == 1) d1 = dp; else if (nd == 2) d2 = dp; else d3 = dp;
+                nd++;
+            } else n_list++;
+        }
+        const bool any_list = n_list != 0;
+        const bool use_bm = n_list > 1 || okbits != nullptr;
+        uint32_t matched;
+        float lmax, lmin;
+        for (;;) {   // (repeats only when a cold threshold overflowed the candidate buffer)
+            const float tau_f = tau ? key_score(tau) : -INFINITY;
+            matched = 0; lmax = 0.f; lmin = 0.f;
+            if (any_list && (nd || use_bm)) {   // mark the rows of the list tokens
+#pragma unroll 1
+                for (uint32_t j = 0; j < BM25_FLAT_TOK; j++) {
+                    const uint32_t n = tab[j].n;
+                    if (n == 0 || (tab[j].flags & TD_DENSE)) continue;
+                    const uint2 *pp = reinterpret_cast<const uint2 *>(tab[j].ptr);
+                    for (uint32_t pi = lane; pi < n; pi += 32) {
+                        const uint32_t row = __ldg(&pp[pi].x);
+                        if (okbits && !((__ldg(okbits + (row >> 5)) >> (row & 31u)) & 1u)) continue;
+                        const uint32_t l = row - row0, bit = 1u << (l & 31u);
+                        if (nd) atomicOr(&touched[l >> 5], bit);
+                        if (use_bm) atomicOr(&bm[j * W + (l >> 5)], bit);
+                    }
+                }
+                __syncwarp();
+            }
+            switch (nd) {   // rows outside every list: dense tokens only, folded in registers
+                case 0: break;
+                case 1: t3_scan<1, 32>(d0, d1, d2, d3, touched, any_list, pos, row0, lane, tau, tau_f, &ws.cnt, ws.tbuf, BW_CAP, matched, lmax, lmin); break;
+                case 2: t3_scan<2, 32>(d0, d1, d2, d3, touched, any_list, pos, row0, lane, tau, tau_f, &ws.cnt, ws.tbuf, BW_CAP, matched, lmax, lmin); break;
+                case 3: t3_scan<3, 32>(d0, d1, d2, d3, touched, any_list, pos, row0, lane, tau, tau_f, &ws.cnt, ws.tbuf, BW_CAP, matched, lmax, lmin); break;
+                default: t3_scan<4, 32>(d0, d1, d2, d3, touched, any_list, pos, row0, lane, tau, tau_f, &ws.cnt, ws.tbuf, BW_CAP, matched, lmax, lmin); break;
+            }
+            if (any_list) {   // rows of the list tokens: the first list token holding the row folds it
+#pragma unroll 1
+                for (uint32_t j = 0; j < BM25_FLAT_TOK; j++) {
+                    const uint32_t n = tab[j].n;
+                    if (n == 0 || (tab[j].flags & TD_DENSE)) continue;
+                    const uint2 *pp = reinterpret_cast<const uint2 *>(tab[j].ptr);
+                    for (uint32_t pi = lane; pi < n; pi += 32) {
+                        const uint2 rec = __ldg(pp + pi);
+                        const uint32_t l = rec.x - row0, w = l >> 5, bit = 1u << (l & 31u);
+                        if (use_bm) {
+                            if (!(bm[j * W + w] & bit)) continue;          // failed the row check
+                            uint32_t earlier = 0;
+                            for (uint32_t jj = 0; jj < j; jj++) earlier |= bm[jj * W + w];
+                            if (earlier & bit) continue;                   // an earlier list token owns the row
+                        }
+                        const float s = t3_fold(tab, bm, j, rec, l, p.k, kp1);
+                        if (s != 0.f) {
+                            matched++;
+                            lmax = fmaxf(lmax, s);
+                            lmin = fminf(lmin, s);
+                            t3_consider(s, rec.x, tau, tau_f, &ws.cnt, ws.tbuf, BW_CAP);
+                        }
+                    }
+                }
+            }
+            __syncwarp();                                      // candidate pushes and bitmap reads of all lanes are done
+            if (any_list) {
+                if (nd) for (uint32_t i = lane; i < W; i += 32) touched[i] = 0u;
+                if (use_bm) for (uint32_t i = lane; i < BM25_FLAT_TOK * W; i += 32) bm[i] = 0u;
+            }
+            if (ws.cnt <= BW_CAP) break;
+            // overflow: the n_keep-th best of the first BW_CAP arrivals bounds the tile's n_keep-th best from below
+            const unsigned long long kth = warp_keep_top(ws.tbuf, BW_CAP, p.n_keep, lane) - 1ull;   // "> kth" keeps that row itself
+            tau = kth > tau ? kth : tau;
+            if (lane == 0) ws.cnt = 0u;
+            __syncwarp();
+        }
+        matched = __reduce_add_sync(0xffffffffu, matched);
+        for (int o = 16; o > 0; o >>= 1) {
+            lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+            lmin = fminf(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+        }
+        // ---- emit: best <= n_keep of the buffer
+        const size_t slot_base = (size_t(q) * p.n_tiles + tile);
+        uint32_t c = ws.cnt;
+        if (c >= p.n_keep && c > 0) {
+            const unsigned long long kth = warp_keep_top(ws.tbuf, c, p.n_keep, lane);
+            c = p.n_keep;
+            if (lane == 0) atomicMax(p.tau + q, kth);
+        }
+        for (uint32_t i = lane; i < c; i += 32) {
+            const uint64_t key = ws.tbuf[i];
+            p.cand_key[slot_base * p.n_keep + i] = key;
+            p.cand_ft[slot_base * p.n_keep + i] = key_score(key);
+        }
+        __syncwarp();
+        if (lane == 0) {
+            p.cand_cnt[slot_base] = c;
+            p.tile_count[slot_base] = matched;
+            p.tile_max[slot_base] = lmax;
+            p.tile_min[slot_base] = lmin;
+            ws.cnt = 0u;
+        }
+        // the next item's descriptors arrived during this one: pull the head of each of its posting ranges / dense slices
+        // towards L1 so its first dependent loads do not pay the L2 round trip
+        if (lane < BM25_FLAT_TOK && nx.n) {
+            const char *pf = reinterpret_cast<const char *>(nx.ptr);
+            const uint32_t bytes = (nx.flags & TD_DENSE) ? 1024u : min(nx.n * 8u, 1024u);
+            for (uint32_t o = 0; o < bytes; o += 128u) asm volatile("prefetch.global.L1 [%0];" ::"l"(pf + o));
+        }
+        cur = nx;
+        item = next;
+        next = __shfl_sync(0xffffffffu, next2, 0);
+        __syncwarp();
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // Hybrid: the fulltext score of each vector hit's document (token_score.rs:416-419 needs it for the <= limit
 // documents of the vector map), by POINT lookups instead of a pass inside the tile scorer: one warp per
@@ -1078,6 +1601,84 @@ __global__ void __launch_bounds__(256) bm25_point_kernel(const PointParams p) {
         p.v_ft[wid] = present ? score : 0.f;
         p.v_present[wid] = present ? 1 : 0;
     }
+}
+
+// ---------------------------------------------------------------------------------------
+// Warm start of the per-query candidate threshold (plain queries, n_keep <= 32): the tile scorers gate candidates by
+// tau[q], which the first tiles of a query would otherwise have to discover themselves (every matched row of those
+// tiles passes a cold threshold).  One warp per query scores the first 64 documents of the query's RAREST list
+// token exactly (the fold of bm25_tile3_kernel: dense arrays by row, other lists by binary search) — documents that
+// hold the rarest term are where the top of the ranking lives — and publishes (n_keep-th best key) - 1: n_keep real
+// rows reach it, so it is a valid lower bound of the final n_keep-th best and pruning by it cannot change a result.
+// ---------------------------------------------------------------------------------------
+constexpr uint32_t SEED_PER_LANE = 2, SEED_MAX_PER_LANE = 8;
+__global__ void __launch_bounds__(256) bm25_seed_kernel(const Bm25Params p) {
+    const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (q >= p.n_queries) return;
+    const QueryDesc qd = p.queries[q];
+    const uint32_t ntok = qd.token_end - qd.token_begin;
+    if (ntok == 0 || ntok > BM25_FLAT_TOK || p.n_keep > 32) return;
+    const float kp1 = __fadd_rn(p.k, 1.0f);
+    uint32_t best = 0xffffffffu, best_len = 0xffffffffu;
+    for (uint32_t j = 0; j < ntok; j++) {
+        const TokenDesc tk = p.tokens[qd.token_begin + j];
+        if (tk.term_end - tk.term_begin != 1) continue;
+        const TermDesc td = p.terms[tk.term_begin];
+        if (!(td.flags & TD_DENSE) && td.len >= p.n_keep && td.len < best_len) { best = j; best_len = td.len; }
+    }
+    // no list token with n_keep postings (every token hot or very rare): score the first 256 rows of the store instead — a
+    // weaker bound, but enough to stop the first tiles from pushing every matched row
+    const bool fallback = best == 0xffffffffu;                             // (warp-uniform)
+    if (fallback && p.n_rows < 32u * SEED_MAX_PER_LANE) return;
+    const uint32_t per = fallback ? SEED_MAX_PER_LANE : SEED_PER_LANE;
+    const uint2 *pb = fallback ? nullptr : reinterpret_cast<const uint2 *>(p.terms[p.tokens[qd.token_begin + best].term_begin].ptr);
+    unsigned long long keys[SEED_MAX_PER_LANE];
+#pragma unroll
+    for (uint32_t u = 0; u < SEED_MAX_PER_LANE; u++) {
+        keys[u] = 0ull;
+        if (u >= per) continue;
+        const uint32_t pi = lane + 32u * u;
+        uint2 rec = make_uint2(pi, 0u);                                    // fallback: row pi
+        if (!fallback) {
+            if (pi >= best_len) continue;
+            rec = __ldg(pb + pi);
+        }
+        if (p.row_ok_bits && !((__ldg(p.row_ok_bits + (rec.x >> 5)) >> (rec.x & 31u)) & 1u)) continue;
+        float s = 0.f;
+        for (uint32_t i = 0; i < ntok; i++) {                              // token order
+            const TokenDesc tk = p.tokens[qd.token_begin + i];
+            if (tk.term_end - tk.term_begin != 1) continue;
+            const TermDesc td = p.terms[tk.term_begin];
+            float ci;
+            if (td.flags & TD_DENSE) ci = __ldg(reinterpret_cast<const float *>(td.ptr) + rec.x);
+            else {
+                uint32_t pay = rec.y;
+                if (i != best && !posting_find(td, rec.x, &pay)) continue;
+                if (td.flags & TD_PRE) ci = __uint_as_float(pay);
+                else {
+                    const float ntf = __fmul_rn(td.weight, __uint_as_float(pay));
+                    ci = f32_is_normal(ntf) ? bm25_sat(ntf, p.k, kp1, tk.idf) : __int_as_float(0x7fc00000);
+                }
+            }
+            if (ci == ci) s = __fadd_rn(s, ci);
+        }
+        if (s != 0.f && s == s) keys[u] = make_key(s, rec.x);
+    }
+    unsigned long long kth = 0ull;
+    for (uint32_t r = 0; r < p.n_keep; r++) {
+        unsigned long long m = keys[0];
+#pragma unroll
+        for (uint32_t u = 1; u < SEED_MAX_PER_LANE; u++) m = keys[u] > m ? keys[u] : m;
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long om = __shfl_xor_sync(0xffffffffu, m, o);
+            m = om > m ? om : m;
+        }
+        kth = m;
+        if (m == 0ull) break;                                              // fewer than n_keep scored rows: no seed
+#pragma unroll
+        for (uint32_t u = 0; u < SEED_MAX_PER_LANE; u++) if (keys[u] == m) keys[u] = 0ull;   // keys are unique (row index)
+    }
+    if (lane == 0 && kth > 1ull) p.tau[q] = kth - 1ull;                    // "> tau" keeps the kth row itself
 }
 
 }  // namespace oc

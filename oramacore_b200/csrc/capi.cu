@@ -1428,21 +1428,76 @@ static int launch_tile2_t(oc_ctx *c, const Bm25Params &bp, size_t smem, cudaStre
     return OC_OK;
 }
 // multi == false (every token resolves to <= 1 term): the posting-centred persistent kernel; else the slot-scan kernel
-static int launch_tile(oc_ctx *c, const Bm25Params &bp, uint32_t grid, bool multi, bool thr, bool omc, cudaStream_t st,
+static int launch_tile(oc_ctx *c, const Bm25Params &bp_in, uint32_t grid, bool multi, bool thr, bool omc, cudaStream_t st,
                        uint32_t max_tokens, unsigned int *counter /* zeroed by the caller */) {
     const char *env = getenv("OC_BM25_TILE2");
     if (!multi && !(env && env[0] == '0')) {
         // one level of descriptors per (tile, query) item, prefetched by the kernel during the previous item
         const ItemTok *flat = nullptr;
         const char *fenv = getenv("OC_BM25_FLAT");
-        if (max_tokens <= BM25_FLAT_TOK && !(fenv && fenv[0] == '0')) {
+        const char *t3e = getenv("OC_BM25_TILE3");
+        const bool can_flat = max_tokens <= BM25_FLAT_TOK && !(fenv && fenv[0] == '0');
+        const bool use3 = can_flat && !thr && !omc && !bp_in.matched_bits && !(t3e && t3e[0] == '0');
+        Bm25Params bp = bp_in;
+        const char *oenv = getenv("OC_BM25_ORDER");
+        if (!use3 || (oenv && oenv[0] == '0')) bp.perm = nullptr;          // natural item order for the accumulator kernels
+        if (can_flat) {
             const uint64_t n_it = uint64_t(bp.n_tiles) * bp.n_queries * BM25_FLAT_TOK;
             OCTRY(c->flat_desc.ensure(n_it * sizeof(ItemTok)));
-            bm25_flatten_kernel<<<(unsigned)((n_it + 255) / 256), 256, 0, st>>>(bp.terms, bp.tokens, bp.queries, bp.seg, bp.n_tiles,
-                                                                                bp.n_queries, c->flat_desc.as<ItemTok>());
+            bm25_flatten_kernel<<<(unsigned)((n_it + 255) / 256), 256, 0, st>>>(bp, c->flat_desc.as<ItemTok>());
             launched(c);
             CU(cudaGetLastError());
             flat = c->flat_desc.as<ItemTok>();
+        }
+        if (use3) {
+            // plain queries: the register-folded scorer (no accumulator arrays)
+            const size_t smem3 = bm25_tile3_smem_bytes(bp.cap);
+            if (smem_cfg_needed(c->device, (const void *)bm25_tile3_kernel, smem3))
+                CU(cudaFuncSetAttribute(bm25_tile3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+            static std::mutex occ3_mu;
+            static std::map<std::pair<int, size_t>, int> occ3;
+            int per_sm = 1;
+            {
+                std::lock_guard<std::mutex> g(occ3_mu);
+                auto it = occ3.find(std::make_pair(c->device, smem3));
+                if (it == occ3.end()) {
+                    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bm25_tile3_kernel, BM25_THREADS, smem3));
+                    occ3[std::make_pair(c->device, smem3)] = per_sm;
+                } else per_sm = it->second;
+            }
+            const uint64_t items = uint64_t(bp.n_tiles) * bp.n_queries;
+            const uint32_t g3 = (uint32_t)std::min<uint64_t>(items, uint64_t(std::max(per_sm, 1)) * c->prop.multiProcessorCount);
+            const char *seed_env = getenv("OC_BM25_SEED");
+            if (bp.n_keep <= 32 && bp.n_tiles > 1 && !(seed_env && seed_env[0] == '0')) {   // warm start of the candidate thresholds
+                bm25_seed_kernel<<<(bp.n_queries * 32 + 255) / 256, 256, 0, st>>>(bp);
+                launched(c);
+            }
+            const char *wenv = getenv("OC_BM25_WARP");
+            if (bp.n_keep <= 32 && !(wenv && wenv[0] == '0')) {   // a warp per item: no block barriers
+                const size_t smemw = size_t(BW_WARPS) * sizeof(WarpScratch);
+                if (smem_cfg_needed(c->device, (const void *)bm25_warp_kernel, smemw))
+                    CU(cudaFuncSetAttribute(bm25_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemw));
+                static std::mutex occw_mu;
+                static std::map<int, int> occw;
+                int pw = 1;
+                {
+                    std::lock_guard<std::mutex> g(occw_mu);
+                    auto it = occw.find(c->device);
+                    if (it == occw.end()) {
+                        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pw, bm25_warp_kernel, BW_WARPS * 32, smemw));
+                        occw[c->device] = pw;
+                    } else pw = it->second;
+                }
+                const uint32_t gw = (uint32_t)std::min<uint64_t>((items + BW_WARPS - 1) / BW_WARPS, uint64_t(std::max(pw, 1)) * c->prop.multiProcessorCount);
+                bm25_warp_kernel<<<gw, BW_WARPS * 32, smemw, st>>>(bp, flat, counter);
+                launched(c);
+                CU(cudaGetLastError());
+                return OC_OK;
+            }
+            bm25_tile3_kernel<<<g3, BM25_THREADS, smem3, st>>>(bp, flat, counter);
+            launched(c);
+            CU(cudaGetLastError());
+            return OC_OK;
         }
         const size_t smem = bm25_tile2_smem_bytes(thr, omc, bp.cap);
         const int sel = (thr ? 2 : 0) | (omc ? 1 : 0);
@@ -1453,6 +1508,8 @@ static int launch_tile(oc_ctx *c, const Bm25Params &bp, uint32_t grid, bool mult
             default: return launch_tile2_t<true, true>(c, bp, smem, st, flat, counter);
         }
     }
+    Bm25Params bp = bp_in;
+    bp.perm = nullptr;
     const size_t smem = bm25_smem_bytes(multi, thr, omc, bp.cap);
     const int sel = (multi ? 4 : 0) | (thr ? 2 : 0) | (omc ? 1 : 0);
     switch (sel) {
@@ -1744,6 +1801,24 @@ static int search_impl(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_para
     const size_t o_omcm = n_omc ? pk.add(p->omc_mult, size_t(n_omc) * 4) : 0;
     const size_t o_omcr = omc_tile ? pk.add(omc_rows.data(), omc_rows.size() * 4) : 0;
     const size_t o_omcrm = omc_tile ? pk.add(omc_row_mult.data(), omc_row_mult.size() * 4) : 0;
+    // item order of the register-folded scorers (Bm25Params::perm): queries by their number of dense tokens, descending
+    std::vector<uint32_t> q_perm;
+    uint32_t cls_nq[BM25_CLASSES] = {0, 0, 0, 0, 0};
+    if (has_ft && !any_multi && max_tokens <= BM25_FLAT_TOK) {
+        std::vector<uint8_t> nd_q(B, 0);
+        for (uint32_t q = 0; q < B; q++) {
+            uint32_t nd = 0;
+            for (uint32_t t = queries[q].token_begin; t < queries[q].token_end; t++)
+                if (tokens[t].term_end > tokens[t].term_begin && (terms[tokens[t].term_begin].flags & TD_DENSE) && terms[tokens[t].term_begin].len) nd++;
+            nd_q[q] = (uint8_t)std::min<uint32_t>(nd, BM25_CLASSES - 1);
+            cls_nq[BM25_CLASSES - 1 - nd_q[q]]++;                       // class 0 = most dense tokens
+        }
+        q_perm.resize(B);
+        uint32_t at[BM25_CLASSES], acc = 0;
+        for (uint32_t g = 0; g < BM25_CLASSES; g++) { at[g] = acc; acc += cls_nq[g]; }
+        for (uint32_t q = 0; q < B; q++) q_perm[at[BM25_CLASSES - 1 - nd_q[q]]++] = q;
+    }
+    const size_t o_perm = q_perm.empty() ? 0 : pk.add(q_perm.data(), q_perm.size() * 4);
     // hybrid: the descriptors, the shared-contribution precompute, the filter bitmap and the (term, tile) plan do
     // not depend on the vector results: they run on the side stream while the main stream sweeps the matrix
     // (OC_SIDE_STREAM=0 disables it: the step gets ~2.5 % longer, the sweep itself ~4 % shorter — A/B switch)
@@ -1866,6 +1941,14 @@ static int search_impl(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_para
         bp.cand_cnt = c->cand_cnt.as<uint32_t>(); bp.tile_count = c->tile_cnt.as<uint32_t>();
         bp.tile_max = c->tile_max.as<float>(); bp.tile_min = c->tile_min.as<float>();
         bp.tile_first = 0;
+        if (!q_perm.empty()) {
+            bp.perm = reinterpret_cast<const uint32_t *>(din + o_perm);
+            uint32_t off = 0, q0 = 0;
+            for (uint32_t g = 0; g < BM25_CLASSES; g++) {
+                bp.cls_off[g] = off; bp.cls_nq[g] = cls_nq[g]; bp.cls_q0[g] = q0;
+                off += cls_nq[g] * n_tiles; q0 += cls_nq[g];
+            }
+        }
         if (fj) {   // facets: the tile kernels also emit the bitmap of matched rows (every (query, tile) item writes its 256 words)
             OCTRY(c->mbits.ensure(size_t(B) * std::max<uint32_t>(n_tiles, 1) * (BM25_TILE / 32) * 4));
             bp.matched_bits = c->mbits.as<uint32_t>();

@@ -13,7 +13,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-fil
 # the sweep is the 2nd launch of emb_gemm_cvt_kernel in a step (the 1st is the one-tile threshold pass): skip 3 steps + 1
 ncu --set full --clock-control none --import-source on -k regex:emb_gemm_cvt_kernel -s 7 -c 1 -f -o gpurun_out/prof_gemm_h1 \
     python bench.py --workload h1 --steps 3 --warmup 3 --no-cpu-baseline --no-extra > /dev/null 2>&1
-OC_SIDE_STREAM=0 ncu --set full --clock-control none --import-source on -k regex:bm25_tile2_kernel -s 4 -c 1 -f -o gpurun_out/prof_bm25_h1 \
+OC_SIDE_STREAM=0 ncu --set full --clock-control none --import-source on -k regex:bm25_warp_kernel -s 4 -c 1 -f -o gpurun_out/prof_bm25_h1 \
     python bench.py --workload h1 --steps 3 --warmup 3 --no-cpu-baseline --no-extra > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:emb_gemm_merge_kernel -s 4 -c 1 -f -o gpurun_out/prof_merge_h1 \
     python bench.py --workload h1 --steps 3 --warmup 3 --no-cpu-baseline --no-extra > /dev/null 2>&1
