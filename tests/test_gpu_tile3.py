@@ -73,7 +73,7 @@ def test_tile3_matches_tile2_and_oracle(gpu_ctx, orc, n_docs, vocab, ntok, limit
         h3b = ob.search(gpu_ctx, None, strs, "fulltext", texts=texts, limit=limit, offset=offset)
     with _env(OC_BM25_TILE3="1", OC_BM25_WARP="0", OC_BM25_SEED="0"):
         h3bn = ob.search(gpu_ctx, None, strs, "fulltext", texts=texts, limit=limit, offset=offset)
-    with _env(OC_BM25_TILE3="1", OC_BM25_ORDER="0"):        # natural item order instead of heaviest-class-first
+    with _env(OC_BM25_TILE3="1", OC_BM25_ORDER="1"):        # dense-token queries first, list-only queries last
         h3o = ob.search(gpu_ctx, None, strs, "fulltext", texts=texts, limit=limit, offset=offset)
     with _env(OC_BM25_TILE3="0"):
         h2 = ob.search(gpu_ctx, None, strs, "fulltext", texts=texts, limit=limit, offset=offset)
