@@ -73,7 +73,7 @@ if __name__ == "__main__":
     for n in ("h1", "v1"):
         launches(n)
     traffic = {}
-    for rep, label, wl in (("prof_gemm_h1.ncu-rep", "ncu_emb_gemm_h1", "h1"), ("prof_bm25_h1.ncu-rep", "ncu_bm25_tile_h1", None),
+    for rep, label, wl in (("prof_gemm_h1.ncu-rep", "ncu_emb_gemm_h1", "h1"), ("prof_bm25_h1.ncu-rep", "ncu_bm25_warp_h1", None),
                            ("prof_merge_h1.ncu-rep", "ncu_emb_merge_h1", None), ("prof_scan_v1.ncu-rep", "ncu_emb_scan_v1", "v1")):
         d = full(rep, label)
         if d and wl:
