@@ -1429,7 +1429,7 @@ static int launch_tile2_t(oc_ctx *c, const Bm25Params &bp, size_t smem, cudaStre
 }
 // multi == false (every token resolves to <= 1 term): the posting-centred persistent kernel; else the slot-scan kernel
 static int launch_tile(oc_ctx *c, const Bm25Params &bp_in, uint32_t grid, bool multi, bool thr, bool omc, cudaStream_t st,
-                       uint32_t max_tokens, unsigned int *counter /* zeroed by the caller */) {
+                       uint32_t max_tokens, unsigned int *counter /* zeroed by the caller */, bool counted_df) {
     const char *env = getenv("OC_BM25_TILE2");
     if (!multi && !(env && env[0] == '0')) {
         // one level of descriptors per (tile, query) item, prefetched by the kernel during the previous item
@@ -1437,7 +1437,10 @@ static int launch_tile(oc_ctx *c, const Bm25Params &bp_in, uint32_t grid, bool m
         const char *fenv = getenv("OC_BM25_FLAT");
         const char *t3e = getenv("OC_BM25_TILE3");
         const bool can_flat = max_tokens <= BM25_FLAT_TOK && !(fenv && fenv[0] == '0');
-        const bool use3 = can_flat && !thr && !omc && !bp_in.matched_bits && !(t3e && t3e[0] == '0');
+        // counted_df (filter / tombstones / OC_SHARD_COUNT_DF): no token has a host-known idf, so nothing is shared or dense
+        // and every hot term arrives as a long posting list — the accumulator kernel walks those at ~10 instructions per
+        // posting, the register-folded scorers would fold each posting's row separately
+        const bool use3 = can_flat && !thr && !omc && !counted_df && !bp_in.matched_bits && !(t3e && t3e[0] == '0');
         Bm25Params bp = bp_in;
         // OC_BM25_ORDER=1: deal the items of the dense-token queries first and the list-only queries last (a lighter
         // ragged end of the persistent schedule); measured 1-2 % SLOWER on both bench shapes (the tile-major order of
@@ -1962,7 +1965,7 @@ static int search_impl(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_para
             OCTRY(c->mbits.ensure(size_t(B) * std::max<uint32_t>(n_tiles, 1) * (BM25_TILE / 32) * 4));
             bp.matched_bits = c->mbits.as<uint32_t>();
         }
-        if (n_tiles) OCTRY(launch_tile(c, bp, n_tiles * B, any_multi, thr, omc_tile, ps, max_tokens, tile_counter));
+        if (n_tiles) OCTRY(launch_tile(c, bp, n_tiles * B, any_multi, thr, omc_tile, ps, max_tokens, tile_counter, need_df));
         CU(cudaEventRecord(c->ev[EV_BM1], ps));
         c->timing.bm25_postings = postings_walked;
         if (side) {   // join: the lookups and the fusion need the vector hits (main stream) and the tiles (side stream)
@@ -2083,7 +2086,7 @@ static int search_impl(oc_ctx *c, oc_emb *emb, oc_str *str, const oc_search_para
             CU(cudaMemcpyAsync(min_hint_dev, mins, size_t(B) * 4, cudaMemcpyHostToDevice, c->stream));
             CU(cudaMemsetAsync(c->tau.p, 0, size_t(B) * 8, c->stream));
             CU(cudaMemsetAsync(tile_counter, 0, 8, c->stream));
-            OCTRY(launch_tile(c, bp, n_tiles * B, any_multi, thr, omc_tile, c->stream, max_tokens, tile_counter));
+            OCTRY(launch_tile(c, bp, n_tiles * B, any_multi, thr, omc_tile, c->stream, max_tokens, tile_counter, need_df));
             fuse_topk_kernel<<<B, 256, fuse_smem, c->stream>>>(fp);
             launched(c);
             CU(cudaMemcpyAsync(c->h_out.p, dout, out_bytes, cudaMemcpyDeviceToHost, c->stream));
