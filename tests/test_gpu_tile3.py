@@ -2,8 +2,8 @@
 item) against the oracle and against K3b
 (bm25_tile2_kernel) on the same inputs — bit-identical scores, same ids, same counts — over the shapes that steer
 its code paths: items with only list tokens, only dense tokens, both (ownership bitmap + binary search in the other
-lists), rows present in several list tokens, filters / tombstones (row check in the posting walk, baked into the dense
-arrays), cold thresholds overflowing the candidate buffer (the redo with a tighter threshold), the warm-start seed,
+lists), rows present in several list tokens, filters / tombstones (batches with device-counted df are routed to K3b by
+default: the comparison then pins that routing), cold thresholds overflowing the candidate buffer (the redo with a tighter threshold), the warm-start seed,
 n_keep > 32 (bitonic keep) and 4-token queries.  The environment switches are read per launch."""
 import os
 
